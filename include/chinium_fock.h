@@ -1,0 +1,144 @@
+/* chinium_fock.h -- C ABI of the B200-native direct-SCF J/K (Fock) build engine.
+ *
+ * Drop-in boundary for ONE path of FreemanTheMaverick/Chinium: the four-centre
+ * two-electron-integral J/K contraction behind `class Int4C2E`
+ * (reference src/Integral/Int4C2E.h:10-50), called once per SCF iteration by
+ * src/HartreeFockKohnSham (e.g. Restricted/SP.cpp:47, Unrestricted/SP.cpp:58,
+ * Universal.cpp:38).  The reference has no FFI; a maintainer binds these entry
+ * points from the C++ adaptor `chinium_b200/cpp/Int4C2E_b200.hpp`, which keeps the
+ * reference's method names.
+ *
+ * Conventions (all from the reference):
+ *   - matrices are column-major FP64 nbf x nbf, ld = nbf (Eigen::MatrixXd,
+ *     src/Macro/Abbreviation.h:4); density inputs are symmetric.
+ *   - shell `type`: 0 = S, +1 = Cartesian P (x,y,z), -l = pure shell of angular
+ *     momentum l in the order m = -l..+l of Racah-normalised real solid harmonics
+ *     (src/Integral/Macro.h:5-8, src/Grid/AO/Pure*.hpp).
+ *   - `coefs_normalized` are MwfnShell.NormalizedCoefficients
+ *     (src/Integral/Normalization.cpp:11-18); coordinates in bohr.
+ *   - J_ij = sum_kl (ij|kl) (2 Dd + Da + Db)_kl ;  KX_ik = exx * sum_jl (ij|kl) DX_jl
+ *     i.e. exactly what Gunified returns (src/Integral/Int4C2E.cpp:601-671).
+ *
+ * There is NO CPU fallback: every entry point that computes returns
+ * CF_ERR_NO_DEVICE when no sm_100 GPU is usable.
+ */
+#ifndef CHINIUM_FOCK_H
+#define CHINIUM_FOCK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CF_OK 0
+#define CF_ERR_NO_DEVICE 1      /* no CUDA device / not sm_100              */
+#define CF_ERR_BAD_ARGUMENT 2   /* null pointer, nbf mismatch, bad type      */
+#define CF_ERR_UNSUPPORTED 3    /* angular momentum above CF_MAX_L, ...      */
+#define CF_ERR_CUDA 4           /* a CUDA runtime call failed                */
+#define CF_ERR_RANGE 5          /* fixed-point accumulator range exceeded    */
+#define CF_ERR_STATE 6          /* calls out of order (reference asserts: Int4C2E.cpp:514,538,555) */
+
+#define CF_MAX_L 4              /* highest shell angular momentum the device kernels accept (g) */
+
+/* Flat basis description; replaces __Make_Basis_Set__ (src/Integral/Macro.h:1-25).
+ * All pointers are HOST pointers, borrowed only for the duration of cf_create. */
+typedef struct cf_basis {
+    int nshell;
+    const int* type;              /* [nshell] 0, +1, -1, -2, -3, ...                       */
+    const int* nprim;             /* [nshell]                                              */
+    const int* prim_offset;       /* [nshell] offset of the shell's first primitive        */
+    const double* exps;           /* [sum nprim]                                           */
+    const double* coefs_normalized; /* [sum nprim]                                         */
+    const double* center_xyz;     /* [3*nshell] bohr                                       */
+    const int* shell2atom;        /* [nshell] (may be NULL; kept for the derivative rows)  */
+} cf_basis;
+
+/* Options; zero-initialise then override.  Replaces the hard-coded
+ * Int4C2E(mwfn, exx, threshold) arguments (src/HartreeFockKohnSham/SelfConsistentField.cpp:47). */
+typedef struct cf_options {
+    double threshold;   /* Cauchy-Schwarz threshold on sqrt((ab|ab)(cd|cd)) as in Int4C2E.cpp:108-113.
+                           <= 0 (the reference passes -1): no Schwarz screening; only shell pairs whose
+                           largest primitive overlap prefactor is < pair_cutoff are dropped.          */
+    double pair_cutoff; /* 0 -> default 1e-18 (drops nothing that can change J/K at the 1e-12 level)  */
+    int device;         /* CUDA device ordinal; -1 -> current device                                  */
+    int rank;           /* this handle computes partition `rank` of `world_size` (static, cost-       */
+    int world_size;     /*  balanced split of the quartet work; 0/0 or 0/1 = everything)              */
+    int verbose;        /* >0: print the reference's "... Done in %f s" lines (Int4C2E.cpp:500-587)   */
+    int reserved[8];
+} cf_options;
+
+typedef struct cf_handle cf_handle;
+
+/* Counters mirrored from the reference's screening printout (Int4C2E.cpp:516-531) plus work metrics. */
+typedef struct cf_stats {
+    int nshell, nbf, ncart;            /* ncart: Cartesian working dimension on the device            */
+    int64_t shell_pairs_total;         /* nshell(nshell+1)/2                                         */
+    int64_t shell_pairs_kept;
+    int64_t canonical_quartets;        /* surviving canonical shell quartets, whole job             */
+    int64_t canonical_quartets_local;  /* ... in this handle's partition                            */
+    int64_t unique_integrals;          /* the reference's RepulsionLength for the surviving quartets */
+    int64_t primitive_quartets;
+    double  flops_alg_jk[4];           /* F_alg (SURVEY 8d model) for nK = 0,1,2,3, this partition    */
+    int     n_launches_last;           /* kernels launched by the last cf_build_* call               */
+    double  ms_device_last;            /* CUDA-event time of the last build (all kernels)            */
+    double  ms_eri_last;               /* ... of the ERI/digestion kernels only                      */
+    double  fixedpoint_scale_log2[2];  /* log2 of the J and K accumulator scales of the last build   */
+} cf_stats;
+
+/* cf_create: pair build + Schwarz bounds + class sort + task lists, all on the device.
+ * Replaces getRepulsionDiag / getRepulsionLength / getRepulsionIndices / getThreadPointers /
+ * CalculateIntegrals(0) (SelfConsistentField.cpp:49-53). Returns NULL on failure; the reason is
+ * available from cf_last_error(NULL). */
+cf_handle* cf_create(const cf_basis* basis, const cf_options* opts);
+void cf_destroy(cf_handle* h);
+const char* cf_last_error(const cf_handle* h);
+int cf_get_stats(const cf_handle* h, cf_stats* out);
+int cf_nbf(const cf_handle* h);
+
+/* Schwarz diagonal (ab|ab) for all basis-function pairs, nbf x nbf col-major
+ * (the reference's Diag1212, Int4C2E.cpp:19-77). */
+int cf_get_repulsion_diag(cf_handle* h, double* diag1212);
+
+/* The hot call; replaces Int4C2E::ContractInts(Dd,Da,Db,nthreads,output) (Int4C2E.cpp:673-683).
+ * HOST pointers. Dd/Da/Db: nullable (absent = the reference's 0x0 matrix). J is always written;
+ * KX is written iff DX is given (zeros when exx <= 0, Int4C2E.cpp:638), and may be NULL otherwise. */
+int cf_build_jk(cf_handle* h, int nbf,
+                const double* Dd, const double* Da, const double* Db, double exx,
+                double* J, double* Kd, double* Ka, double* Kb);
+
+/* Same with DEVICE pointers on the handle's device (steady-state SCF keeps D/J/K resident);
+ * work is enqueued on `stream` (a cudaStream_t; NULL = default stream) and not synchronised. */
+int cf_build_jk_device(cf_handle* h, int nbf,
+                       const double* Dd, const double* Da, const double* Db, double exx,
+                       double* J, double* Kd, double* Ka, double* Kb, void* stream);
+
+/* Multi-GPU building blocks (one process per GPU).  The raw accumulators are 64-bit
+ * fixed point, so the cross-rank sum is an INTEGER all-reduce (ncclInt64/ncclSum) and the result is
+ * bit-identical for any world_size.
+ *   cf_accumulate_device : this rank's partition -> acc (device, int64[cf_acc_len(h,nk)]), zeroed first
+ *   (caller all-reduces acc)
+ *   cf_finalize_device   : acc -> J, K (device, col-major nbf x nbf)                                */
+size_t cf_acc_len(const cf_handle* h, int nk);
+int cf_accumulate_device(cf_handle* h, int nbf,
+                         const double* Dd, const double* Da, const double* Db, double exx,
+                         int64_t* acc, void* stream);
+int cf_finalize_device(cf_handle* h, int nbf, const int64_t* acc, double exx,
+                       int has_d, int has_a, int has_b,
+                       double* J, double* Kd, double* Ka, double* Kb, void* stream);
+
+/* Multi-density build; replaces Int4C2E::ContractInts(std::vector<EigenMatrix>&, ...) /
+ * GhfMultiple (Int4C2E.cpp:685-745): G_k = J[2 D_k] - exx * K[D_k].  HOST pointers,
+ * Ds/Gs are nmat consecutive nbf x nbf col-major matrices. */
+int cf_build_g_multi(cf_handle* h, int nbf, int nmat, const double* Ds, double exx, double* Gs);
+
+/* Library/device facts for logs and benchmarks. */
+int cf_device_info(int device, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor);
+/* Measured FP64 FMA peak of the device (a register-resident DFMA loop, CUDA events), TFLOP/s. */
+int cf_measure_fp64_peak(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHINIUM_FOCK_H */

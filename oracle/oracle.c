@@ -1,0 +1,809 @@
+/* oracle.c -- CPU ORACLE for the J/K path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library; the product (chinium_b200/csrc) never does.
+ *
+ * What it restates, and from where (paths relative to /root/reference):
+ *   - enumeration, uniqueness predicate, degeneracy weights, digestion, symmetrisation,
+ *     EXX scaling: literal restatement of src/Integral/Int4C2E.cpp:19-302 and :589-671
+ *     (functions ref_*, same loop nests and index types).
+ *   - the ERI VALUES: the reference gets them from libint2 (linked as -lint2, makefile:66;
+ *     NOT vendored, NO version pinned anywhere in the repo).  libint2 cannot be built here, so
+ *     the values come from an independent textbook McMurchie-Davidson scheme (Hermite
+ *     expansion coefficients E, Hermite Coulomb integrals R from the Boys function), in
+ *     libint2's conventions for shell order / pure ordering / normalisation
+ *     (src/Integral/Macro.h:1-25, src/Grid/AO/Pure*.hpp, src/Integral/Normalization.cpp).
+ *   - PARITY PIN: weak external pin only -- the RHF/cc-pVDZ energy of CH3ClF- recorded in
+ *     tools/sn2/sn2.cnm.log:204 (reproduced by tests/test_oracle.py through this oracle to
+ *     < 1e-7 Eh), plus first-principles checks (Boys vs mpmath, permutational symmetry,
+ *     diag(S)=1, brute-force einsum).  The device kernels use a DIFFERENT algorithm (Rys
+ *     quadrature), so oracle == device agreement is a two-route check.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "../include/chinium_fock.h"
+
+#define LMAX 6
+#define NCART(l) (((l) + 1) * ((l) + 2) / 2)
+#define NCMAX NCART(LMAX)
+#define L4MAX (4 * LMAX)
+#define PI 3.14159265358979323846264338327950288
+
+/* ---------------------------------------------------------------- Boys function F_m(T), m=0..mmax */
+static void boys(int mmax, double T, double* F) {
+    if (T < 1e-15) {
+        for (int m = 0; m <= mmax; m++) F[m] = 1.0 / (2 * m + 1);
+        return;
+    }
+    double eT = exp(-T);
+    if (T < 50.0 + mmax) {
+        /* all-positive series for the top order, then downward recursion (both stable) */
+        double term = 1.0 / (2 * mmax + 1), sum = term;
+        for (int k = 1; k < 400; k++) {
+            term *= 2.0 * T / (2 * mmax + 2 * k + 1);
+            sum += term;
+            if (term < 1e-18 * sum) break;
+        }
+        F[mmax] = eT * sum;
+        for (int m = mmax; m > 0; m--) F[m - 1] = (2.0 * T * F[m] + eT) / (2 * m - 1);
+    } else {
+        F[0] = 0.5 * sqrt(PI / T) * erf(sqrt(T));
+        for (int m = 0; m < mmax; m++) F[m + 1] = ((2 * m + 1) * F[m] - eT) / (2.0 * T);
+    }
+}
+void oracle_boys(int mmax, double T, double* F) { boys(mmax, T, F); }
+
+/* ---------------------------------------------------------------- shells */
+static inline int sh_l(const cf_basis* b, int s) { return abs(b->type[s]); }
+static inline int sh_nfun(const cf_basis* b, int s) {
+    int t = b->type[s], l = abs(t);
+    return t < 0 ? 2 * l + 1 : NCART(l);
+}
+int oracle_nbf(const cf_basis* b) {
+    int n = 0;
+    for (int s = 0; s < b->nshell; s++) n += sh_nfun(b, s);
+    return n;
+}
+static void shell2bf(const cf_basis* b, int* s2bf) {
+    int n = 0;
+    for (int s = 0; s < b->nshell; s++) { s2bf[s] = n; n += sh_nfun(b, s); }
+}
+
+/* Cartesian component order: lx descending, then ly descending (p: x,y,z). */
+static void cart_components(int l, int (*c)[3]) {
+    int n = 0;
+    for (int lx = l; lx >= 0; lx--)
+        for (int ly = l - lx; ly >= 0; ly--) { c[n][0] = lx; c[n][1] = ly; c[n][2] = l - lx - ly; n++; }
+}
+static int cart_index(int l, int lx, int ly) { /* position of (lx,ly,l-lx-ly) in the order above */
+    int n = 0;
+    for (int x = l; x > lx; x--) n += l - x + 1;
+    return n + (l - lx - ly);
+}
+
+static double fact(int n) { double r = 1; for (int i = 2; i <= n; i++) r *= i; return r; }
+static double binom(int n, int k) { if (k < 0 || k > n) return 0; return fact(n) / (fact(k) * fact(n - k)); }
+
+/* Racah-normalised real solid harmonics as monomial coefficients, m = -l..l
+ * (the polynomials of src/Grid/AO/PureD.hpp .. PureI.hpp).  C is [2l+1][NCART(l)]. */
+static void pure_matrix(int l, double* C) {
+    int nc = NCART(l);
+    memset(C, 0, sizeof(double) * (2 * l + 1) * nc);
+    for (int m = -l; m <= l; m++) {
+        int am = abs(m);
+        double N = sqrt(2.0 * fact(l + am) * fact(l - am) / (m == 0 ? 2.0 : 1.0)) / (pow(2.0, am) * fact(l));
+        for (int t = 0; t <= (l - am) / 2; t++)
+            for (int u = 0; u <= t; u++) {
+                /* 2v runs over even (m>=0) or odd (m<0) integers <= |m| */
+                for (int v2 = (m >= 0 ? 0 : 1); v2 <= am; v2 += 2) {
+                    int k = (m >= 0) ? v2 / 2 : (v2 - 1) / 2;
+                    double c = ((t + k) % 2 ? -1.0 : 1.0) * pow(0.25, t) * binom(l, t) * binom(l - t, am + t) *
+                               binom(t, u) * binom(am, v2);
+                    int ex = 2 * t + am - 2 * u - v2, ey = 2 * u + v2;
+                    if (ex < 0) continue;
+                    C[(m + l) * nc + cart_index(l, ex, ey)] += N * c;
+                }
+            }
+    }
+}
+/* transformation of one shell: rows = functions of the shell as the reference orders them */
+static int shell_transform(int type, double* C) {
+    int l = abs(type), nc = NCART(l);
+    if (type >= 0) { /* S, Cartesian P (x,y,z): identity (Cartesian l>=2 is never produced by the reference's reader) */
+        memset(C, 0, sizeof(double) * nc * nc);
+        for (int i = 0; i < nc; i++) C[i * nc + i] = 1.0;
+        return nc;
+    }
+    pure_matrix(l, C);
+    return 2 * l + 1;
+}
+void oracle_pure_matrix(int l, double* C) { pure_matrix(l, C); }
+
+/* ---------------------------------------------------------------- Hermite expansion coefficients
+ * E[i][j][t], 0<=i<=la, 0<=j<=lb, 0<=t<=i+j, for one Cartesian direction; E^{00}_0 = 1
+ * (the Gaussian-product prefactor is carried separately). */
+#define EDIM (LMAX + 1)
+typedef struct { double e[EDIM][EDIM][2 * LMAX + 1]; } ecoef;
+static void hermite_E(int la, int lb, double p, double PA, double PB, ecoef* E) {
+    memset(E, 0, sizeof(*E));
+    double h = 0.5 / p;
+    E->e[0][0][0] = 1.0;
+    for (int i = 0; i <= la; i++) {
+        if (i > 0)
+            for (int t = 0; t <= i; t++) {
+                double v = PA * E->e[i - 1][0][t];
+                if (t > 0) v += h * E->e[i - 1][0][t - 1];
+                if (t + 1 <= i - 1) v += (t + 1) * E->e[i - 1][0][t + 1];
+                E->e[i][0][t] = v;
+            }
+        for (int j = 1; j <= lb; j++)
+            for (int t = 0; t <= i + j; t++) {
+                double v = PB * E->e[i][j - 1][t];
+                if (t > 0) v += h * E->e[i][j - 1][t - 1];
+                if (t + 1 <= i + j - 1) v += (t + 1) * E->e[i][j - 1][t + 1];
+                E->e[i][j][t] = v;
+            }
+    }
+}
+
+/* Hermite Coulomb integrals R_{tuv} = R^0_{tuv}(alpha, PQ), t+u+v <= L. out[t][u][v], dim L+1 each */
+static void hermite_R(int L, double alpha, const double* PQ, double* out /* (L+1)^3 */) {
+    double F[L4MAX + 1];
+    double T = alpha * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
+    boys(L, T, F);
+    int d = L + 1;
+    /* work[n][t][u][v] built downward in n; keep two layers via full array for clarity */
+    size_t sz = (size_t)d * d * d;
+    double* w = (double*)calloc(sz * (L + 1), sizeof(double));
+#define RW(n, t, u, v) w[(size_t)(n) * sz + ((size_t)(t) * d + (u)) * d + (v)]
+    double f = 1.0;
+    for (int n = 0; n <= L; n++) { RW(n, 0, 0, 0) = f * F[n]; f *= -2.0 * alpha; }
+    for (int n = L - 1; n >= 0; n--) {
+        int M = L - n; /* t+u+v <= M at level n */
+        for (int t = 0; t <= M; t++)
+            for (int u = 0; t + u <= M; u++)
+                for (int v = 0; t + u + v <= M; v++) {
+                    if (t + u + v == 0) continue;
+                    double r;
+                    if (t > 0) {
+                        r = PQ[0] * RW(n + 1, t - 1, u, v);
+                        if (t > 1) r += (t - 1) * RW(n + 1, t - 2, u, v);
+                    } else if (u > 0) {
+                        r = PQ[1] * RW(n + 1, t, u - 1, v);
+                        if (u > 1) r += (u - 1) * RW(n + 1, t, u - 2, v);
+                    } else {
+                        r = PQ[2] * RW(n + 1, t, u, v - 1);
+                        if (v > 1) r += (v - 1) * RW(n + 1, t, u, v - 2);
+                    }
+                    RW(n, t, u, v) = r;
+                }
+    }
+    memcpy(out, w, sz * sizeof(double));
+#undef RW
+    free(w);
+}
+
+/* ---------------------------------------------------------------- primitive-pair data of a shell pair */
+typedef struct {
+    int la, lb, npp;
+    double AB[3];
+    double* p;      /* [npp] */
+    double* P;      /* [npp][3] */
+    double* K;      /* [npp] ca*cb*exp(-mu AB^2) */
+    ecoef* E;       /* [npp][3] */
+} pairdata;
+
+static void make_pair(const cf_basis* b, int sa, int sb, pairdata* pd) {
+    int la = sh_l(b, sa), lb = sh_l(b, sb);
+    int na = b->nprim[sa], nb = b->nprim[sb];
+    const double* A = b->center_xyz + 3 * sa;
+    const double* B = b->center_xyz + 3 * sb;
+    pd->la = la; pd->lb = lb; pd->npp = na * nb;
+    double r2 = 0;
+    for (int x = 0; x < 3; x++) { pd->AB[x] = A[x] - B[x]; r2 += pd->AB[x] * pd->AB[x]; }
+    pd->p = (double*)malloc(sizeof(double) * pd->npp);
+    pd->P = (double*)malloc(sizeof(double) * 3 * pd->npp);
+    pd->K = (double*)malloc(sizeof(double) * pd->npp);
+    pd->E = (ecoef*)malloc(sizeof(ecoef) * 3 * pd->npp);
+    int n = 0;
+    for (int i = 0; i < na; i++)
+        for (int j = 0; j < nb; j++, n++) {
+            double a = b->exps[b->prim_offset[sa] + i], bb = b->exps[b->prim_offset[sb] + j];
+            double ca = b->coefs_normalized[b->prim_offset[sa] + i], cb = b->coefs_normalized[b->prim_offset[sb] + j];
+            double p = a + bb;
+            pd->p[n] = p;
+            pd->K[n] = ca * cb * exp(-a * bb / p * r2);
+            for (int x = 0; x < 3; x++) {
+                double Px = (a * A[x] + bb * B[x]) / p;
+                pd->P[3 * n + x] = Px;
+                hermite_E(la, lb, p, Px - A[x], Px - B[x], &pd->E[3 * n + x]);
+            }
+        }
+}
+static void free_pair(pairdata* pd) { free(pd->p); free(pd->P); free(pd->K); free(pd->E); }
+
+/* Cartesian (ab|cd) of a shell quartet from two pairdata; out[na_c][nb_c][nc_c][nd_c] (accumulated from 0) */
+static void eri_cart(const pairdata* ab, const pairdata* cd, double* out) {
+    int la = ab->la, lb = ab->lb, lc = cd->la, ld = cd->lb;
+    int nca = NCART(la), ncb = NCART(lb), ncc = NCART(lc), ncd = NCART(ld);
+    int Lab = la + lb, Lcd = lc + ld, L = Lab + Lcd, d = L + 1;
+    int ca[NCMAX][3], cb[NCMAX][3], cc[NCMAX][3], cdd[NCMAX][3];
+    cart_components(la, ca); cart_components(lb, cb); cart_components(lc, cc); cart_components(ld, cdd);
+    size_t ntot = (size_t)nca * ncb * ncc * ncd;
+    memset(out, 0, sizeof(double) * ntot);
+    double* R = (double*)malloc(sizeof(double) * d * d * d);
+    int dab = Lab + 1;
+    double* G = (double*)malloc(sizeof(double) * dab * dab * dab);
+    for (int i = 0; i < ab->npp; i++)
+        for (int j = 0; j < cd->npp; j++) {
+            double p = ab->p[i], q = cd->p[j];
+            double alpha = p * q / (p + q);
+            double PQ[3] = {ab->P[3 * i] - cd->P[3 * j], ab->P[3 * i + 1] - cd->P[3 * j + 1], ab->P[3 * i + 2] - cd->P[3 * j + 2]};
+            double pref = 2.0 * pow(PI, 2.5) / (p * q * sqrt(p + q)) * ab->K[i] * cd->K[j];
+            hermite_R(L, alpha, PQ, R);
+            const ecoef* Eab = &ab->E[3 * i];
+            const ecoef* Ecd = &cd->E[3 * j];
+            for (int ic = 0; ic < ncc; ic++)
+                for (int id = 0; id < ncd; id++) {
+                    int mx = cc[ic][0] + cdd[id][0], my = cc[ic][1] + cdd[id][1], mz = cc[ic][2] + cdd[id][2];
+                    const double* ex = Ecd[0].e[cc[ic][0]][cdd[id][0]];
+                    const double* ey = Ecd[1].e[cc[ic][1]][cdd[id][1]];
+                    const double* ez = Ecd[2].e[cc[ic][2]][cdd[id][2]];
+                    /* G[t][u][v] = sum_{tau,nu,phi} (-1)^(tau+nu+phi) Ecd R[t+tau][u+nu][v+phi] */
+                    for (int t = 0; t <= Lab; t++)
+                        for (int u = 0; t + u <= Lab; u++)
+                            for (int v = 0; t + u + v <= Lab; v++) {
+                                double s = 0;
+                                for (int a = 0; a <= mx; a++)
+                                    for (int bq = 0; bq <= my; bq++) {
+                                        double exy = ex[a] * ey[bq];
+                                        for (int c = 0; c <= mz; c++) {
+                                            double sg = ((a + bq + c) & 1) ? -1.0 : 1.0;
+                                            s += sg * exy * ez[c] * R[((t + a) * d + (u + bq)) * d + (v + c)];
+                                        }
+                                    }
+                                G[(t * dab + u) * dab + v] = s;
+                            }
+                    for (int ia = 0; ia < nca; ia++)
+                        for (int ib = 0; ib < ncb; ib++) {
+                            int nx = ca[ia][0] + cb[ib][0], ny = ca[ia][1] + cb[ib][1], nz = ca[ia][2] + cb[ib][2];
+                            const double* fx = Eab[0].e[ca[ia][0]][cb[ib][0]];
+                            const double* fy = Eab[1].e[ca[ia][1]][cb[ib][1]];
+                            const double* fz = Eab[2].e[ca[ia][2]][cb[ib][2]];
+                            double s = 0;
+                            for (int t = 0; t <= nx; t++)
+                                for (int u = 0; u <= ny; u++) {
+                                    double fxy = fx[t] * fy[u];
+                                    for (int v = 0; v <= nz; v++) s += fxy * fz[v] * G[(t * dab + u) * dab + v];
+                                }
+                            out[(((size_t)ia * ncb + ib) * ncc + ic) * ncd + id] += pref * s;
+                        }
+                }
+        }
+    free(R); free(G);
+}
+
+/* transform index `which` (0..3) of a 4-index tensor with dims n[4] by matrix C [nnew][n[which]] */
+static void transform_index(const double* in, double* out, const int* n, int which, const double* C, int nnew) {
+    size_t outer = 1, inner = 1;
+    for (int i = 0; i < which; i++) outer *= n[i];
+    for (int i = which + 1; i < 4; i++) inner *= n[i];
+    int nold = n[which];
+    for (size_t o = 0; o < outer; o++)
+        for (int m = 0; m < nnew; m++)
+            for (size_t k = 0; k < inner; k++) {
+                double s = 0;
+                for (int c = 0; c < nold; c++) s += C[m * nold + c] * in[(o * nold + c) * inner + k];
+                out[(o * nnew + m) * inner + k] = s;
+            }
+}
+
+/* (s1 s2|s3 s4) in the reference's function order; buf is the dense [n1][n2][n3][n4] tensor,
+ * f4 fastest -- the layout the reference reads at src/Integral/Int4C2E.cpp:276-283. */
+typedef struct { pairdata* pd; int nshell; } paircache;
+
+static void eri_shell_quartet_pd(const cf_basis* b, const pairdata* ab, const pairdata* cd,
+                                 int s1, int s2, int s3, int s4, double* buf) {
+    int sh[4] = {s1, s2, s3, s4};
+    int n[4];
+    for (int i = 0; i < 4; i++) n[i] = NCART(sh_l(b, sh[i]));
+    size_t ntot = (size_t)n[0] * n[1] * n[2] * n[3];
+    double* t1 = (double*)malloc(sizeof(double) * ntot);
+    double* t2 = (double*)malloc(sizeof(double) * ntot);
+    eri_cart(ab, cd, t1);
+    double C[(2 * LMAX + 1) * NCMAX];
+    for (int i = 0; i < 4; i++) {
+        int nnew = shell_transform(b->type[sh[i]], C);
+        transform_index(t1, t2, n, i, C, nnew);
+        n[i] = nnew;
+        double* tmp = t1; t1 = t2; t2 = tmp;
+    }
+    memcpy(buf, t1, sizeof(double) * (size_t)n[0] * n[1] * n[2] * n[3]);
+    free(t1); free(t2);
+}
+void oracle_eri_shell_quartet(const cf_basis* b, int s1, int s2, int s3, int s4, double* buf) {
+    pairdata ab, cd;
+    make_pair(b, s1, s2, &ab); make_pair(b, s3, s4, &cd);
+    eri_shell_quartet_pd(b, &ab, &cd, s1, s2, s3, s4, buf);
+    free_pair(&ab); free_pair(&cd);
+}
+
+/* all shell pairs s1>=s2 (plus s1<s2 on demand is never needed: every loop below has s2<=s1, s4<=s3 or
+ * builds the pair explicitly) */
+static pairdata* all_pairs(const cf_basis* b) {
+    int ns = b->nshell;
+    pairdata* pd = (pairdata*)malloc(sizeof(pairdata) * (size_t)ns * ns);
+    for (int i = 0; i < ns; i++)
+        for (int j = 0; j < ns; j++) make_pair(b, i, j, &pd[(size_t)i * ns + j]);
+    return pd;
+}
+static void free_all_pairs(const cf_basis* b, pairdata* pd) {
+    size_t n = (size_t)b->nshell * b->nshell;
+    for (size_t i = 0; i < n; i++) free_pair(&pd[i]);
+    free(pd);
+}
+
+/* ================================================================ one-electron integrals (harness) */
+static void one_electron(const cf_basis* b, int natom, const double* Z, const double* xyz,
+                         double* S, double* T, double* V) {
+    int nbf = oracle_nbf(b), ns = b->nshell;
+    int* s2bf = (int*)malloc(sizeof(int) * ns);
+    shell2bf(b, s2bf);
+    for (int sa = 0; sa < ns; sa++)
+        for (int sb = 0; sb < ns; sb++) {
+            int la = sh_l(b, sa), lb = sh_l(b, sb);
+            int nca = NCART(la), ncb = NCART(lb);
+            int ca[NCMAX][3], cb[NCMAX][3];
+            cart_components(la, ca); cart_components(lb, cb);
+            double sc[NCMAX * NCMAX] = {0}, tc[NCMAX * NCMAX] = {0}, vc[NCMAX * NCMAX] = {0};
+            const double* A = b->center_xyz + 3 * sa;
+            const double* B = b->center_xyz + 3 * sb;
+            double r2 = 0;
+            for (int x = 0; x < 3; x++) r2 += (A[x] - B[x]) * (A[x] - B[x]);
+            int Lab = la + lb, d = Lab + 1;
+            double* R = (double*)malloc(sizeof(double) * d * d * d);
+            for (int i = 0; i < b->nprim[sa]; i++)
+                for (int j = 0; j < b->nprim[sb]; j++) {
+                    double a = b->exps[b->prim_offset[sa] + i], bb = b->exps[b->prim_offset[sb] + j];
+                    double cc = b->coefs_normalized[b->prim_offset[sa] + i] * b->coefs_normalized[b->prim_offset[sb] + j];
+                    double p = a + bb, K = cc * exp(-a * bb / p * r2);
+                    double P[3];
+                    ecoef E[3]; /* need j up to lb+2 for kinetic: build with lb+2 (<= LMAX+2 guard) */
+                    double e2[3][EDIM][EDIM + 2]; /* overlap 1D s[i][j], j up to lb+2 */
+                    for (int x = 0; x < 3; x++) {
+                        P[x] = (a * A[x] + bb * B[x]) / p;
+                        hermite_E(la, lb, p, P[x] - A[x], P[x] - B[x], &E[x]);
+                        /* 1D overlaps S_ij = E^{ij}_0 sqrt(pi/p) via Obara-Saika-like recursion up to j = lb+2 */
+                        double PA = P[x] - A[x], PB = P[x] - B[x], h = 0.5 / p;
+                        for (int ii = 0; ii <= la; ii++)
+                            for (int jj = 0; jj <= lb + 2; jj++) {
+                                double v;
+                                if (ii == 0 && jj == 0) v = sqrt(PI / p);
+                                else if (jj == 0) v = PA * e2[x][ii - 1][0] + (ii > 1 ? (ii - 1) * h * e2[x][ii - 2][0] : 0);
+                                else v = PB * e2[x][ii][jj - 1] + (ii > 0 ? ii * h * e2[x][ii - 1][jj - 1] : 0) +
+                                         (jj > 1 ? (jj - 1) * h * e2[x][ii][jj - 2] : 0);
+                                e2[x][ii][jj] = v;
+                            }
+                    }
+                    for (int ia = 0; ia < nca; ia++)
+                        for (int ib = 0; ib < ncb; ib++) {
+                            double s1d[3], k1d[3];
+                            for (int x = 0; x < 3; x++) {
+                                int ii = ca[ia][x], jj = cb[ib][x];
+                                s1d[x] = e2[x][ii][jj];
+                                k1d[x] = -2.0 * bb * bb * e2[x][ii][jj + 2] + bb * (2 * jj + 1) * e2[x][ii][jj] -
+                                         (jj > 1 ? 0.5 * jj * (jj - 1) * e2[x][ii][jj - 2] : 0);
+                            }
+                            sc[ia * ncb + ib] += K * s1d[0] * s1d[1] * s1d[2];
+                            tc[ia * ncb + ib] += K * (k1d[0] * s1d[1] * s1d[2] + s1d[0] * k1d[1] * s1d[2] + s1d[0] * s1d[1] * k1d[2]);
+                        }
+                    for (int c = 0; c < natom; c++) {
+                        double PC[3] = {P[0] - xyz[3 * c], P[1] - xyz[3 * c + 1], P[2] - xyz[3 * c + 2]};
+                        hermite_R(Lab, p, PC, R);
+                        for (int ia = 0; ia < nca; ia++)
+                            for (int ib = 0; ib < ncb; ib++) {
+                                double s = 0;
+                                for (int t = 0; t <= ca[ia][0] + cb[ib][0]; t++)
+                                    for (int u = 0; u <= ca[ia][1] + cb[ib][1]; u++)
+                                        for (int v = 0; v <= ca[ia][2] + cb[ib][2]; v++)
+                                            s += E[0].e[ca[ia][0]][cb[ib][0]][t] * E[1].e[ca[ia][1]][cb[ib][1]][u] *
+                                                 E[2].e[ca[ia][2]][cb[ib][2]][v] * R[(t * d + u) * d + v];
+                                vc[ia * ncb + ib] += -Z[c] * 2.0 * PI / p * K * s;
+                            }
+                    }
+                }
+            free(R);
+            /* cart -> reference function order */
+            double Ca[(2 * LMAX + 1) * NCMAX], Cb[(2 * LMAX + 1) * NCMAX];
+            int na = shell_transform(b->type[sa], Ca), nb = shell_transform(b->type[sb], Cb);
+            double* mats[3] = {sc, tc, vc};
+            double* outs[3] = {S, T, V};
+            for (int m = 0; m < 3; m++)
+                for (int i = 0; i < na; i++)
+                    for (int j = 0; j < nb; j++) {
+                        double s = 0;
+                        for (int x = 0; x < nca; x++)
+                            for (int y = 0; y < ncb; y++) s += Ca[i * nca + x] * Cb[j * ncb + y] * mats[m][x * ncb + y];
+                        outs[m][(size_t)(s2bf[sb] + j) * nbf + (s2bf[sa] + i)] = s; /* col-major (symmetric anyway) */
+                    }
+        }
+    free(s2bf);
+}
+void oracle_one_electron(const cf_basis* b, int natom, const double* Z, const double* xyz, double* S, double* T, double* V) {
+    one_electron(b, natom, Z, xyz, S, T, V);
+}
+
+/* ================================================================ literal restatement of the reference path
+ * Index variables are `short` where the reference uses short int (Int4C2E.h:19-29). Matrices col-major. */
+#define M(A, i, j) (A)[(size_t)(j) * nbf + (i)]
+
+/* ::getRepulsionDiag, Int4C2E.cpp:19-77 (only Diag1212 is ever consumed: :515, :544) */
+void ref_getRepulsionDiag(const cf_basis* b, double* Diag1212) {
+    int nbf = oracle_nbf(b), ns = b->nshell;
+    int* s2bf = (int*)malloc(sizeof(int) * ns);
+    shell2bf(b, s2bf);
+    memset(Diag1212, 0, sizeof(double) * (size_t)nbf * nbf);
+    for (short s1 = 0; s1 < (short)ns; s1++) {
+        short bf1_first = s2bf[s1], n1 = sh_nfun(b, s1);
+        for (short s2 = 0; s2 <= s1; s2++) {
+            short bf2_first = s2bf[s2], n2 = sh_nfun(b, s2);
+            double* buf = (double*)malloc(sizeof(double) * (size_t)n1 * n2 * n1 * n2);
+            oracle_eri_shell_quartet(b, s1, s2, s1, s2, buf);
+            int f1234 = 0;
+            for (short f1 = 0; f1 < n1; f1++) {
+                short bf1 = f1 + bf1_first;
+                for (short f2 = 0; f2 < n2; f2++) {
+                    short bf2 = f2 + bf2_first;
+                    for (short f3 = 0; f3 < n1; f3++) {
+                        short bf3 = f3 + bf1_first;
+                        for (short f4 = 0; f4 < n2; f4++, f1234++) {
+                            short bf4 = f4 + bf2_first;
+                            if (bf1 == bf3 && bf2 == bf4 && bf1 >= bf2) {
+                                M(Diag1212, bf1, bf2) = buf[f1234];
+                                M(Diag1212, bf2, bf1) = buf[f1234];
+                            }
+                        }
+                    }
+                }
+            }
+            free(buf);
+        }
+    }
+    free(s2bf);
+}
+
+/* ::getRepulsionLength (:79-128) and ::getRepulsionIndices (:130-182) in one routine: when shells != NULL the
+ * (s1,s2,s3,s4) are recorded with the `>=` test of :166, the counts use the `>` test of :111. */
+void ref_getRepulsionLengthIndices(const cf_basis* b, const double* diag, double threshold,
+                                   long* n2integrals_out, long* nshellquartets_out,
+                                   short* shellis, short* shelljs, short* shellks, short* shellls) {
+    int nbf = oracle_nbf(b), ns = b->nshell;
+    int* s2bf = (int*)malloc(sizeof(int) * ns);
+    shell2bf(b, s2bf);
+    long n2integrals = 0, nshellquartets = 0, nrec = 0;
+    for (short s1 = 0; s1 < (short)ns; s1++) {
+        short bf1_first = s2bf[s1], n1 = sh_nfun(b, s1);
+        for (short s2 = 0; s2 <= s1; s2++) {
+            short bf2_first = s2bf[s2], n2 = sh_nfun(b, s2);
+            for (short s3 = 0; s3 <= s1; s3++) {
+                short bf3_first = s2bf[s3], n3 = sh_nfun(b, s3);
+                for (short s4 = 0; s4 <= (s2 > s3 ? s2 : s3); s4++) {
+                    short bf4_first = s2bf[s4], n4 = sh_nfun(b, s4);
+                    int discard = 1, discard_ge = 1, uniquebf = 0;
+                    for (short f1 = 0; f1 < n1; f1++) {
+                        short bf1 = f1 + bf1_first;
+                        for (short f2 = 0; f2 < n2; f2++) {
+                            short bf2 = f2 + bf2_first;
+                            for (short f3 = 0; f3 < n3; f3++) {
+                                short bf3 = f3 + bf3_first;
+                                for (short f4 = 0; f4 < n4; f4++) {
+                                    short bf4 = f4 + bf4_first;
+                                    if (bf2 <= bf1 && bf3 <= bf1 && bf4 <= ((bf1 == bf3) ? bf2 : bf3)) {
+                                        uniquebf++;
+                                        double upperbound = sqrt(fabs(M(diag, bf1, bf2) * M(diag, bf3, bf4)));
+                                        if (upperbound > threshold) discard = 0;
+                                        if (upperbound >= threshold) discard_ge = 0;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (!discard) { nshellquartets++; n2integrals += uniquebf; }
+                    if (!discard_ge && shellis) {
+                        shellis[nrec] = s1; shelljs[nrec] = s2; shellks[nrec] = s3; shellls[nrec] = s4;
+                        nrec++;
+                    }
+                }
+            }
+        }
+    }
+    *n2integrals_out = n2integrals; *nshellquartets_out = nshellquartets;
+    free(s2bf);
+}
+
+/* getRepulsion0 (:233-302): evaluate, keep unique function quartets, store value * abcd_deg.
+ * The equal-count thread split of ::getThreadPointers (:184-231) only decides which thread writes which
+ * slice of the SAME arrays, so a serial fill in list order produces the identical arrays. */
+long ref_getRepulsion0(const cf_basis* b, long nsq, const short* shellis, const short* shelljs,
+                       const short* shellks, const short* shellls,
+                       short* basisis, short* basisjs, short* basisks, short* basisls, double* repulsionints) {
+    int ns = b->nshell;
+    int* s2bf = (int*)malloc(sizeof(int) * ns);
+    shell2bf(b, s2bf);
+    pairdata* pd = all_pairs(b);
+    /* first pass: offsets per quartet so the fill can run in parallel like the reference's (:244) */
+    long* head = (long*)malloc(sizeof(long) * (nsq + 1));
+    head[0] = 0;
+    for (long q = 0; q < nsq; q++) {
+        short s1 = shellis[q], s2 = shelljs[q], s3 = shellks[q], s4 = shellls[q];
+        long cnt = 0;
+        for (short f1 = 0; f1 < sh_nfun(b, s1); f1++) for (short f2 = 0; f2 < sh_nfun(b, s2); f2++)
+            for (short f3 = 0; f3 < sh_nfun(b, s3); f3++) for (short f4 = 0; f4 < sh_nfun(b, s4); f4++) {
+                short bf1 = s2bf[s1] + f1, bf2 = s2bf[s2] + f2, bf3 = s2bf[s3] + f3, bf4 = s2bf[s4] + f4;
+                if (bf2 <= bf1 && bf3 <= bf1 && bf4 <= ((bf1 == bf3) ? bf2 : bf3)) cnt++;
+            }
+        head[q + 1] = head[q] + cnt;
+    }
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long q = 0; q < nsq; q++) {
+        short s1 = shellis[q], s2 = shelljs[q], s3 = shellks[q], s4 = shellls[q];
+        short bf1_first = s2bf[s1], bf2_first = s2bf[s2], bf3_first = s2bf[s3], bf4_first = s2bf[s4];
+        short n1 = sh_nfun(b, s1), n2 = sh_nfun(b, s2), n3 = sh_nfun(b, s3), n4 = sh_nfun(b, s4);
+        double* buf = (double*)malloc(sizeof(double) * (size_t)n1 * n2 * n3 * n4);
+        eri_shell_quartet_pd(b, &pd[(size_t)s1 * ns + s2], &pd[(size_t)s3 * ns + s4], s1, s2, s3, s4, buf);
+        long w = head[q];
+        int f1234 = 0;
+        for (short f1 = 0; f1 < n1; f1++) {
+            short bf1 = bf1_first + f1;
+            for (short f2 = 0; f2 < n2; f2++) {
+                short bf2 = bf2_first + f2;
+                char ab_deg = (bf1 == bf2) ? 1 : 2;
+                for (short f3 = 0; f3 < n3; f3++) {
+                    short bf3 = bf3_first + f3;
+                    for (short f4 = 0; f4 < n4; f4++, f1234++) {
+                        short bf4 = bf4_first + f4;
+                        char cd_deg = (bf3 == bf4) ? 1 : 2;
+                        char ab_cd_deg = (bf1 == bf3) ? (bf2 == bf4 ? 1 : 2) : 2;
+                        char abcd_deg = ab_deg * cd_deg * ab_cd_deg;
+                        if (bf2 <= bf1 && bf3 <= bf1 && bf4 <= ((bf1 == bf3) ? bf2 : bf3)) {
+                            basisis[w] = bf1; basisjs[w] = bf2; basisks[w] = bf3; basisls[w] = bf4;
+                            repulsionints[w] = buf[f1234] * abcd_deg;
+                            w++;
+                        }
+                    }
+                }
+            }
+        }
+        free(buf);
+    }
+    long total = head[nsq];
+    free(head); free_all_pairs(b, pd); free(s2bf);
+    return total;
+}
+
+/* Gunified (:601-671). Dd/Da/Db may be NULL (= the reference's 0x0 matrices). Outputs nbf x nbf each. */
+void ref_Gunified(const short* is, const short* js, const short* ks, const short* ls, const double* ints, long length,
+                  int nbf, const double* Dd, const double* Da, const double* Db, double kscale, int nthreads,
+                  double* J, double* Kd, double* Ka, double* Kb) {
+    size_t n2 = (size_t)nbf * nbf;
+    double* Dtot = (double*)calloc(n2, sizeof(double));
+    for (size_t i = 0; i < n2; i++) Dtot[i] = (Dd ? 2 * Dd[i] : 0) + (Da ? Da[i] : 0) + (Db ? Db[i] : 0);
+    double* raw = (double*)calloc(4 * n2 * nthreads, sizeof(double)); /* thread-private rawJ,rawKd,rawKa,rawKb */
+    long fewer = length / nthreads;
+    int nfewers = (int)(nthreads - length + fewer * nthreads);
+#pragma omp parallel for num_threads(nthreads) schedule(static, 1)
+    for (int ith = 0; ith < nthreads; ith++) {
+        long head = 0;
+        for (int t = 0; t < ith; t++) head += (t < nfewers) ? fewer : fewer + 1;
+        long nints = (ith < nfewers) ? fewer : fewer + 1;
+        double* rawJ = raw + (size_t)ith * 4 * n2;
+        double* rawKd = rawJ + n2; double* rawKa = rawKd + n2; double* rawKb = rawKa + n2;
+        for (long q = head; q < head + nints; q++) {
+            short i = is[q], j = js[q], k = ks[q], l = ls[q];
+            double repulsion = ints[q];
+            M(rawJ, i, j) += M(Dtot, k, l) * repulsion;
+            M(rawJ, k, l) += M(Dtot, i, j) * repulsion;
+            if (kscale > 0.) {
+                if (Dd) { M(rawKd, i, k) += M(Dd, j, l) * repulsion; M(rawKd, j, l) += M(Dd, i, k) * repulsion;
+                          M(rawKd, i, l) += M(Dd, j, k) * repulsion; M(rawKd, j, k) += M(Dd, i, l) * repulsion; }
+                if (Da) { M(rawKa, i, k) += M(Da, j, l) * repulsion; M(rawKa, j, l) += M(Da, i, k) * repulsion;
+                          M(rawKa, i, l) += M(Da, j, k) * repulsion; M(rawKa, j, k) += M(Da, i, l) * repulsion; }
+                if (Db) { M(rawKb, i, k) += M(Db, j, l) * repulsion; M(rawKb, j, l) += M(Db, i, k) * repulsion;
+                          M(rawKb, i, l) += M(Db, j, k) * repulsion; M(rawKb, j, k) += M(Db, i, l) * repulsion; }
+            }
+        }
+    }
+    for (int t = 1; t < nthreads; t++)
+        for (size_t i = 0; i < 4 * n2; i++) raw[i] += raw[(size_t)t * 4 * n2 + i];
+    double* outs[4] = {J, Kd, Ka, Kb};
+    double sc[4] = {0.25, 0.125 * kscale, 0.125 * kscale, 0.125 * kscale};
+    for (int m = 0; m < 4; m++) {
+        if (!outs[m]) continue;
+        const double* r = raw + m * n2;
+        for (int i = 0; i < nbf; i++)
+            for (int j = 0; j < nbf; j++) M(outs[m], i, j) = sc[m] * (M(r, i, j) + M(r, j, i));
+    }
+    free(raw); free(Dtot);
+}
+
+/* ================================================================ direct build over canonical shell quartets
+ * (B2 of BASELINE.md): same ERI values, integrals digested on the fly with shell-level degeneracy
+ * weights; mathematically identical to the stored path.  stride/offset select a 1/stride sample of the
+ * bra pairs for bounded timing runs (results are then partial).  counts: [0] canonical quartets visited,
+ * [1] primitive quartets. */
+void oracle_direct_jk(const cf_basis* b, int nbf, const double* Dd, const double* Da, const double* Db, double kscale,
+                      double* J, double* Kd, double* Ka, double* Kb, int nthreads, int stride, int offset, long* counts) {
+    int ns = b->nshell;
+    int* s2bf = (int*)malloc(sizeof(int) * ns);
+    shell2bf(b, s2bf);
+    size_t n2 = (size_t)nbf * nbf;
+    double* Dtot = (double*)calloc(n2, sizeof(double));
+    for (size_t i = 0; i < n2; i++) Dtot[i] = (Dd ? 2 * Dd[i] : 0) + (Da ? Da[i] : 0) + (Db ? Db[i] : 0);
+    pairdata* pd = all_pairs(b);
+    if (nthreads < 1) nthreads = 1;
+    double* raw = (double*)calloc(4 * n2 * nthreads, sizeof(double));
+    const double* DX[3] = {Dd, Da, Db};
+    long npairs = (long)ns * (ns + 1) / 2;
+    long nq = 0, npq = 0;
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1) reduction(+ : nq, npq)
+    for (long ip = npairs - 1; ip >= 0; ip--) {
+        if (stride > 1 && (ip % stride) != offset) continue;
+        int s1 = (int)((sqrt(8.0 * ip + 1) - 1) / 2);
+        while ((long)(s1 + 1) * (s1 + 2) / 2 <= ip) s1++;
+        while ((long)s1 * (s1 + 1) / 2 > ip) s1--;
+        int s2 = (int)(ip - (long)s1 * (s1 + 1) / 2);
+#ifdef _OPENMP
+        int ith = omp_get_thread_num();
+#else
+        int ith = 0;
+#endif
+        double* rawJ = raw + (size_t)ith * 4 * n2;
+        int n1 = sh_nfun(b, s1), n2f = sh_nfun(b, s2);
+        double* buf = (double*)malloc(sizeof(double) * (size_t)n1 * n2f * (2 * LMAX + 1) * (2 * LMAX + 1) * 4);
+        for (int s3 = 0; s3 <= s1; s3++)
+            for (int s4 = 0; s4 <= (s3 == s1 ? s2 : s3); s4++) {
+                int n3 = sh_nfun(b, s3), n4 = sh_nfun(b, s4);
+                const pairdata* ab = &pd[(size_t)s1 * ns + s2];
+                const pairdata* cd = &pd[(size_t)s3 * ns + s4];
+                eri_shell_quartet_pd(b, ab, cd, s1, s2, s3, s4, buf);
+                nq++; npq += (long)ab->npp * cd->npp;
+                double w = (s1 == s2 ? 1.0 : 2.0) * (s3 == s4 ? 1.0 : 2.0) * ((s1 == s3 && s2 == s4) ? 1.0 : 2.0);
+                int f = 0;
+                for (int f1 = 0; f1 < n1; f1++) for (int f2 = 0; f2 < n2f; f2++)
+                    for (int f3 = 0; f3 < n3; f3++) for (int f4 = 0; f4 < n4; f4++, f++) {
+                        int i = s2bf[s1] + f1, j = s2bf[s2] + f2, k = s2bf[s3] + f3, l = s2bf[s4] + f4;
+                        double v = buf[f] * w;
+                        M(rawJ, i, j) += M(Dtot, k, l) * v;
+                        M(rawJ, k, l) += M(Dtot, i, j) * v;
+                        if (kscale > 0.)
+                            for (int x = 0; x < 3; x++) {
+                                if (!DX[x]) continue;
+                                double* rK = rawJ + (x + 1) * n2;
+                                const double* D = DX[x];
+                                M(rK, i, k) += M(D, j, l) * v; M(rK, j, l) += M(D, i, k) * v;
+                                M(rK, i, l) += M(D, j, k) * v; M(rK, j, k) += M(D, i, l) * v;
+                            }
+                    }
+            }
+        free(buf);
+    }
+    for (int t = 1; t < nthreads; t++)
+        for (size_t i = 0; i < 4 * n2; i++) raw[i] += raw[(size_t)t * 4 * n2 + i];
+    double* outs[4] = {J, Kd, Ka, Kb};
+    double sc[4] = {0.25, 0.125 * kscale, 0.125 * kscale, 0.125 * kscale};
+    for (int m = 0; m < 4; m++) {
+        if (!outs[m]) continue;
+        const double* r = raw + m * n2;
+        for (int i = 0; i < nbf; i++)
+            for (int j = 0; j < nbf; j++) M(outs[m], i, j) = sc[m] * (M(r, i, j) + M(r, j, i));
+    }
+    if (counts) { counts[0] = nq; counts[1] = npq; }
+    free(raw); free(Dtot); free_all_pairs(b, pd); free(s2bf);
+}
+
+/* Exact J and K blocks for ONE shell pair (sa,sb) of a large system (sampled parity at full size):
+ *   Jblk[i][j] = sum_kl (ij|kl) Dtot_kl      i in sa, j in sb     (row-major na x nb)
+ *   Kblk[i][k] = sum_jl (ij|kl) D_jl         i in sa, k in sb     (row-major na x nb), unscaled by exx
+ * brute force over all shells, no symmetry. */
+void oracle_jk_block(const cf_basis* b, int nbf, const double* Dtot, const double* D, int sa, int sb,
+                     double* Jblk, double* Kblk, int nthreads) {
+    int ns = b->nshell;
+    int* s2bf = (int*)malloc(sizeof(int) * ns);
+    shell2bf(b, s2bf);
+    int na = sh_nfun(b, sa), nb = sh_nfun(b, sb);
+    memset(Jblk, 0, sizeof(double) * na * nb);
+    memset(Kblk, 0, sizeof(double) * na * nb);
+    if (nthreads < 1) nthreads = 1;
+    double* part = (double*)calloc((size_t)2 * na * nb * nthreads, sizeof(double));
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
+    for (int s3 = 0; s3 < ns; s3++) {
+#ifdef _OPENMP
+        int ith = omp_get_thread_num();
+#else
+        int ith = 0;
+#endif
+        double* pj = part + (size_t)ith * 2 * na * nb;
+        double* pk = pj + na * nb;
+        double* buf = (double*)malloc(sizeof(double) * (2 * LMAX + 1) * (2 * LMAX + 1) * (2 * LMAX + 1) * (2 * LMAX + 1));
+        for (int s4 = 0; s4 < ns; s4++) {
+            int n3 = sh_nfun(b, s3), n4 = sh_nfun(b, s4);
+            /* J: (sa sb | s3 s4) */
+            oracle_eri_shell_quartet(b, sa, sb, s3, s4, buf);
+            for (int i = 0; i < na; i++) for (int j = 0; j < nb; j++)
+                for (int k = 0; k < n3; k++) for (int l = 0; l < n4; l++)
+                    pj[i * nb + j] += buf[((i * nb + j) * n3 + k) * n4 + l] * M(Dtot, s2bf[s3] + k, s2bf[s4] + l);
+            /* K: (sa s3 | sb s4) D_{s3,s4} */
+            if (D) {
+                oracle_eri_shell_quartet(b, sa, s3, sb, s4, buf);
+                for (int i = 0; i < na; i++) for (int j = 0; j < n3; j++)
+                    for (int k = 0; k < nb; k++) for (int l = 0; l < n4; l++)
+                        pk[i * nb + k] += buf[((i * n3 + j) * nb + k) * n4 + l] * M(D, s2bf[s3] + j, s2bf[s4] + l);
+            }
+        }
+        free(buf);
+    }
+    for (int t = 0; t < nthreads; t++)
+        for (int i = 0; i < na * nb; i++) { Jblk[i] += part[(size_t)t * 2 * na * nb + i]; Kblk[i] += part[(size_t)t * 2 * na * nb + na * nb + i]; }
+    free(part); free(s2bf);
+}
+
+/* The whole reference path in one call (setup :49-53 of SelfConsistentField.cpp + ContractInts).
+ * counts: [0] RepulsionLength, [1] ShellQuartetLength. Returns 0. */
+int ref_full_path(const cf_basis* b, double threshold, double exx, int nthreads,
+                  const double* Dd, const double* Da, const double* Db,
+                  double* J, double* Kd, double* Ka, double* Kb, long* counts) {
+    int nbf = oracle_nbf(b);
+    double* diag = (double*)malloc(sizeof(double) * (size_t)nbf * nbf);
+    ref_getRepulsionDiag(b, diag);
+    long nint, nsq;
+    ref_getRepulsionLengthIndices(b, diag, threshold, &nint, &nsq, NULL, NULL, NULL, NULL);
+    short* sh = (short*)malloc(sizeof(short) * 4 * (nsq + 1));
+    long dummy1, dummy2;
+    ref_getRepulsionLengthIndices(b, diag, threshold, &dummy1, &dummy2, sh, sh + nsq, sh + 2 * nsq, sh + 3 * nsq);
+    short* bf = (short*)malloc(sizeof(short) * 4 * (nint + 1));
+    double* ints = (double*)calloc(nint + 1, sizeof(double));
+    ref_getRepulsion0(b, nsq, sh, sh + nsq, sh + 2 * nsq, sh + 3 * nsq, bf, bf + nint, bf + 2 * nint, bf + 3 * nint, ints);
+    ref_Gunified(bf, bf + nint, bf + 2 * nint, bf + 3 * nint, ints, nint, nbf, Dd, Da, Db, exx, nthreads, J, Kd, Ka, Kb);
+    if (counts) { counts[0] = nint; counts[1] = nsq; }
+    free(diag); free(sh); free(bf); free(ints);
+    return 0;
+}
+
+/* Stored-integral handle for timing B1 (the reference's real per-iteration cost): build once, contract many. */
+typedef struct { long nint; short* bf; double* ints; int nbf; } ref_store;
+ref_store* ref_store_build(const cf_basis* b, double threshold) {
+    ref_store* st = (ref_store*)calloc(1, sizeof(ref_store));
+    int nbf = oracle_nbf(b);
+    double* diag = (double*)malloc(sizeof(double) * (size_t)nbf * nbf);
+    ref_getRepulsionDiag(b, diag);
+    long nint, nsq, d1, d2;
+    ref_getRepulsionLengthIndices(b, diag, threshold, &nint, &nsq, NULL, NULL, NULL, NULL);
+    short* sh = (short*)malloc(sizeof(short) * 4 * (nsq + 1));
+    ref_getRepulsionLengthIndices(b, diag, threshold, &d1, &d2, sh, sh + nsq, sh + 2 * nsq, sh + 3 * nsq);
+    st->bf = (short*)malloc(sizeof(short) * 4 * (nint + 1));
+    st->ints = (double*)calloc(nint + 1, sizeof(double));
+    st->nint = nint; st->nbf = nbf;
+    ref_getRepulsion0(b, nsq, sh, sh + nsq, sh + 2 * nsq, sh + 3 * nsq, st->bf, st->bf + nint, st->bf + 2 * nint, st->bf + 3 * nint, st->ints);
+    free(diag); free(sh);
+    return st;
+}
+long ref_store_len(const ref_store* st) { return st->nint; }
+void ref_store_contract(const ref_store* st, const double* Dd, const double* Da, const double* Db, double exx, int nthreads,
+                        double* J, double* Kd, double* Ka, double* Kb) {
+    long n = st->nint;
+    ref_Gunified(st->bf, st->bf + n, st->bf + 2 * n, st->bf + 3 * n, st->ints, n, st->nbf, Dd, Da, Db, exx, nthreads, J, Kd, Ka, Kb);
+}
+void ref_store_free(ref_store* st) { free(st->bf); free(st->ints); free(st); }
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

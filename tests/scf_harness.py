@@ -1,0 +1,109 @@
+"""Minimal RHF / UHF drivers used as TEST HARNESS around the J/K path (not product code).
+
+Restates the callers' combination rules:
+  RHF  (src/HartreeFockKohnSham/Restricted/SP.cpp:38-73):  D = C_occ C_occ^T (no factor 2),
+        (J,K) = ContractInts(D,0x0,0x0), F = Hcore + J - K, E = sum D o (2 Hcore + J - K),
+        residual 2(F D S - S D F), converged when max|resid| < 1e-6 (:77-79).
+  UHF  (Unrestricted/SP.cpp:42-94): (J,Ka,Kb) = ContractInts(0x0,Da,Db), F_s = Hcore + J - K_s,
+        E = 1/2 [Da o (Hcore+Fa) + Db o (Hcore+Fb)] (:75).
+Pulay CDIIS as in src/DIIS/CDIIS.cpp:24-47 (the ADIIS warm-up phase needs Maniverse and only
+changes the path to convergence, so it is skipped).
+`jk` is any callable (Dd, Da, Db) -> (J, Kd, Ka, Kb): the oracle or the CUDA engine.
+"""
+import numpy as np
+from scipy.linalg import eigh
+
+
+def nuclear_repulsion(Z, xyz):
+    e = 0.0
+    for i in range(len(Z)):
+        for j in range(i):
+            e += Z[i] * Z[j] / np.linalg.norm(xyz[i] - xyz[j])
+    return e
+
+
+def _diis_extrapolate(Fs, Rs):
+    n = len(Fs)
+    B = -np.ones((n + 1, n + 1))
+    B[n, n] = 0
+    for i in range(n):
+        for j in range(n):
+            B[i, j] = np.vdot(Rs[i], Rs[j])
+    rhs = np.zeros(n + 1)
+    rhs[n] = -1
+    try:
+        c = np.linalg.solve(B, rhs)[:n]
+    except np.linalg.LinAlgError:
+        return Fs[-1]
+    return sum(ci * Fi for ci, Fi in zip(c, Fs))
+
+
+def rhf(S, Hcore, nocc, jk, e_nuc=0.0, D0=None, max_iter=100, tol=1e-8, diis_space=12, verbose=False):
+    w, U = np.linalg.eigh(S)
+    X = U @ np.diag(w ** -0.5) @ U.T
+    def density(F):
+        e, Cp = np.linalg.eigh(X.T @ F @ X)
+        C_ = X @ Cp
+        return C_[:, :nocc] @ C_[:, :nocc].T
+    D = density(Hcore) if D0 is None else D0
+    Fs, Rs = [], []
+    E = 0.0
+    for it in range(max_iter):
+        J, K, _, _ = jk(D, None, None)
+        F = Hcore + J - K
+        E = np.sum(D * (2 * Hcore + J - K)) + e_nuc
+        R = 2 * (F @ D @ S - S @ D @ F)
+        err = np.abs(R).max()
+        if verbose:
+            print("  it %2d  E = %.10f  |R| = %.2e" % (it, E, err))
+        if err < tol:
+            return E, D, F, it
+        Fs.append(F); Rs.append(X.T @ R @ X)
+        Fs, Rs = Fs[-diis_space:], Rs[-diis_space:]
+        D = density(_diis_extrapolate(Fs, Rs))
+    raise RuntimeError("Convergence failed!")  # same message as Restricted/SP.cpp:76
+
+
+def uhf(S, Hcore, na, nb, jk, e_nuc=0.0, D0=None, max_iter=200, tol=1e-8, diis_space=12, verbose=False, level_shift=0.0):
+    w, U = np.linalg.eigh(S)
+    X = U @ np.diag(w ** -0.5) @ U.T
+    def density(F, n):
+        e, Cp = np.linalg.eigh(X.T @ F @ X)
+        C_ = X @ Cp
+        return C_[:, :n] @ C_[:, :n].T
+    if D0 is None:
+        Da, Db = density(Hcore, na), density(Hcore, nb)
+    else:
+        Da, Db = D0
+    Fs, Rs = [], []
+    for it in range(max_iter):
+        J, _, Ka, Kb = jk(None, Da, Db)
+        Fa, Fb = Hcore + J - Ka, Hcore + J - Kb
+        E = 0.5 * (np.sum(Da * (Hcore + Fa)) + np.sum(Db * (Hcore + Fb))) + e_nuc
+        Ra = Fa @ Da @ S - S @ Da @ Fa
+        Rb = Fb @ Db @ S - S @ Db @ Fb
+        err = max(np.abs(Ra).max(), np.abs(Rb).max())
+        if verbose:
+            print("  it %2d  E = %.10f  |R| = %.2e" % (it, E, err))
+        if err < tol:
+            return E, (Da, Db), (Fa, Fb), it
+        Fs.append(np.stack([Fa, Fb])); Rs.append(np.stack([X.T @ Ra @ X, X.T @ Rb @ X]))
+        Fs, Rs = Fs[-diis_space:], Rs[-diis_space:]
+        Fx = _diis_extrapolate(Fs, Rs)
+        if level_shift:
+            Fx = Fx + level_shift * np.stack([S - S @ Da @ S, S - S @ Db @ S])
+        Da, Db = density(Fx[0], na), density(Fx[1], nb)
+    raise RuntimeError("Convergence failed!")
+
+
+def core_density(S, Hcore, nocc):
+    """D_core of SURVEY 8d: occupied projector of Hcore in the S-orthonormal basis."""
+    e, C_ = eigh(Hcore, S)
+    return C_[:, :nocc] @ C_[:, :nocc].T
+
+
+def random_symmetric_density(nbf, seed=0):
+    """stress density of SURVEY 8d: D=(A+A^T)/2, A_ij ~ U(-1,1)/nbf"""
+    rng = np.random.default_rng(seed)
+    A = rng.uniform(-1, 1, (nbf, nbf)) / nbf
+    return 0.5 * (A + A.T)
