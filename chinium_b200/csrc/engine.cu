@@ -1,0 +1,861 @@
+// engine.cu -- host side of the B200 J/K engine + the C ABI of include/chinium_fock.h.
+//
+// Replaces the reference's Int4C2E setup pipeline and ContractInts
+// (src/Integral/Int4C2E.cpp:494-587, :673-683).  Design:
+//   * shell pairs grouped by angular class (la>=lb), primitive-pair data SoA in HBM
+//   * Schwarz bounds from the SAME quartet kernels run on the (ab|ab) diagonal
+//   * J/K digested in the CARTESIAN working basis: D_cart = C^T D C on the way in,
+//     J = C J_cart C^T on the way out (C = Racah solid-harmonic coefficients), so the ERI
+//     kernels never do a 4-index cart->pure transform
+//   * accumulators are 64-bit fixed point with a power-of-two scale derived on the device from a
+//     rigorous Schwarz bound -> integer adds commute -> results are bit-identical for any launch
+//     geometry, stream interleaving and number of GPUs
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/chinium_fock.h"
+#include "cf_common.cuh"
+#include "eri_generic.cuh"     // rys_tmax/rys_off (host constexpr) -- no kernels instantiated here
+#include "rys_tables_data.h"
+
+#define CUDA_TRY(x)                                                                             \
+    do {                                                                                        \
+        cudaError_t e_ = (x);                                                                   \
+        if (e_ != cudaSuccess) {                                                                \
+            set_error(h, std::string(#x) + ": " + cudaGetErrorString(e_));                      \
+            return CF_ERR_CUDA;                                                                 \
+        }                                                                                       \
+    } while (0)
+
+// launchers from eri_inst.cu (one translation unit per bra class)
+#define DECL_BRA(n) cudaError_t cf_launch_bra##n(int, const QuartetTask&, int, int, cudaStream_t, int*, size_t*);
+DECL_BRA(0) DECL_BRA(1) DECL_BRA(2) DECL_BRA(3) DECL_BRA(4) DECL_BRA(5) DECL_BRA(6) DECL_BRA(7) DECL_BRA(8) DECL_BRA(9)
+typedef cudaError_t (*bra_launch_fn)(int, const QuartetTask&, int, int, cudaStream_t, int*, size_t*);
+static bra_launch_fn g_bra_launch[CF_NCLS] = {cf_launch_bra0, cf_launch_bra1, cf_launch_bra2, cf_launch_bra3, cf_launch_bra4,
+                                              cf_launch_bra5, cf_launch_bra6, cf_launch_bra7, cf_launch_bra8, cf_launch_bra9};
+
+static std::string g_last_error;
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& v) {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct PairClassHost {
+    int la = 0, lb = 0;
+    std::vector<int> sa, sb, cao_a, cao_b, prim_off, nprim, nprim_full;
+    std::vector<double> A, AB, Q, Qpure, p, P, c;
+    DevBuf<int> d_sa, d_sb, d_cao_a, d_cao_b, d_prim_off, d_nprim;
+    DevBuf<double> d_A, d_AB, d_Q, d_p, d_P, d_c;
+    int npair() const { return (int)sa.size(); }
+    PairClassDev dev() const {
+        PairClassDev d;
+        d.npair = npair();
+        d.sa = d_sa.p; d.sb = d_sb.p; d.cao_a = d_cao_a.p; d.cao_b = d_cao_b.p;
+        d.prim_off = d_prim_off.p; d.nprim = d_nprim.p; d.A = d_A.p; d.AB = d_AB.p; d.Q = d_Q.p;
+        d.p = d_p.p; d.P = d_P.p; d.c = d_c.p;
+        return d;
+    }
+    cudaError_t upload() {
+        cudaError_t e;
+        if ((e = d_sa.upload(sa)) != cudaSuccess) return e;
+        if ((e = d_sb.upload(sb)) != cudaSuccess) return e;
+        if ((e = d_cao_a.upload(cao_a)) != cudaSuccess) return e;
+        if ((e = d_cao_b.upload(cao_b)) != cudaSuccess) return e;
+        if ((e = d_prim_off.upload(prim_off)) != cudaSuccess) return e;
+        if ((e = d_nprim.upload(nprim)) != cudaSuccess) return e;
+        if ((e = d_A.upload(A)) != cudaSuccess) return e;
+        if ((e = d_AB.upload(AB)) != cudaSuccess) return e;
+        if ((e = d_Q.upload(Q)) != cudaSuccess) return e;
+        if ((e = d_p.upload(p)) != cudaSuccess) return e;
+        if ((e = d_P.upload(P)) != cudaSuccess) return e;
+        return d_c.upload(c);
+    }
+    void release() {
+        d_sa.release(); d_sb.release(); d_cao_a.release(); d_cao_b.release(); d_prim_off.release(); d_nprim.release();
+        d_A.release(); d_AB.release(); d_Q.release(); d_p.release(); d_P.release(); d_c.release();
+    }
+};
+
+struct ClassPairTask {
+    int bra = 0, ket = 0;
+    long long nquartet = 0;
+    DevBuf<long long> d_qoff;
+    int G = 32;
+    size_t smem[4] = {0, 0, 0, 0};   // by nk
+    double flops_eri = 0;            // F_alg without the digestion term
+    double nfun_sum = 0;             // sum over quartets of N_s (pure functions) for the digestion term
+};
+
+struct cf_handle {
+    int device = 0;
+    cf_options opt{};
+    int nshell = 0, nbf = 0, ncart = 0;
+    std::vector<int> type, l, nprim, prim_off, bf_off, cao_off, nfun;
+    std::vector<double> exps, coefs, xyz;
+    // per-shell transformation (function x cartesian), pooled by type
+    std::vector<double> ctrans;            // pool
+    std::vector<int> ct_off;               // [nshell] offset into pool
+    DevBuf<double> d_ctrans;
+    DevBuf<int> d_ct_off, d_bf_off, d_cao_off, d_nfun, d_ncartsh;
+    PairClassHost cls[CF_NCLS];
+    std::vector<ClassPairTask*> tasks;
+    DevBuf<double> d_rys_table, d_rys_asym;
+    // per-build work space
+    DevBuf<double> d_Dpure[3], d_Dcart[4] /* 0: Dtot, 1..3: Dk */, d_out[4] /* pure J,Kd,Ka,Kb */, d_partial, d_scales, d_diag;
+    DevBuf<long long> d_acc;
+    double qmax_cart = 0;
+    cudaEvent_t ev[4];
+    cudaStream_t side[3];
+    cudaEvent_t ev_fork, ev_join[3];
+    cf_stats stats{};
+    std::string err;
+    bool diag_ready = false;
+};
+
+static void set_error(cf_handle* h, const std::string& s) {
+    if (h) h->err = s;
+    g_last_error = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small device kernels
+// ------------------------------------------------------------------------------------------------
+// D_cart(block sa,sb) = C_a^T Dsym(block) C_b, with Dsym = (D + D^T)/2 ; optionally Dtot = 2Dd + Da + Db
+__global__ void pure_to_cart_kernel(int nshell, int nbf, int ncart, const double* __restrict__ Dd, const double* __restrict__ Da,
+                                    const double* __restrict__ Db, double fd, double fa, double fb,
+                                    const double* __restrict__ ctrans, const int* __restrict__ ct_off, const int* __restrict__ bf_off,
+                                    const int* __restrict__ cao_off, const int* __restrict__ nfun, const int* __restrict__ ncsh,
+                                    double* __restrict__ out) {
+    const int sa = blockIdx.x, sb = blockIdx.y;
+    const int na = nfun[sa], nb = nfun[sb], nca = ncsh[sa], ncb = ncsh[sb];
+    const double* Ca = ctrans + ct_off[sa];
+    const double* Cb = ctrans + ct_off[sb];
+    for (int e = threadIdx.x; e < nca * ncb; e += blockDim.x) {
+        const int x = e / ncb, y = e % ncb;
+        double s = 0.0;
+        for (int m = 0; m < na; m++) {
+            const double cam = Ca[m * nca + x];
+            if (cam == 0.0) continue;
+            for (int n = 0; n < nb; n++) {
+                const size_t i = bf_off[sa] + m, j = bf_off[sb] + n;
+                double d = 0.0;
+                if (Dd) d += fd * 0.5 * (Dd[j * nbf + i] + Dd[i * nbf + j]);
+                if (Da) d += fa * 0.5 * (Da[j * nbf + i] + Da[i * nbf + j]);
+                if (Db) d += fb * 0.5 * (Db[j * nbf + i] + Db[i * nbf + j]);
+                s = fma(cam * Cb[n * ncb + y], d, s);
+            }
+        }
+        out[(size_t)(cao_off[sb] + y) * ncart + cao_off[sa] + x] = s;
+    }
+}
+
+// out_pure(block) = factor * C_a [ (acc + acc^T) / scale ] C_b^T ; integer sum first (exact), one conversion
+__global__ void finalize_kernel(int nbf, int ncart, const long long* __restrict__ acc, const double* __restrict__ scales, int which_scale,
+                                double factor, const double* __restrict__ ctrans, const int* __restrict__ ct_off,
+                                const int* __restrict__ bf_off, const int* __restrict__ cao_off, const int* __restrict__ nfun,
+                                const int* __restrict__ ncsh, double* __restrict__ out) {
+    const int sa = blockIdx.x, sb = blockIdx.y;
+    const int na = nfun[sa], nb = nfun[sb], nca = ncsh[sa], ncb = ncsh[sb];
+    const double* Ca = ctrans + ct_off[sa];
+    const double* Cb = ctrans + ct_off[sb];
+    const double f = factor / scales[which_scale];
+    for (int e = threadIdx.x; e < na * nb; e += blockDim.x) {
+        const int m = e / nb, n = e % nb;
+        double s = 0.0;
+        for (int x = 0; x < nca; x++) {
+            const double cam = Ca[m * nca + x];
+            if (cam == 0.0) continue;
+            for (int y = 0; y < ncb; y++) {
+                const size_t i = cao_off[sa] + x, j = cao_off[sb] + y;
+                const long long v = acc[j * ncart + i] + acc[i * ncart + j];
+                s = fma(cam * Cb[n * ncb + y], (double)v, s);
+            }
+        }
+        out[(size_t)(bf_off[sb] + n) * nbf + bf_off[sa] + m] = s * f;
+    }
+}
+
+// entrywise 1-norm partial sums in a FIXED order (deterministic): block b sums elements b, b+grid, ... per thread,
+// then a fixed tree in shared memory
+__global__ void norm1_partial_kernel(const double* __restrict__ a, size_t n, double* __restrict__ partial) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += fabs(a[i]);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+// scales[0] = J scale, scales[1] = K scale (powers of two); bound = 16 * qmax^2 * ||D||_1
+__global__ void scales_kernel(const double* __restrict__ partial, int nblk, int nk, double qmax2, double* __restrict__ scales) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double nj = 0.0;
+    for (int i = 0; i < nblk; i++) nj += partial[i];
+    double nkmax = 0.0;
+    for (int x = 0; x < nk; x++) {
+        double s = 0.0;
+        for (int i = 0; i < nblk; i++) s += partial[(x + 1) * nblk + i];
+        nkmax = fmax(nkmax, s);
+    }
+    const double bj = 16.0 * qmax2 * nj, bk = 16.0 * qmax2 * nkmax;
+    int ej, ek;
+    frexp(fmax(bj, 1e-300), &ej);
+    frexp(fmax(bk, 1e-300), &ek);
+    scales[0] = ldexp(1.0, 62 - ej);
+    scales[1] = ldexp(1.0, 62 - ek);
+    scales[2] = bj;
+    scales[3] = bk;
+}
+
+// Schwarz bounds of one pair class from the stored Cartesian (ab|ab) blocks: one CTA per pair
+__global__ void schwarz_kernel(int npair, int nca, int ncb, const double* __restrict__ blocks, const int* __restrict__ sa,
+                               const int* __restrict__ sb, const double* __restrict__ ctrans, const int* __restrict__ ct_off,
+                               const int* __restrict__ bf_off, const int* __restrict__ nfun, int nbf, double* __restrict__ Qcart,
+                               double* __restrict__ Qpure, double* __restrict__ diag) {
+    const int ip = blockIdx.x;
+    const int nab = nca * ncb;
+    const double* V = blocks + (size_t)ip * nab * nab;
+    const int a = sa[ip], b = sb[ip];
+    const int na = nfun[a], nb = nfun[b];
+    const double* Ca = ctrans + ct_off[a];
+    const double* Cb = ctrans + ct_off[b];
+    __shared__ double red[2][128];
+    double qc = 0.0, qp = 0.0;
+    for (int x = threadIdx.x; x < nab; x += blockDim.x) qc = fmax(qc, sqrt(fabs(V[(size_t)x * nab + x])));
+    for (int m = threadIdx.x; m < na * nb; m += blockDim.x) {
+        const int ma = m / nb, mb = m % nb;
+        double s = 0.0;
+        for (int x = 0; x < nab; x++) {
+            const double mx = Ca[ma * nca + x / ncb] * Cb[mb * ncb + x % ncb];
+            if (mx == 0.0) continue;
+            double r = 0.0;
+            for (int y = 0; y < nab; y++) r = fma(Ca[ma * nca + y / ncb] * Cb[mb * ncb + y % ncb], V[(size_t)x * nab + y], r);
+            s = fma(mx, r, s);
+        }
+        qp = fmax(qp, sqrt(fabs(s)));
+        if (diag) {
+            diag[(size_t)(bf_off[b] + mb) * nbf + bf_off[a] + ma] = s;
+            diag[(size_t)(bf_off[a] + ma) * nbf + bf_off[b] + mb] = s;
+        }
+    }
+    red[0][threadIdx.x] = qc; red[1][threadIdx.x] = qp;
+    __syncthreads();
+    for (int w = 64; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            red[0][threadIdx.x] = fmax(red[0][threadIdx.x], red[0][threadIdx.x + w]);
+            red[1][threadIdx.x] = fmax(red[1][threadIdx.x], red[1][threadIdx.x + w]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { Qcart[ip] = red[0][0]; Qpure[ip] = red[1][0]; }
+}
+
+// register-resident DFMA loop: the FP64 roofline denominator measured on the device itself
+__global__ void dfma_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+static double fact_d(int n) { double r = 1; for (int i = 2; i <= n; i++) r *= i; return r; }
+static double binom_d(int n, int k) { return (k < 0 || k > n) ? 0.0 : fact_d(n) / (fact_d(k) * fact_d(n - k)); }
+static int cart_index_h(int l, int lx, int ly) {
+    int n = 0;
+    for (int x = l; x > lx; x--) n += l - x + 1;
+    return n + (l - lx - ly);
+}
+// rows: functions of a shell of `type` in the reference's order; cols: Cartesian monomials (lx desc, ly desc)
+static std::vector<double> shell_transform_h(int type) {
+    const int l = std::abs(type), nc = cf_ncart(l);
+    if (type >= 0) {
+        std::vector<double> C((size_t)nc * nc, 0.0);
+        for (int i = 0; i < nc; i++) C[(size_t)i * nc + i] = 1.0;
+        return C;
+    }
+    std::vector<double> C((size_t)(2 * l + 1) * nc, 0.0);
+    for (int m = -l; m <= l; m++) {
+        const int am = std::abs(m);
+        const double N = std::sqrt(2.0 * fact_d(l + am) * fact_d(l - am) / (m == 0 ? 2.0 : 1.0)) / (std::pow(2.0, am) * fact_d(l));
+        for (int t = 0; t <= (l - am) / 2; t++)
+            for (int u = 0; u <= t; u++)
+                for (int v2 = (m >= 0 ? 0 : 1); v2 <= am; v2 += 2) {
+                    const int k = (m >= 0) ? v2 / 2 : (v2 - 1) / 2;
+                    const double c = (((t + k) & 1) ? -1.0 : 1.0) * std::pow(0.25, t) * binom_d(l, t) * binom_d(l - t, am + t) *
+                                     binom_d(t, u) * binom_d(am, v2);
+                    const int ex = 2 * t + am - 2 * u - v2, ey = 2 * u + v2;
+                    if (ex < 0) continue;
+                    C[(size_t)(m + l) * nc + cart_index_h(l, ex, ey)] += N * c;
+                }
+    }
+    return C;
+}
+
+static int check_device(cf_handle* h, int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { set_error(h, "no CUDA device (this engine has no CPU fallback)"); return CF_ERR_NO_DEVICE; }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= n) { set_error(h, "device ordinal out of range"); return CF_ERR_NO_DEVICE; }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { set_error(h, "cudaGetDeviceProperties failed"); return CF_ERR_NO_DEVICE; }
+    if (p.major != 10) { set_error(h, "device is not sm_100 (kernels are built for sm_100a only)"); return CF_ERR_NO_DEVICE; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error(h, "cudaSetDevice failed"); return CF_ERR_NO_DEVICE; }
+    if (h) h->device = device;
+    return CF_OK;
+}
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static int launch_task(cf_handle* h, ClassPairTask* t, QuartetTask& qt, int store, cudaStream_t s) {
+    const PairClassHost& B = h->cls[t->bra];
+    const PairClassHost& K = h->cls[t->ket];
+    qt.bra = B.dev(); qt.ket = K.dev();
+    qt.qoff = t->d_qoff.p; qt.nquartet = t->nquartet;
+    qt.same_class = (t->bra == t->ket);
+    const long long nq = qt.nquartet;
+    if (nq == 0) return CF_OK;
+    // chunk: enough chunks to fill the machine ~8x over, at most 64 quartets each
+    long long chunk = nq / (148LL * 32 * std::max(1, qt.world));
+    chunk = std::max(1LL, std::min(64LL, chunk));
+    qt.chunk = (int)chunk;
+    const long long nchunk_total = (nq + chunk - 1) / chunk;
+    const long long nchunk_local = (nchunk_total - qt.rank + qt.world - 1) / qt.world;
+    if (nchunk_local <= 0) return CF_OK;
+    const int grid = (int)std::min<long long>(nchunk_local, 148LL * 32);
+    cudaError_t e = g_bra_launch[t->bra](t->ket, qt, store, grid, s, nullptr, nullptr);
+    if (e != cudaSuccess) { set_error(h, std::string("ERI kernel launch failed: ") + cudaGetErrorString(e)); return CF_ERR_CUDA; }
+    h->stats.n_launches_last++;
+    return CF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* cf_last_error(const cf_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int cf_device_info(int device, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { set_error(nullptr, "no CUDA device"); return CF_ERR_NO_DEVICE; }
+    if (device < 0) cudaGetDevice(&device);
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return CF_ERR_CUDA;
+    if (name && name_len > 0) { std::strncpy(name, p.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return CF_OK;
+}
+
+extern "C" int cf_measure_fp64_peak(int device, double* tflops) {
+    cf_handle* h = nullptr;
+    int rc = check_device(nullptr, device);
+    if (rc != CF_OK) return rc;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device < 0 ? 0 : device);
+    const int threads = 512, blocks = sms * 4, iters = 1 << 15;
+    double* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, sizeof(double) * threads * blocks));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, threads>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 8.0 * iters * (double)threads * blocks;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    if (tflops) *tflops = best;
+    return CF_OK;
+}
+
+extern "C" void cf_destroy(cf_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto& c : h->cls) c.release();
+    for (auto* t : h->tasks) { t->d_qoff.release(); delete t; }
+    h->d_ctrans.release(); h->d_ct_off.release(); h->d_bf_off.release(); h->d_cao_off.release(); h->d_nfun.release(); h->d_ncartsh.release();
+    h->d_rys_table.release(); h->d_rys_asym.release();
+    for (auto& b : h->d_Dpure) b.release();
+    for (auto& b : h->d_Dcart) b.release();
+    for (auto& b : h->d_out) b.release();
+    h->d_partial.release(); h->d_scales.release(); h->d_diag.release(); h->d_acc.release();
+    for (auto& e : h->ev) cudaEventDestroy(e);
+    for (int i = 0; i < 3; i++) { cudaStreamDestroy(h->side[i]); cudaEventDestroy(h->ev_join[i]); }
+    cudaEventDestroy(h->ev_fork);
+    delete h;
+}
+
+static void fill_rys(QuartetTask& qt, const cf_handle* h) {
+    qt.rys.table = h->d_rys_table.p;
+    qt.rys.asym = h->d_rys_asym.p;
+}
+
+extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
+    if (!basis || basis->nshell <= 0 || !basis->type || !basis->nprim || !basis->prim_offset || !basis->exps ||
+        !basis->coefs_normalized || !basis->center_xyz) {
+        set_error(nullptr, "cf_create: null or empty basis");
+        return nullptr;
+    }
+    cf_handle* h = new cf_handle();
+    if (opts) h->opt = *opts;
+    if (h->opt.world_size <= 0) { h->opt.world_size = 1; h->opt.rank = 0; }
+    if (h->opt.rank < 0 || h->opt.rank >= h->opt.world_size) { set_error(nullptr, "cf_create: rank out of range"); delete h; return nullptr; }
+    if (h->opt.pair_cutoff <= 0) h->opt.pair_cutoff = 1e-20;
+    if (check_device(h, h->opt.device) != CF_OK) { g_last_error = h->err; delete h; return nullptr; }
+    const double t_start = now_s();
+    auto fail = [&](const std::string& s) -> cf_handle* { set_error(nullptr, s); cf_destroy(h); return nullptr; };
+    for (auto& e : h->ev) cudaEventCreate(&e);
+    for (int i = 0; i < 3; i++) { cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming); }
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+
+    // static check of the table geometry assumed by the kernels
+    for (int n = 1; n <= RYS_NMAX; n++)
+        if (rys_tmax(n) != rys_tmax_h[n] || rys_off(n) != rys_off_h[n] || rys_asym_off(n) != rys_asym_off_h[n])
+            return fail("Rys table geometry mismatch between generator and kernels");
+
+    // ---- shells
+    const int ns = basis->nshell;
+    h->nshell = ns;
+    h->type.assign(basis->type, basis->type + ns);
+    h->nprim.assign(basis->nprim, basis->nprim + ns);
+    h->prim_off.assign(basis->prim_offset, basis->prim_offset + ns);
+    h->xyz.assign(basis->center_xyz, basis->center_xyz + 3 * ns);
+    int nptot = 0;
+    for (int s = 0; s < ns; s++) nptot = std::max(nptot, h->prim_off[s] + h->nprim[s]);
+    h->exps.assign(basis->exps, basis->exps + nptot);
+    h->coefs.assign(basis->coefs_normalized, basis->coefs_normalized + nptot);
+    h->l.resize(ns); h->bf_off.resize(ns); h->cao_off.resize(ns); h->nfun.resize(ns); h->ct_off.resize(ns);
+    std::vector<int> ncsh(ns);
+    std::vector<int> pool_off(32, -1);   // by type + 16
+    int nbf = 0, ncart = 0;
+    for (int s = 0; s < ns; s++) {
+        const int t = h->type[s], l = std::abs(t);
+        if (l > CF_LMAX_DEV) return fail("cf_create: shell angular momentum above CF_MAX_L is not supported by the device kernels");
+        if (t > 1) return fail("cf_create: Cartesian shells with l >= 2 are not produced by the reference's basis reader and are not supported");
+        if (h->nprim[s] <= 0) return fail("cf_create: shell without primitives");
+        h->l[s] = l;
+        h->nfun[s] = t < 0 ? 2 * l + 1 : cf_ncart(l);
+        ncsh[s] = cf_ncart(l);
+        h->bf_off[s] = nbf; h->cao_off[s] = ncart;
+        nbf += h->nfun[s]; ncart += ncsh[s];
+        if (pool_off[t + 16] < 0) {
+            pool_off[t + 16] = (int)h->ctrans.size();
+            auto C = shell_transform_h(t);
+            h->ctrans.insert(h->ctrans.end(), C.begin(), C.end());
+        }
+        h->ct_off[s] = pool_off[t + 16];
+    }
+    if (nbf >= 32768) return fail("cf_create: nbf >= 32768 (the reference's short int indices, Int4C2E.h:19-29)");
+    h->nbf = nbf; h->ncart = ncart;
+
+#define UP(buf, vec) if ((buf).upload(vec) != cudaSuccess) return fail("cudaMalloc/cudaMemcpy failed in cf_create")
+    UP(h->d_ctrans, h->ctrans); UP(h->d_ct_off, h->ct_off); UP(h->d_bf_off, h->bf_off); UP(h->d_cao_off, h->cao_off);
+    UP(h->d_nfun, h->nfun); UP(h->d_ncartsh, ncsh);
+    {
+        std::vector<double> tab(rys_table_h, rys_table_h + RYS_TABLE_LEN), asym(rys_asym_h, rys_asym_h + RYS_NMAX * (RYS_NMAX + 1));
+        UP(h->d_rys_table, tab); UP(h->d_rys_asym, asym);
+    }
+
+    // ---- shell pairs by class
+    const double pref = std::sqrt(2.0) * std::pow(M_PI, 1.25);
+    for (int la = 0; la <= CF_LMAX_DEV; la++)
+        for (int lb = 0; lb <= la; lb++) { auto& c = h->cls[cf_pair_class(la, lb)]; c.la = la; c.lb = lb; }
+    long long pairs_kept = 0;
+    for (int s1 = 0; s1 < ns; s1++)
+        for (int s2 = 0; s2 <= s1; s2++) {
+            int a = s1, b = s2;
+            if (h->l[b] > h->l[a]) std::swap(a, b);
+            PairClassHost& c = h->cls[cf_pair_class(h->l[a], h->l[b])];
+            const double* A = &h->xyz[3 * a];
+            const double* B = &h->xyz[3 * b];
+            const double ab[3] = {A[0] - B[0], A[1] - B[1], A[2] - B[2]};
+            const double r2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
+            const int p0 = (int)c.p.size();
+            int kept = 0;
+            for (int i = 0; i < h->nprim[a]; i++)
+                for (int j = 0; j < h->nprim[b]; j++) {
+                    const double ea = h->exps[h->prim_off[a] + i], eb = h->exps[h->prim_off[b] + j];
+                    const double p = ea + eb;
+                    const double cc = h->coefs[h->prim_off[a] + i] * h->coefs[h->prim_off[b] + j] * std::exp(-ea * eb / p * r2) * pref / p;
+                    if (std::fabs(cc) < h->opt.pair_cutoff) continue;
+                    c.p.push_back(p);
+                    for (int x = 0; x < 3; x++) c.P.push_back((ea * A[x] + eb * B[x]) / p);
+                    c.c.push_back(cc);
+                    kept++;
+                }
+            if (kept == 0) continue;
+            c.sa.push_back(a); c.sb.push_back(b);
+            c.cao_a.push_back(h->cao_off[a]); c.cao_b.push_back(h->cao_off[b]);
+            c.prim_off.push_back(p0); c.nprim.push_back(kept); c.nprim_full.push_back(h->nprim[a] * h->nprim[b]);
+            for (int x = 0; x < 3; x++) { c.A.push_back(A[x]); c.AB.push_back(ab[x]); }
+            c.Q.push_back(0.0); c.Qpure.push_back(0.0);
+            pairs_kept++;
+        }
+    for (auto& c : h->cls) if (c.upload() != cudaSuccess) return fail("pair upload failed");
+
+    // ---- Schwarz bounds: (ab|ab) Cartesian blocks from the quartet kernel in STORE/diag mode
+    if (h->d_diag.alloc((size_t)nbf * nbf) != cudaSuccess) return fail("cudaMalloc failed (diag)");
+    cudaMemset(h->d_diag.p, 0, sizeof(double) * (size_t)nbf * nbf);
+    for (int ci = 0; ci < CF_NCLS; ci++) {
+        PairClassHost& c = h->cls[ci];
+        const int np = c.npair();
+        if (np == 0) continue;
+        const int nca = cf_ncart(c.la), ncb = cf_ncart(c.lb);
+        const size_t nout = (size_t)nca * ncb * nca * ncb;
+        // in slabs so the store buffer stays below ~1 GiB
+        const int slab = (int)std::max<size_t>(1, std::min<size_t>(np, (1ull << 27) / nout));
+        DevBuf<double> blocks, qpure;
+        if (blocks.alloc(nout * slab) != cudaSuccess || qpure.alloc(np) != cudaSuccess) return fail("cudaMalloc failed (Schwarz)");
+        for (int p0 = 0; p0 < np; p0 += slab) {
+            const int cnt = std::min(slab, np - p0);
+            QuartetTask qt{};
+            PairClassDev d = c.dev();
+            // shift the pair arrays so that local pair q maps to global pair p0+q
+            d.npair = cnt; d.sa += p0; d.sb += p0; d.cao_a += p0; d.cao_b += p0; d.prim_off += p0; d.nprim += p0; d.A += 3 * p0; d.AB += 3 * p0; d.Q += p0;
+            qt.bra = d; qt.ket = d; qt.qoff = nullptr; qt.nquartet = cnt; qt.chunk = 1; qt.rank = 0; qt.world = 1;
+            qt.same_class = 1; qt.ncart = ncart; qt.nk = 0; qt.store = blocks.p; qt.diag = 1; qt.prim_cut = 0.0;
+            fill_rys(qt, h);
+            cudaError_t e = g_bra_launch[ci](ci, qt, 1, cnt, 0, nullptr, nullptr);
+            if (e != cudaSuccess) return fail(std::string("Schwarz launch failed: ") + cudaGetErrorString(e));
+            schwarz_kernel<<<cnt, 128>>>(cnt, nca, ncb, blocks.p, c.d_sa.p + p0, c.d_sb.p + p0, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
+                                         h->d_nfun.p, nbf, c.d_Q.p + p0, qpure.p + p0, h->d_diag.p);
+        }
+        if (cudaMemcpy(c.Q.data(), c.d_Q.p, sizeof(double) * np, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(c.Qpure.data(), qpure.p, sizeof(double) * np, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(std::string("Schwarz kernels failed: ") + cudaGetErrorString(cudaGetLastError()));
+        blocks.release(); qpure.release();
+    }
+    h->diag_ready = true;
+
+    // ---- sort each class by the (pure-function) Schwarz bound, descending; re-upload
+    h->qmax_cart = 0;
+    for (auto& c : h->cls) {
+        const int np = c.npair();
+        if (np == 0) continue;
+        std::vector<int> perm(np);
+        std::iota(perm.begin(), perm.end(), 0);
+        std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return c.Qpure[x] > c.Qpure[y]; });
+        auto permute_i = [&](std::vector<int>& v, int w) { std::vector<int> o(v.size()); for (int i = 0; i < np; i++) for (int k = 0; k < w; k++) o[(size_t)i * w + k] = v[(size_t)perm[i] * w + k]; v.swap(o); };
+        auto permute_d = [&](std::vector<double>& v, int w) { std::vector<double> o(v.size()); for (int i = 0; i < np; i++) for (int k = 0; k < w; k++) o[(size_t)i * w + k] = v[(size_t)perm[i] * w + k]; v.swap(o); };
+        permute_i(c.sa, 1); permute_i(c.sb, 1); permute_i(c.cao_a, 1); permute_i(c.cao_b, 1); permute_i(c.prim_off, 1);
+        permute_i(c.nprim, 1); permute_i(c.nprim_full, 1); permute_d(c.A, 3); permute_d(c.AB, 3); permute_d(c.Q, 1); permute_d(c.Qpure, 1);
+        for (double q : c.Q) h->qmax_cart = std::max(h->qmax_cart, q);
+        if (c.upload() != cudaSuccess) return fail("pair re-upload failed");
+    }
+
+    // ---- class-pair tasks: per bra pair the kets are a prefix of the sorted ket list
+    const double thr = h->opt.threshold;
+    cf_stats& st = h->stats;
+    st = cf_stats{};
+    st.nshell = ns; st.nbf = nbf; st.ncart = ncart;
+    st.shell_pairs_total = (long long)ns * (ns + 1) / 2;
+    st.shell_pairs_kept = pairs_kept;
+    for (int cb = 0; cb < CF_NCLS; cb++)
+        for (int ck = 0; ck <= cb; ck++) {
+            const PairClassHost& B = h->cls[cb];
+            const PairClassHost& K = h->cls[ck];
+            if (B.npair() == 0 || K.npair() == 0) continue;
+            ClassPairTask* t = new ClassPairTask();
+            t->bra = cb; t->ket = ck;
+            const int nb = B.npair(), nk = K.npair();
+            std::vector<long long> qoff(nb + 1, 0);
+            // prefix sums over the ket list for the statistics
+            std::vector<double> pre_prim(nk + 1, 0.0), pre_primfull(nk + 1, 0.0), pre_uniq(nk + 1, 0.0);
+            const int nfc = h->nfun[K.sa[0]], nfd = h->nfun[K.sb[0]];
+            for (int k = 0; k < nk; k++) {
+                pre_prim[k + 1] = pre_prim[k] + K.nprim[k];
+                pre_primfull[k + 1] = pre_primfull[k] + K.nprim_full[k];
+                const double ncd = (K.sa[k] == K.sb[k]) ? nfc * (nfc + 1) / 2.0 : (double)nfc * nfd;
+                pre_uniq[k + 1] = pre_uniq[k] + ncd;
+            }
+            const int nfa = h->nfun[B.sa[0]], nfb = h->nfun[B.sb[0]];
+            const int L = B.la + B.lb + K.la + K.lb, nr = L / 2 + 1;
+            const double per_prim = nr * (40.0 + 12.0 * (B.la + B.lb + 1) * (K.la + K.lb + 1) +
+                                          3.0 * cf_ncart(B.la) * cf_ncart(B.lb) * cf_ncart(K.la) * cf_ncart(K.lb));
+            double uniq = 0, primq = 0, primq_full = 0;
+            for (int i = 0; i < nb; i++) {
+                int cnt = nk;
+                if (thr > 0) {   // kets with Qb*Qk > thr form a prefix (Q sorted descending); Int4C2E.cpp:108-113
+                    const double need = thr / std::max(B.Qpure[i], 1e-300);
+                    cnt = (int)(std::partition_point(K.Qpure.begin(), K.Qpure.end(), [&](double q) { return q > need; }) - K.Qpure.begin());
+                }
+                if (cb == ck) cnt = std::min(cnt, i + 1);
+                qoff[i + 1] = qoff[i] + cnt;
+                const double nab = (B.sa[i] == B.sb[i]) ? nfa * (nfa + 1) / 2.0 : (double)nfa * nfb;
+                uniq += nab * pre_uniq[cnt];
+                if (cb == ck && cnt == i + 1) uniq -= nab * nab - nab * (nab + 1) / 2.0;   // diagonal quartet (ab|ab)
+                primq += (double)B.nprim[i] * pre_prim[cnt];
+                primq_full += (double)B.nprim_full[i] * pre_primfull[cnt];
+            }
+            t->nquartet = qoff[nb];
+            if (t->nquartet == 0) { delete t; continue; }
+            if (t->d_qoff.upload(qoff) != cudaSuccess) { delete t; return fail("qoff upload failed"); }
+            QuartetTask dummy{};
+            for (int k = 0; k < 4; k++) { dummy.nk = k; g_bra_launch[cb](ck, dummy, 0, 0, 0, &t->G, &t->smem[k]); }
+            t->flops_eri = primq_full * per_prim;
+            t->nfun_sum = (double)t->nquartet * nfa * nfb * nfc * nfd;
+            st.canonical_quartets += t->nquartet;
+            st.unique_integrals += (long long)(uniq + 0.5);
+            st.primitive_quartets += (long long)(primq + 0.5);
+            for (int k = 0; k < 4; k++) st.flops_alg_jk[k] += t->flops_eri + 2.0 * (2 + 4 * k) * t->nfun_sum;
+            h->tasks.push_back(t);
+        }
+    st.canonical_quartets_local = st.canonical_quartets / h->opt.world_size;
+    if (h->opt.world_size > 1) for (int k = 0; k < 4; k++) st.flops_alg_jk[k] /= h->opt.world_size;
+    // heavy tasks first so the tail of the build is made of small kernels
+    std::sort(h->tasks.begin(), h->tasks.end(), [](const ClassPairTask* a, const ClassPairTask* b) { return a->flops_eri > b->flops_eri; });
+
+    // ---- work space
+    const size_t n2p = (size_t)nbf * nbf, n2c = (size_t)ncart * ncart;
+    bool ok = true;
+    for (auto& b : h->d_Dpure) ok = ok && b.alloc(n2p) == cudaSuccess;
+    for (auto& b : h->d_Dcart) ok = ok && b.alloc(n2c) == cudaSuccess;
+    for (auto& b : h->d_out) ok = ok && b.alloc(n2p) == cudaSuccess;
+    ok = ok && h->d_acc.alloc(4 * n2c) == cudaSuccess && h->d_partial.alloc(4 * 256) == cudaSuccess && h->d_scales.alloc(4) == cudaSuccess;
+    if (!ok) return fail("cudaMalloc failed (work space)");
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(std::string("setup kernels failed: ") + cudaGetErrorString(cudaGetLastError()));
+    if (h->opt.verbose > 0) {
+        // the reference prints one line per setup stage (Int4C2E.cpp:500-587); the stages are fused here
+        std::printf("Calculating diagonal elements of repulsion integrals ... Done in %f s\n", now_s() - t_start);
+        std::printf("After screening: %lld integrals and %lld shell quartets\n", (long long)st.unique_integrals, (long long)st.canonical_quartets);
+    }
+    return h;
+}
+
+extern "C" int cf_nbf(const cf_handle* h) { return h ? h->nbf : -1; }
+
+extern "C" int cf_get_stats(const cf_handle* h, cf_stats* out) {
+    if (!h || !out) return CF_ERR_BAD_ARGUMENT;
+    *out = h->stats;
+    return CF_OK;
+}
+
+extern "C" int cf_get_repulsion_diag(cf_handle* h, double* diag1212) {
+    if (!h || !diag1212) return CF_ERR_BAD_ARGUMENT;
+    if (!h->diag_ready) { set_error(h, "Diagonal elements of repulsion integrals are missing!"); return CF_ERR_STATE; }
+    cudaSetDevice(h->device);
+    CUDA_TRY(cudaMemcpy(diag1212, h->d_diag.p, sizeof(double) * (size_t)h->nbf * h->nbf, cudaMemcpyDeviceToHost));
+    return CF_OK;
+}
+
+extern "C" size_t cf_acc_len(const cf_handle* h, int nk) {
+    if (!h || nk < 0 || nk > 3) return 0;
+    return (size_t)(1 + nk) * h->ncart * h->ncart;
+}
+
+// densities present -> compact list of exchange densities
+static int exchange_list(const double* Dd, const double* Da, const double* Db, double exx, const double* out[3], int slot[3]) {
+    int nk = 0;
+    if (exx > 0.0) {
+        if (Dd) { out[nk] = Dd; slot[nk++] = 0; }
+        if (Da) { out[nk] = Da; slot[nk++] = 1; }
+        if (Db) { out[nk] = Db; slot[nk++] = 2; }
+    }
+    return nk;
+}
+
+extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, const double* Da, const double* Db, double exx,
+                                    int64_t* acc, void* stream) {
+    if (!h) return CF_ERR_BAD_ARGUMENT;
+    if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
+    if (!Dd && !Da && !Db) { set_error(h, "at least one density is required"); return CF_ERR_BAD_ARGUMENT; }
+    if (!acc) { set_error(h, "null accumulator"); return CF_ERR_BAD_ARGUMENT; }
+    cudaSetDevice(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const double* dk[3]; int slot[3];
+    const int nk = exchange_list(Dd, Da, Db, exx, dk, slot);
+    const int ns = h->nshell, ncart = h->ncart;
+    const size_t n2c = (size_t)ncart * ncart;
+    h->stats.n_launches_last = 0;
+    dim3 grid2(ns, ns);
+    // total density 2Dd + Da + Db (Int4C2E.cpp:612-615) and the exchange densities, in the Cartesian working basis
+    pure_to_cart_kernel<<<grid2, 64, 0, s>>>(ns, nbf, ncart, Dd, Da, Db, 2.0, 1.0, 1.0, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
+                                             h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[0].p);
+    h->stats.n_launches_last++;
+    for (int x = 0; x < nk; x++) {
+        pure_to_cart_kernel<<<grid2, 64, 0, s>>>(ns, nbf, ncart, dk[x], nullptr, nullptr, 1.0, 0.0, 0.0, h->d_ctrans.p, h->d_ct_off.p,
+                                                 h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[1 + x].p);
+        h->stats.n_launches_last++;
+    }
+    const int nblk = 256;
+    for (int x = 0; x <= nk; x++) {
+        norm1_partial_kernel<<<nblk, 256, 0, s>>>(h->d_Dcart[x].p, n2c, h->d_partial.p + (size_t)x * nblk);
+        h->stats.n_launches_last++;
+    }
+    scales_kernel<<<1, 32, 0, s>>>(h->d_partial.p, nblk, nk, h->qmax_cart * h->qmax_cart, h->d_scales.p);
+    h->stats.n_launches_last++;
+    CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * (1 + nk) * n2c, s));
+    // the scales live on the device; the ERI kernels need them as values -> one small synchronous read
+    double scales[4];
+    CUDA_TRY(cudaMemcpyAsync(scales, h->d_scales.p, sizeof(scales), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->stats.fixedpoint_scale_log2[0] = std::log2(scales[0]);
+    h->stats.fixedpoint_scale_log2[1] = std::log2(scales[1]);
+    if (!(scales[0] >= 0x1p30) || (nk > 0 && !(scales[1] >= 0x1p30))) {
+        set_error(h, "fixed-point accumulator range exceeded: the density is too large for 1e-10 absolute accuracy in 64 bits");
+        return CF_ERR_RANGE;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[1], s));
+    // fan the class-pair kernels out over the caller's stream + 3 side streams (small launches overlap)
+    CUDA_TRY(cudaEventRecord(h->ev_fork, s));
+    for (int i = 0; i < 3; i++) CUDA_TRY(cudaStreamWaitEvent(h->side[i], h->ev_fork, 0));
+    int it = 0;
+    for (ClassPairTask* t : h->tasks) {
+        QuartetTask qt{};
+        qt.rank = h->opt.rank; qt.world = h->opt.world_size;
+        qt.ncart = ncart; qt.nk = nk;
+        qt.Dtot = h->d_Dcart[0].p;
+        for (int x = 0; x < nk; x++) { qt.Dk[x] = h->d_Dcart[1 + x].p; qt.accK[x] = (long long*)acc + (size_t)(1 + x) * n2c; }
+        qt.accJ = (long long*)acc;
+        qt.scaleJ = scales[0]; qt.scaleK = scales[1];
+        qt.store = nullptr; qt.diag = 0; qt.prim_cut = 1e-22;
+        fill_rys(qt, h);
+        cudaStream_t ts = (it % 4 == 0) ? s : h->side[it % 4 - 1];
+        it++;
+        int rc = launch_task(h, t, qt, 0, ts);
+        if (rc != CF_OK) return rc;
+    }
+    for (int i = 0; i < 3; i++) { CUDA_TRY(cudaEventRecord(h->ev_join[i], h->side[i])); CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join[i], 0)); }
+    CUDA_TRY(cudaEventRecord(h->ev[2], s));
+    return CF_OK;
+}
+
+extern "C" int cf_finalize_device(cf_handle* h, int nbf, const int64_t* acc, double exx, int has_d, int has_a, int has_b,
+                                  double* J, double* Kd, double* Ka, double* Kb, void* stream) {
+    if (!h || !acc || !J) return CF_ERR_BAD_ARGUMENT;
+    if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
+    cudaSetDevice(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int ns = h->nshell, ncart = h->ncart;
+    const size_t n2c = (size_t)ncart * ncart, n2p = (size_t)nbf * nbf;
+    dim3 grid2(ns, ns);
+    // J = 1/4 (raw + raw^T), K = 1/8 (raw + raw^T) * EXX   (Int4C2E.cpp:661-670)
+    finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, (const long long*)acc, h->d_scales.p, 0, 0.25, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
+                                         h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, J);
+    h->stats.n_launches_last++;
+    double* outs[3] = {Kd, Ka, Kb};
+    const int has[3] = {has_d, has_a, has_b};
+    int x = 0;
+    for (int k = 0; k < 3; k++) {
+        if (!has[k]) continue;
+        if (!outs[k]) { set_error(h, "K output missing for a density that was given"); return CF_ERR_BAD_ARGUMENT; }
+        if (exx > 0.0) {
+            finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, (const long long*)acc + (size_t)(1 + x) * n2c, h->d_scales.p, 1, 0.125 * exx,
+                                                 h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, outs[k]);
+            h->stats.n_launches_last++;
+            x++;
+        } else {
+            CUDA_TRY(cudaMemsetAsync(outs[k], 0, sizeof(double) * n2p, s));   // EXX <= 0: K returned as zeros (Int4C2E.cpp:638)
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return CF_OK;
+}
+
+extern "C" int cf_build_jk_device(cf_handle* h, int nbf, const double* Dd, const double* Da, const double* Db, double exx,
+                                  double* J, double* Kd, double* Ka, double* Kb, void* stream) {
+    if (!h) return CF_ERR_BAD_ARGUMENT;
+    cudaSetDevice(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaEventRecord(h->ev[0], s));
+    int rc = cf_accumulate_device(h, nbf, Dd, Da, Db, exx, (int64_t*)h->d_acc.p, stream);
+    if (rc != CF_OK) return rc;
+    rc = cf_finalize_device(h, nbf, (const int64_t*)h->d_acc.p, exx, Dd != nullptr, Da != nullptr, Db != nullptr, J, Kd, Ka, Kb, stream);
+    if (rc != CF_OK) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev[3], s));
+    return CF_OK;
+}
+
+static int fetch_times(cf_handle* h) {
+    float a = 0, b = 0;
+    if (cudaEventElapsedTime(&a, h->ev[0], h->ev[3]) == cudaSuccess) h->stats.ms_device_last = a;
+    if (cudaEventElapsedTime(&b, h->ev[1], h->ev[2]) == cudaSuccess) h->stats.ms_eri_last = b;
+    return CF_OK;
+}
+
+extern "C" int cf_sync_stats(cf_handle* h) {   // after a *_device call has been synchronised by the caller
+    if (!h) return CF_ERR_BAD_ARGUMENT;
+    cudaSetDevice(h->device);
+    return fetch_times(h);
+}
+
+extern "C" int cf_build_jk(cf_handle* h, int nbf, const double* Dd, const double* Da, const double* Db, double exx,
+                           double* J, double* Kd, double* Ka, double* Kb) {
+    if (!h) return CF_ERR_BAD_ARGUMENT;
+    if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
+    if (!J) { set_error(h, "J output is required"); return CF_ERR_BAD_ARGUMENT; }
+    if (!Dd && !Da && !Db) { set_error(h, "at least one density is required"); return CF_ERR_BAD_ARGUMENT; }
+    if ((Dd && !Kd) || (Da && !Ka) || (Db && !Kb)) { set_error(h, "K output missing for a density that was given"); return CF_ERR_BAD_ARGUMENT; }
+    cudaSetDevice(h->device);
+    const double t0 = now_s();
+    if (h->opt.verbose > 0) std::printf("Contracting 4c-2e repulsion integrals with 1 matrix ... ");
+    const size_t bytes = sizeof(double) * (size_t)nbf * nbf;
+    const double* src[3] = {Dd, Da, Db};
+    const double* dev[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3; k++)
+        if (src[k]) { CUDA_TRY(cudaMemcpyAsync(h->d_Dpure[k].p, src[k], bytes, cudaMemcpyHostToDevice, 0)); dev[k] = h->d_Dpure[k].p; }
+    int rc = cf_build_jk_device(h, nbf, dev[0], dev[1], dev[2], exx, h->d_out[0].p, h->d_out[1].p, h->d_out[2].p, h->d_out[3].p, nullptr);
+    if (rc != CF_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(J, h->d_out[0].p, bytes, cudaMemcpyDeviceToHost, 0));
+    double* outs[3] = {Kd, Ka, Kb};
+    for (int k = 0; k < 3; k++)
+        if (src[k]) CUDA_TRY(cudaMemcpyAsync(outs[k], h->d_out[1 + k].p, bytes, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    CUDA_TRY(cudaGetLastError());
+    fetch_times(h);
+    if (h->opt.verbose > 0) std::printf("Done in %f s\n", now_s() - t0);
+    return CF_OK;
+}
+
+// G_k = J[2 D_k] - exx K[D_k]  (GhfMultiple, Int4C2E.cpp:685-731): one J/K build per matrix for now
+extern "C" int cf_build_g_multi(cf_handle* h, int nbf, int nmat, const double* Ds, double exx, double* Gs) {
+    if (!h || !Ds || !Gs || nmat <= 0) return CF_ERR_BAD_ARGUMENT;
+    if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
+    const size_t n2 = (size_t)nbf * nbf;
+    std::vector<double> J(n2), K(n2);
+    for (int k = 0; k < nmat; k++) {
+        int rc = cf_build_jk(h, nbf, Ds + k * n2, nullptr, nullptr, exx, J.data(), K.data(), nullptr, nullptr);
+        if (rc != CF_OK) return rc;
+        // ContractInts(Dd=D) returns J[2D] and exx*K[D]
+        for (size_t i = 0; i < n2; i++) Gs[k * n2 + i] = J[i] - K[i];
+    }
+    return CF_OK;
+}

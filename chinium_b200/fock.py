@@ -1,0 +1,271 @@
+"""Python mirror of the reference's `class Int4C2E` (src/Integral/Int4C2E.h:10-50) over the C ABI.
+
+Same method names, argument meaning and error behaviour as the reference:
+    Int4C2E(basis, exx, threshold); getRepulsionDiag(output); getRepulsionLength(output);
+    getRepulsionIndices(output); getThreadPointers(nthreads, output); CalculateIntegrals(order, output);
+    ContractInts(Dd, Da, Db, nthreads, output) -> (J, Kd, Ka, Kb)     [None = the reference's 0x0 matrix]
+    ContractInts([D...], nthreads, output) -> [G...]
+Everything numerical happens in libchinium_fock.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libchinium_fock.so")
+
+
+class FockEngineError(RuntimeError):
+    pass
+
+
+class _CfBasis(C.Structure):
+    _fields_ = [("nshell", C.c_int), ("type", C.POINTER(C.c_int)), ("nprim", C.POINTER(C.c_int)),
+                ("prim_offset", C.POINTER(C.c_int)), ("exps", C.POINTER(C.c_double)),
+                ("coefs_normalized", C.POINTER(C.c_double)), ("center_xyz", C.POINTER(C.c_double)),
+                ("shell2atom", C.POINTER(C.c_int))]
+
+
+class _CfOptions(C.Structure):
+    _fields_ = [("threshold", C.c_double), ("pair_cutoff", C.c_double), ("device", C.c_int), ("rank", C.c_int),
+                ("world_size", C.c_int), ("verbose", C.c_int), ("reserved", C.c_int * 8)]
+
+
+class CfStats(C.Structure):
+    _fields_ = [("nshell", C.c_int), ("nbf", C.c_int), ("ncart", C.c_int),
+                ("shell_pairs_total", C.c_int64), ("shell_pairs_kept", C.c_int64),
+                ("canonical_quartets", C.c_int64), ("canonical_quartets_local", C.c_int64),
+                ("unique_integrals", C.c_int64), ("primitive_quartets", C.c_int64),
+                ("flops_alg_jk", C.c_double * 4), ("n_launches_last", C.c_int),
+                ("ms_device_last", C.c_double), ("ms_eri_last", C.c_double), ("fixedpoint_scale_log2", C.c_double * 2)]
+
+    def as_dict(self):
+        d = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            d[name] = list(v) if hasattr(v, "__len__") else v
+        return d
+
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """Load libchinium_fock.so; raise (never fall back) if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise FockEngineError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or make -C chinium_b200/csrc). There is no CPU fallback.")
+    L = C.CDLL(path)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.c_int
+    L.cf_create.restype = vp
+    L.cf_create.argtypes = [C.POINTER(_CfBasis), C.POINTER(_CfOptions)]
+    L.cf_destroy.argtypes = [vp]
+    L.cf_last_error.restype = C.c_char_p
+    L.cf_last_error.argtypes = [vp]
+    L.cf_get_stats.argtypes = [vp, C.POINTER(CfStats)]
+    L.cf_nbf.argtypes = [vp]
+    L.cf_get_repulsion_diag.argtypes = [vp, dp]
+    L.cf_build_jk.argtypes = [vp, ip, dp, dp, dp, C.c_double, dp, dp, dp, dp]
+    L.cf_build_jk_device.argtypes = [vp, ip, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp]
+    L.cf_acc_len.restype = C.c_size_t
+    L.cf_acc_len.argtypes = [vp, ip]
+    L.cf_accumulate_device.argtypes = [vp, ip, vp, vp, vp, C.c_double, vp, vp]
+    L.cf_finalize_device.argtypes = [vp, ip, vp, C.c_double, ip, ip, ip, vp, vp, vp, vp, vp]
+    L.cf_build_g_multi.argtypes = [vp, ip, ip, dp, C.c_double, dp]
+    L.cf_device_info.argtypes = [ip, C.c_char_p, ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]
+    L.cf_measure_fp64_peak.argtypes = [ip, dp]
+    L.cf_sync_stats.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _dptr(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _fmat(a, nbf):
+    if a is None:
+        return None
+    a = np.asfortranarray(a, dtype=np.float64)
+    if a.size == 0:
+        return None  # the reference's 0x0 "absent" matrix (Int4C2E.cpp:608-610)
+    if a.shape != (nbf, nbf):
+        raise FockEngineError(f"density has shape {a.shape}, expected ({nbf},{nbf})")
+    return a
+
+
+class Int4C2E:
+    """Drop-in mirror of the reference class; `basis` is a chinium_b200.inputs.FlatBasis (the Mwfn stand-in)."""
+
+    def __init__(self, basis, exx: float = 1.0, threshold: float = -1.0, device: int = -1, rank: int = 0,
+                 world_size: int = 1, pair_cutoff: float = 0.0):
+        self.MWFN = basis
+        self.EXX = float(exx)            # read at contract time, like the reference (SelfConsistentField.cpp:48)
+        self.Threshold = float(threshold)
+        self._opts = dict(device=device, rank=rank, world_size=world_size, pair_cutoff=pair_cutoff)
+        self._h = None
+        self._lib = load_library()
+        self.RepulsionDiags = None
+        self.RepulsionLength = None
+        self.ShellQuartetLength = None
+        self._stage = 0
+
+    # ---- handle management -----------------------------------------------------------------------
+    def _ensure(self, output=0):
+        if self._h is not None:
+            return
+        fb = self.MWFN
+        keep = dict(type=np.ascontiguousarray(fb.type, np.int32), nprim=np.ascontiguousarray(fb.nprim, np.int32),
+                    off=np.ascontiguousarray(fb.prim_offset, np.int32), exps=np.ascontiguousarray(fb.exps, np.float64),
+                    coefs=np.ascontiguousarray(fb.coefs_normalized, np.float64),
+                    xyz=np.ascontiguousarray(fb.center_xyz, np.float64).reshape(-1),
+                    s2a=np.ascontiguousarray(fb.shell2atom, np.int32))
+        ipt = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        b = _CfBasis(fb.nshell, ipt(keep["type"]), ipt(keep["nprim"]), ipt(keep["off"]), _dptr(keep["exps"]),
+                     _dptr(keep["coefs"]), _dptr(keep["xyz"]), ipt(keep["s2a"]))
+        o = _CfOptions()
+        o.threshold = self.Threshold
+        o.pair_cutoff = self._opts["pair_cutoff"]
+        o.device = self._opts["device"]
+        o.rank = self._opts["rank"]
+        o.world_size = self._opts["world_size"]
+        o.verbose = int(output)
+        h = self._lib.cf_create(C.byref(b), C.byref(o))
+        if not h:
+            raise FockEngineError(self._lib.cf_last_error(None).decode())
+        self._h = h
+        self.nbf = self._lib.cf_nbf(h)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FockEngineError("chinium_fock error %d: %s" % (rc, self._lib.cf_last_error(self._h).decode()))
+
+    def close(self):
+        if self._h is not None:
+            self._lib.cf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stats(self) -> dict:
+        self._ensure()
+        s = CfStats()
+        self._check(self._lib.cf_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    # ---- the reference's five setup stages (SelfConsistentField.cpp:49-53) -----------------------
+    def getRepulsionDiag(self, output=0):
+        self._ensure(output)
+        d = np.zeros((self.nbf, self.nbf), order="F")
+        self._check(self._lib.cf_get_repulsion_diag(self._h, _dptr(d)))
+        self.RepulsionDiags = (d, None)   # only Diag1212 is ever consumed (Int4C2E.cpp:515,544)
+        self._stage = max(self._stage, 1)
+
+    def getRepulsionLength(self, output=0):
+        assert self.RepulsionDiags is not None, "Diagonal elements of repulsion integrals are missing!"  # Int4C2E.cpp:514
+        st = self.stats
+        self.RepulsionLength = st["unique_integrals"]
+        self.ShellQuartetLength = st["canonical_quartets"]
+        if output > 0:
+            nb, nsh = st["nbf"], st["nshell"]
+            print("Before screening: %d integrals and %d shell quartets" % (
+                nb * (nb + 1) * (nb * (nb + 1) // 2 + 1) // 4, nsh * (nsh + 1) * (nsh * (nsh + 1) // 2 + 1) // 4))
+            print("After screening: %d integrals and %d shell quartets" % (self.RepulsionLength, self.ShellQuartetLength))
+            print("Memory needed for 4c-2e repulsion integrals and their indices: 0 GB (direct build; the reference "
+                  "would need %f GB)" % (self.RepulsionLength * 16.0 / 1024 ** 3))
+        self._stage = max(self._stage, 2)
+
+    def getRepulsionIndices(self, output=0):
+        assert self._stage >= 2, "Shell quartet counts are missing!"
+        self._stage = max(self._stage, 3)   # quartet lists are implicit (pair x pair tiles), nothing to store
+
+    def getThreadPointers(self, nthreads=1, output=0):
+        assert self._stage >= 3, "Shell indices are missing!"                               # Int4C2E.cpp:555
+        self._stage = max(self._stage, 4)   # the static partition is (rank, world_size) of the handle
+
+    def CalculateIntegrals(self, order=0, output=0):
+        if order != 0:
+            raise FockEngineError("derivative ERIs (order %d) are outside this engine's scope" % order)
+        self._ensure(output)
+        self._stage = max(self._stage, 5)
+
+    # ---- the hot call -------------------------------------------------------------------------------
+    def ContractInts(self, *args):
+        """ContractInts(Dd, Da, Db, nthreads=1, output=0) or ContractInts([D...], nthreads=1, output=0)."""
+        if len(args) >= 1 and isinstance(args[0], (list, tuple)):
+            return self._contract_multi(list(args[0]))
+        Dd, Da, Db = (list(args) + [None, None, None])[:3]
+        return self._contract(Dd, Da, Db)
+
+    def _contract(self, Dd, Da, Db):
+        self._ensure()
+        n = self.nbf
+        Dd, Da, Db = _fmat(Dd, n), _fmat(Da, n), _fmat(Db, n)
+        J = np.zeros((n, n), order="F")
+        Ks = [np.zeros((n, n), order="F") if D is not None else None for D in (Dd, Da, Db)]
+        self._check(self._lib.cf_build_jk(self._h, n, _dptr(Dd), _dptr(Da), _dptr(Db), self.EXX, _dptr(J),
+                                          _dptr(Ks[0]), _dptr(Ks[1]), _dptr(Ks[2])))
+        # the reference returns all-zero nbf x nbf matrices for absent K's (Int4C2E.cpp:616-619)
+        Ks = [k if k is not None else np.zeros((n, n), order="F") for k in Ks]
+        return J, Ks[0], Ks[1], Ks[2]
+
+    def _contract_multi(self, Ds):
+        self._ensure()
+        n = self.nbf
+        stack = np.ascontiguousarray(np.stack([np.asfortranarray(D, dtype=np.float64).T for D in Ds]))  # each block col-major
+        out = np.zeros_like(stack)
+        self._check(self._lib.cf_build_g_multi(self._h, n, len(Ds), _dptr(stack), self.EXX, _dptr(out)))
+        return [np.asfortranarray(out[k].T) for k in range(len(Ds))]
+
+    # ---- device-resident / multi-GPU building blocks (plain pointers: e.g. torch tensors' data_ptr()) ---
+    def acc_len(self, nk):
+        self._ensure()
+        return int(self._lib.cf_acc_len(self._h, nk))
+
+    def accumulate_device(self, Dd_ptr, Da_ptr, Db_ptr, acc_ptr, stream=None):
+        self._ensure()
+        self._check(self._lib.cf_accumulate_device(self._h, self.nbf, Dd_ptr, Da_ptr, Db_ptr, self.EXX, acc_ptr, stream))
+
+    def finalize_device(self, acc_ptr, has, J_ptr, Kd_ptr, Ka_ptr, Kb_ptr, stream=None):
+        self._ensure()
+        self._check(self._lib.cf_finalize_device(self._h, self.nbf, acc_ptr, self.EXX, int(has[0]), int(has[1]), int(has[2]),
+                                                 J_ptr, Kd_ptr, Ka_ptr, Kb_ptr, stream))
+
+    def build_jk_device(self, Dd_ptr, Da_ptr, Db_ptr, J_ptr, Kd_ptr, Ka_ptr, Kb_ptr, stream=None):
+        self._ensure()
+        self._check(self._lib.cf_build_jk_device(self._h, self.nbf, Dd_ptr, Da_ptr, Db_ptr, self.EXX, J_ptr, Kd_ptr, Ka_ptr,
+                                                 Kb_ptr, stream))
+
+    def sync_stats(self):
+        self._lib.cf_sync_stats(self._h)
+        return self.stats
+
+
+def measure_fp64_peak(device=-1) -> float:
+    L = load_library()
+    v = C.c_double(0)
+    rc = L.cf_measure_fp64_peak(device, C.byref(v))
+    if rc != 0:
+        raise FockEngineError("cf_measure_fp64_peak failed: %s" % L.cf_last_error(None).decode())
+    return v.value
+
+
+def device_info(device=-1):
+    L = load_library()
+    name = C.create_string_buffer(128)
+    sm, ma, mi = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = L.cf_device_info(device, name, 128, C.byref(sm), C.byref(ma), C.byref(mi))
+    if rc != 0:
+        raise FockEngineError("no CUDA device: %s" % L.cf_last_error(None).decode())
+    return dict(name=name.value.decode(), sm_count=sm.value, cc=(ma.value, mi.value))
