@@ -170,18 +170,22 @@ __global__ void pure_to_cart_kernel(int nshell, int nbf, int ncart, const double
     }
 }
 
-// out_pure(block) = factor * C_a [ (acc + acc^T) / scale ] C_b^T ; integer sum first (exact), one conversion
+// out_pure(block) = factor * C_a [ (acc + acc^T) / scale ] C_b^T ; integer sum first (exact), one conversion.
+// Only blocks sb <= sa (and m >= n inside diagonal blocks) are computed and mirrored, so the output is EXACTLY
+// symmetric like the reference's 1/4 (raw + raw^T) (Int4C2E.cpp:661-664).
 __global__ void finalize_kernel(int nbf, int ncart, const long long* __restrict__ acc, const double* __restrict__ scales, int which_scale,
                                 double factor, const double* __restrict__ ctrans, const int* __restrict__ ct_off,
                                 const int* __restrict__ bf_off, const int* __restrict__ cao_off, const int* __restrict__ nfun,
                                 const int* __restrict__ ncsh, double* __restrict__ out) {
     const int sa = blockIdx.x, sb = blockIdx.y;
+    if (sb > sa) return;
     const int na = nfun[sa], nb = nfun[sb], nca = ncsh[sa], ncb = ncsh[sb];
     const double* Ca = ctrans + ct_off[sa];
     const double* Cb = ctrans + ct_off[sb];
     const double f = factor / scales[which_scale];
     for (int e = threadIdx.x; e < na * nb; e += blockDim.x) {
         const int m = e / nb, n = e % nb;
+        if (sa == sb && n > m) continue;
         double s = 0.0;
         for (int x = 0; x < nca; x++) {
             const double cam = Ca[m * nca + x];
@@ -192,7 +196,9 @@ __global__ void finalize_kernel(int nbf, int ncart, const long long* __restrict_
                 s = fma(cam * Cb[n * ncb + y], (double)v, s);
             }
         }
-        out[(size_t)(bf_off[sb] + n) * nbf + bf_off[sa] + m] = s * f;
+        s *= f;
+        out[(size_t)(bf_off[sb] + n) * nbf + bf_off[sa] + m] = s;
+        out[(size_t)(bf_off[sa] + m) * nbf + bf_off[sb] + n] = s;
     }
 }
 
@@ -225,8 +231,9 @@ __global__ void scales_kernel(const double* __restrict__ partial, int nblk, int 
     int ej, ek;
     frexp(fmax(bj, 1e-300), &ej);
     frexp(fmax(bk, 1e-300), &ek);
-    scales[0] = ldexp(1.0, 62 - ej);
-    scales[1] = ldexp(1.0, 62 - ek);
+    // zero / tiny densities: cap the exponent so the scale stays finite (contributions are then exactly 0 anyway)
+    scales[0] = ldexp(1.0, min(62 - ej, 512));
+    scales[1] = ldexp(1.0, min(62 - ek, 512));
     scales[2] = bj;
     scales[3] = bk;
 }
@@ -705,6 +712,7 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
     const int ns = h->nshell, ncart = h->ncart;
     const size_t n2c = (size_t)ncart * ncart;
     h->stats.n_launches_last = 0;
+    CUDA_TRY(cudaEventRecord(h->ev[0], s));
     dim3 grid2(ns, ns);
     // total density 2Dd + Da + Db (Int4C2E.cpp:612-615) and the exchange densities, in the Cartesian working basis
     pure_to_cart_kernel<<<grid2, 64, 0, s>>>(ns, nbf, ncart, Dd, Da, Db, 2.0, 1.0, 1.0, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
@@ -729,8 +737,10 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
     CUDA_TRY(cudaStreamSynchronize(s));
     h->stats.fixedpoint_scale_log2[0] = std::log2(scales[0]);
     h->stats.fixedpoint_scale_log2[1] = std::log2(scales[1]);
-    if (!(scales[0] >= 0x1p30) || (nk > 0 && !(scales[1] >= 0x1p30))) {
-        set_error(h, "fixed-point accumulator range exceeded: the density is too large for 1e-10 absolute accuracy in 64 bits");
+    // 62 bits below the rigorous bound are always available, i.e. ~1e-18 RELATIVE to the largest possible element;
+    // the only way to leave the representable range is a non-finite or absurdly large density
+    if (!(scales[0] > 0x1p-900) || !std::isfinite(scales[2]) || !std::isfinite(scales[3])) {
+        set_error(h, "fixed-point accumulator range exceeded: density contains non-finite or astronomically large entries");
         return CF_ERR_RANGE;
     }
     CUDA_TRY(cudaEventRecord(h->ev[1], s));
@@ -787,6 +797,7 @@ extern "C" int cf_finalize_device(cf_handle* h, int nbf, const int64_t* acc, dou
         }
     }
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev[3], s));
     return CF_OK;
 }
 
@@ -794,20 +805,17 @@ extern "C" int cf_build_jk_device(cf_handle* h, int nbf, const double* Dd, const
                                   double* J, double* Kd, double* Ka, double* Kb, void* stream) {
     if (!h) return CF_ERR_BAD_ARGUMENT;
     cudaSetDevice(h->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    CUDA_TRY(cudaEventRecord(h->ev[0], s));
     int rc = cf_accumulate_device(h, nbf, Dd, Da, Db, exx, (int64_t*)h->d_acc.p, stream);
     if (rc != CF_OK) return rc;
     rc = cf_finalize_device(h, nbf, (const int64_t*)h->d_acc.p, exx, Dd != nullptr, Da != nullptr, Db != nullptr, J, Kd, Ka, Kb, stream);
-    if (rc != CF_OK) return rc;
-    CUDA_TRY(cudaEventRecord(h->ev[3], s));
-    return CF_OK;
+    return rc;
 }
 
 static int fetch_times(cf_handle* h) {
     float a = 0, b = 0;
     if (cudaEventElapsedTime(&a, h->ev[0], h->ev[3]) == cudaSuccess) h->stats.ms_device_last = a;
     if (cudaEventElapsedTime(&b, h->ev[1], h->ev[2]) == cudaSuccess) h->stats.ms_eri_last = b;
+    (void)cudaGetLastError();   // events not recorded yet are not an error worth keeping
     return CF_OK;
 }
 
@@ -842,6 +850,50 @@ extern "C" int cf_build_jk(cf_handle* h, int nbf, const double* Dd, const double
     CUDA_TRY(cudaGetLastError());
     fetch_times(h);
     if (h->opt.verbose > 0) std::printf("Done in %f s\n", now_s() - t0);
+    return CF_OK;
+}
+
+// Per-class-pair timing of the last densities' build (serialised, CUDA events): the measurement behind the
+// per-kernel roofline table.  rows of 6 doubles: bra class, ket class, quartets, ms, F_alg (for nk), group size
+extern "C" int cf_profile_tasks(cf_handle* h, int nbf, const double* Dd_dev, const double* Da_dev, const double* Db_dev, double exx,
+                                double* rows, int max_rows, int* nrows) {
+    if (!h || !rows || !nrows) return CF_ERR_BAD_ARGUMENT;
+    int rc = cf_accumulate_device(h, nbf, Dd_dev, Da_dev, Db_dev, exx, (int64_t*)h->d_acc.p, nullptr);   // sets densities + scales
+    if (rc != CF_OK) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    double scales[4];
+    CUDA_TRY(cudaMemcpy(scales, h->d_scales.p, sizeof(scales), cudaMemcpyDeviceToHost));
+    const double* dk[3]; int slot[3];
+    const int nk = exchange_list(Dd_dev, Da_dev, Db_dev, exx, dk, slot);
+    const size_t n2c = (size_t)h->ncart * h->ncart;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int n = 0;
+    for (ClassPairTask* t : h->tasks) {
+        if (n >= max_rows) break;
+        QuartetTask qt{};
+        qt.rank = h->opt.rank; qt.world = h->opt.world_size; qt.ncart = h->ncart; qt.nk = nk;
+        qt.Dtot = h->d_Dcart[0].p;
+        for (int x = 0; x < nk; x++) { qt.Dk[x] = h->d_Dcart[1 + x].p; qt.accK[x] = h->d_acc.p + (size_t)(1 + x) * n2c; }
+        qt.accJ = h->d_acc.p; qt.scaleJ = scales[0]; qt.scaleK = scales[1]; qt.prim_cut = 1e-22;
+        fill_rys(qt, h);
+        float best = 1e30f;
+        for (int rep = 0; rep < 2; rep++) {
+            cudaEventRecord(e0, 0);
+            rc = launch_task(h, t, qt, 0, 0);
+            cudaEventRecord(e1, 0);
+            if (rc != CF_OK) return rc;
+            CUDA_TRY(cudaEventSynchronize(e1));
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            best = std::min(best, ms);
+        }
+        double* r = rows + 6 * n;
+        r[0] = t->bra; r[1] = t->ket; r[2] = (double)t->nquartet / h->opt.world_size; r[3] = best;
+        r[4] = (t->flops_eri + 2.0 * (2 + 4 * nk) * t->nfun_sum) / h->opt.world_size; r[5] = t->G;
+        n++;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *nrows = n;
     return CF_OK;
 }
 

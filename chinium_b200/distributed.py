@@ -1,0 +1,82 @@
+"""Multi-GPU J/K build: one process per GPU, static cost-balanced partition of the quartet work, partial
+accumulators summed with ONE integer all-reduce over NCCL/NVLink.
+
+PyTorch is plumbing only (device buffers, streams, torch.distributed); all arithmetic is in
+libchinium_fock.so.  Because the accumulators are 64-bit fixed point and integer addition is
+associative, the all-reduced result is bit-identical to the single-GPU result.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .fock import Int4C2E, FockEngineError
+
+
+class DistributedInt4C2E:
+    """Same `ContractInts` contract as `Int4C2E`, computed by `world_size` GPUs."""
+
+    def __init__(self, basis, exx=1.0, threshold=-1.0, device=None, group=None):
+        if not torch.cuda.is_available():
+            raise FockEngineError("no CUDA device (this engine has no CPU fallback)")
+        self.group = group
+        self.distributed = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.eng = Int4C2E(basis, exx, threshold, device=self.device.index, rank=self.rank, world_size=self.world)
+        self.eng._ensure()
+        self.nbf = self.eng.nbf
+        n = self.nbf
+        self._D = [torch.empty((n, n), dtype=torch.float64, device=self.device) for _ in range(3)]
+        self._out = [torch.empty((n, n), dtype=torch.float64, device=self.device) for _ in range(4)]
+        self._acc = torch.empty(self.eng.acc_len(3), dtype=torch.int64, device=self.device)
+        self._pin_in = [torch.empty((n, n), dtype=torch.float64).pin_memory() for _ in range(3)]
+        self._pin_out = [torch.empty((n, n), dtype=torch.float64).pin_memory() for _ in range(4)]
+
+    @property
+    def EXX(self):
+        return self.eng.EXX
+
+    @EXX.setter
+    def EXX(self, v):
+        self.eng.EXX = float(v)
+
+    def build_device(self, present):
+        """Densities already in self._D (column-major, i.e. the transposed torch view is irrelevant for
+        symmetric D); results land in self._out.  Enqueued on torch's current stream."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        ptr = lambda t, on: t.data_ptr() if on else None
+        nk = sum(present) if self.eng.EXX > 0 else 0
+        acc = self._acc[: self.eng.acc_len(nk)]
+        self.eng.accumulate_device(ptr(self._D[0], present[0]), ptr(self._D[1], present[1]), ptr(self._D[2], present[2]),
+                                   acc.data_ptr(), stream)
+        if self.world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+        self.eng.finalize_device(acc.data_ptr(), present, self._out[0].data_ptr(), ptr(self._out[1], present[0]),
+                                 ptr(self._out[2], present[1]), ptr(self._out[3], present[2]), stream)
+
+    def ContractInts(self, Dd=None, Da=None, Db=None, nthreads=1, output=0):
+        """Host matrices in, host matrices out (the reference's call); H2D / D2H through pinned buffers."""
+        n = self.nbf
+        present = [D is not None and np.size(D) > 0 for D in (Dd, Da, Db)]
+        for k, D in enumerate((Dd, Da, Db)):
+            if present[k]:
+                self._pin_in[k].numpy()[...] = np.asarray(D, dtype=np.float64).T   # torch row-major == col-major of D
+                self._D[k].copy_(self._pin_in[k], non_blocking=True)
+        self.build_device(present)
+        res = []
+        for k in range(4):
+            if k == 0 or present[k - 1]:
+                self._pin_out[k].copy_(self._out[k], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        for k in range(4):
+            if k == 0 or present[k - 1]:
+                res.append(np.asfortranarray(self._pin_out[k].numpy().T.copy()))
+            else:
+                res.append(np.zeros((n, n), order="F"))
+        return tuple(res)
+
+    def close(self):
+        self.eng.close()

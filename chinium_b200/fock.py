@@ -81,6 +81,7 @@ def load_library(path: str = LIB_PATH):
     L.cf_device_info.argtypes = [ip, C.c_char_p, ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]
     L.cf_measure_fp64_peak.argtypes = [ip, dp]
     L.cf_sync_stats.argtypes = [vp]
+    L.cf_profile_tasks.argtypes = [vp, ip, vp, vp, vp, C.c_double, dp, ip, C.POINTER(ip)]
     _lib = L
     return L
 
@@ -246,6 +247,16 @@ class Int4C2E:
         self._ensure()
         self._check(self._lib.cf_build_jk_device(self._h, self.nbf, Dd_ptr, Da_ptr, Db_ptr, self.EXX, J_ptr, Kd_ptr, Ka_ptr,
                                                  Kb_ptr, stream))
+
+    def profile_tasks(self, Dd_ptr, Da_ptr, Db_ptr):
+        """-> list of dicts (bra, ket class names, quartets, ms, flops_alg, group): every class-pair kernel timed alone."""
+        self._ensure()
+        rows = np.zeros((64, 6))
+        n = C.c_int(0)
+        self._check(self._lib.cf_profile_tasks(self._h, self.nbf, Dd_ptr, Da_ptr, Db_ptr, self.EXX, _dptr(rows), 64, C.byref(n)))
+        names = ["ss", "ps", "pp", "ds", "dp", "dd", "fs", "fp", "fd", "ff"]
+        return [dict(bra=names[int(r[0])], ket=names[int(r[1])], quartets=int(r[2]), ms=float(r[3]), flops_alg=float(r[4]),
+                     group=int(r[5])) for r in rows[:n.value]]
 
     def sync_stats(self):
         self._lib.cf_sync_stats(self._h)

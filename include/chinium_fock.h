@@ -40,7 +40,7 @@ extern "C" {
 #define CF_ERR_RANGE 5          /* fixed-point accumulator range exceeded    */
 #define CF_ERR_STATE 6          /* calls out of order (reference asserts: Int4C2E.cpp:514,538,555) */
 
-#define CF_MAX_L 4              /* highest shell angular momentum the device kernels accept (g) */
+#define CF_MAX_L 3              /* highest shell angular momentum the device kernels accept (f) */
 
 /* Flat basis description; replaces __Make_Basis_Set__ (src/Integral/Macro.h:1-25).
  * All pointers are HOST pointers, borrowed only for the duration of cf_create. */
@@ -132,6 +132,13 @@ int cf_finalize_device(cf_handle* h, int nbf, const int64_t* acc, double exx,
  * GhfMultiple (Int4C2E.cpp:685-745): G_k = J[2 D_k] - exx * K[D_k].  HOST pointers,
  * Ds/Gs are nmat consecutive nbf x nbf col-major matrices. */
 int cf_build_g_multi(cf_handle* h, int nbf, int nmat, const double* Ds, double exx, double* Gs);
+
+/* After the caller has synchronised the stream of a *_device call: refresh ms_device_last / ms_eri_last. */
+int cf_sync_stats(cf_handle* h);
+/* Developer/benchmark aid: run every (bra class, ket class) kernel alone and time it with CUDA events.
+ * DEVICE density pointers. rows: 6 doubles each = bra class, ket class, quartets, ms, F_alg, threads per quartet. */
+int cf_profile_tasks(cf_handle* h, int nbf, const double* Dd, const double* Da, const double* Db, double exx,
+                     double* rows, int max_rows, int* nrows);
 
 /* Library/device facts for logs and benchmarks. */
 int cf_device_info(int device, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor);

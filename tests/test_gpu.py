@@ -1,0 +1,239 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA engine, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  Tolerances are north_star's: every J/K element within 1e-10 absolute,
+converged SCF energies within 1e-8 Eh."""
+import os
+
+import numpy as np
+import pytest
+
+import scf_harness as H
+from chinium_b200.inputs import load_fixture_molecule
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def Int4C2E():
+    from chinium_b200 import Int4C2E as cls
+    from chinium_b200.fock import device_info
+    info = device_info()
+    assert info["cc"][0] == 10, info
+    return cls
+
+
+def _engine(Int4C2E, fb, exx=1.0, thr=-1.0, **kw):
+    e = Int4C2E(fb, exx, thr, **kw)
+    # the reference's setup sequence (SelfConsistentField.cpp:49-53)
+    e.getRepulsionDiag(0); e.getRepulsionLength(0); e.getRepulsionIndices(0); e.getThreadPointers(1, 0); e.CalculateIntegrals(0, 0)
+    return e
+
+
+@pytest.mark.parametrize("name", ["h2o", "hf_tz", "bo3h3"])
+def test_jk_parity_rhf_uhf_rohf(Int4C2E, oracle, name):
+    mol, fb = load_fixture_molecule(name)
+    n = fb.nbf
+    Dd, Da, Db = (H.random_symmetric_density(n, s) for s in (0, 1, 2))
+    eng = _engine(Int4C2E, fb)
+    for dens in ((Dd, None, None), (None, Da, Db), (Dd, Da, Db)):      # RHF, UHF, ROHF-type calls
+        got = eng.ContractInts(*dens, 1, 0)
+        ref = oracle.direct_jk(fb, *dens)[:4]
+        for g, r in zip(got, ref):
+            if r is None:
+                assert np.abs(g).max() == 0.0          # absent density -> zero matrix (Int4C2E.cpp:616-619)
+            else:
+                assert np.abs(g - r).max() < TOL
+        assert np.abs(got[0] - got[0].T).max() == 0.0  # exactly symmetric outputs
+    eng.close()
+
+
+def test_golden_fixture_and_reference_stored_path(Int4C2E, oracle):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "jk_golden.npz"))
+    for name in ("h2o", "hf_tz"):
+        mol, fb = load_fixture_molecule(name)
+        eng = _engine(Int4C2E, fb)
+        D, Da, Db = (H.random_symmetric_density(fb.nbf, s) for s in (0, 1, 2))
+        J, K, _, _ = eng.ContractInts(D, None, None, 1, 0)
+        assert np.abs(J - g[name + "_J"]).max() < TOL and np.abs(K - g[name + "_K"]).max() < TOL
+        J2, _, Ka, Kb = eng.ContractInts(None, Da, Db, 1, 0)
+        assert np.abs(J2 - g[name + "_J_ab"]).max() < TOL
+        assert np.abs(Ka - g[name + "_Ka"]).max() < TOL and np.abs(Kb - g[name + "_Kb"]).max() < TOL
+        assert eng.RepulsionLength == int(g[name + "_counts"][0])    # the reference's RepulsionLength
+        eng.close()
+
+
+def test_repulsion_diag(Int4C2E, oracle):
+    mol, fb = load_fixture_molecule("hf_tz")
+    eng = _engine(Int4C2E, fb)
+    assert np.abs(eng.RepulsionDiags[0] - oracle.repulsion_diag(fb)).max() < TOL
+    eng.close()
+
+
+def test_exx_semantics(Int4C2E, oracle):
+    mol, fb = load_fixture_molecule("bo3h3")
+    D = H.random_symmetric_density(fb.nbf, 0)
+    eng = _engine(Int4C2E, fb, exx=1.0)
+    eng.EXX = 0.2                                   # overwritten after construction, read at contract time
+    J, K, _, _ = eng.ContractInts(D, None, None, 1, 0)
+    Jo, Ko, _, _, _ = oracle.direct_jk(fb, D, exx=0.2)
+    assert np.abs(J - Jo).max() < TOL and np.abs(K - Ko).max() < TOL
+    eng.EXX = 0.0                                   # pure DFT: J only, K zeros (Int4C2E.cpp:638)
+    J0, K0, _, _ = eng.ContractInts(D, None, None, 1, 0)
+    assert np.abs(J0 - Jo).max() < TOL and np.abs(K0).max() == 0.0
+    eng.close()
+
+
+def test_edge_cases(Int4C2E):
+    from chinium_b200 import FockEngineError
+    mol, fb = load_fixture_molecule("h2o")
+    eng = _engine(Int4C2E, fb)
+    n = fb.nbf
+    # 0x0 matrices mean "absent" (Int4C2E.cpp:608-610)
+    J, Kd, Ka, Kb = eng.ContractInts(np.eye(n), np.zeros((0, 0)), np.zeros((0, 0)), 1, 0)
+    assert np.abs(Ka).max() == 0 and np.abs(Kb).max() == 0 and np.abs(J).max() > 0
+    # zero density -> zero J/K
+    J, Kd, _, _ = eng.ContractInts(np.zeros((n, n)), None, None, 1, 0)
+    assert np.abs(J).max() == 0 and np.abs(Kd).max() == 0
+    with pytest.raises(FockEngineError):
+        eng.ContractInts(np.eye(n + 1), None, None, 1, 0)
+    with pytest.raises(FockEngineError):
+        eng.ContractInts(None, None, None, 1, 0)
+    # non-symmetric input is symmetrised defensively (the reference assumes symmetric D)
+    A = np.random.default_rng(5).uniform(-1, 1, (n, n))
+    J1, K1, _, _ = eng.ContractInts(A, None, None, 1, 0)
+    J2, K2, _, _ = eng.ContractInts(0.5 * (A + A.T), None, None, 1, 0)
+    assert np.abs(J1 - J2).max() < 1e-12 and np.abs(K1 - K2).max() < 1e-12
+    # huge density: the fixed-point scale follows the density, so relative accuracy is kept
+    Jh, Kh, _, _ = eng.ContractInts(1e6 * np.eye(n), None, None, 1, 0)
+    J1, K1, _, _ = eng.ContractInts(np.eye(n), None, None, 1, 0)
+    assert np.abs(Jh - 1e6 * J1).max() < 1e-6 and np.abs(Kh - 1e6 * K1).max() < 1e-6
+    with pytest.raises(FockEngineError):
+        eng.ContractInts(np.full((n, n), np.nan), None, None, 1, 0)
+    eng.close()
+
+
+def test_size_independent_properties_c18(Int4C2E):
+    """Full-size BASELINE config: linearity, symmetry, bit-stability, partition independence."""
+    mol, fb = load_fixture_molecule("c18")
+    n = fb.nbf
+    D1, D2 = H.random_symmetric_density(n, 0), H.random_symmetric_density(n, 7)
+    full = _engine(Int4C2E, fb, pair_cutoff=1e-300)     # nothing dropped: the reference's unscreened counts
+    st = full.stats
+    assert st["canonical_quartets"] == 132690195 and st["unique_integrals"] == 10668085485
+    assert abs(st["flops_alg_jk"][1] / 2.365e12 - 1) < 5e-3
+    full.close()
+    eng = _engine(Int4C2E, fb)
+    assert eng.stats["canonical_quartets"] <= 132690195
+    J1, K1, _, _ = eng.ContractInts(D1, None, None, 1, 0)
+    J1b, K1b, _, _ = eng.ContractInts(D1, None, None, 1, 0)
+    assert (J1 == J1b).all() and (K1 == K1b).all()          # bit-stable run to run
+    J2, K2, _, _ = eng.ContractInts(D2, None, None, 1, 0)
+    J3, K3, _, _ = eng.ContractInts(0.5 * D1 - 2.0 * D2, None, None, 1, 0)
+    assert np.abs(J3 - (0.5 * J1 - 2.0 * J2)).max() < TOL   # linearity
+    assert np.abs(K3 - (0.5 * K1 - 2.0 * K2)).max() < TOL
+    assert np.abs(J1 - J1.T).max() == 0 and np.abs(K1 - K1.T).max() == 0
+    # energy-like checksum: sum D1 o J[D2] == sum D2 o J[D1]
+    assert abs(np.sum(D1 * J2) - np.sum(D2 * J1)) < 1e-9
+    assert abs(np.sum(D1 * K2) - np.sum(D2 * K1)) < 1e-9
+    eng.close()
+
+
+def test_sampled_blocks_c18(Int4C2E, oracle):
+    """c18 / cc-pVTZ at full size: exact oracle J and K blocks for a sample of shell pairs (s..f)."""
+    mol, fb = load_fixture_molecule("c18")
+    n = fb.nbf
+    D = H.random_symmetric_density(n, 0)
+    eng = _engine(Int4C2E, fb)
+    J, K, _, _ = eng.ContractInts(D, None, None, 1, 0)
+    # shells of atom 0: s s s s p p p d d f ; pick pairs covering the classes, on near and far atoms
+    per_atom = fb.nshell // 18
+    for sa, sb in ((0, 0), (per_atom * 9 + 4, 2), (8, per_atom * 5 + 7), (9, per_atom * 17 + 9), (per_atom * 3 + 9, 5)):
+        Jb, Kb = oracle.jk_block(fb, 2 * D, D, sa, sb)
+        ia, ib = fb.shell2bf[sa], fb.shell2bf[sb]
+        assert np.abs(Jb - J[ia:ia + fb.nfun[sa], ib:ib + fb.nfun[sb]]).max() < TOL, (sa, sb)
+        assert np.abs(Kb - K[ia:ia + fb.nfun[sa], ib:ib + fb.nfun[sb]]).max() < TOL, (sa, sb)
+    eng.close()
+
+
+def test_partition_independence_bitwise(Int4C2E):
+    """Two-rank partition summed in integers == single-rank result, bit for bit (multi-GPU path)."""
+    import torch
+    mol, fb = load_fixture_molecule("bo3h3")
+    n = fb.nbf
+    D = torch.from_numpy(H.random_symmetric_density(n, 0)).cuda()
+    outs = []
+    for world in (1, 2, 3):
+        acc_sum = None
+        engs = []
+        for r in range(world):
+            e = Int4C2E(fb, 1.0, -1.0, rank=r, world_size=world)
+            acc = torch.zeros(e.acc_len(1), dtype=torch.int64, device="cuda")
+            e.accumulate_device(D.data_ptr(), None, None, acc.data_ptr(), None)
+            torch.cuda.synchronize()
+            acc_sum = acc if acc_sum is None else acc_sum + acc
+            engs.append(e)
+        J = torch.empty((n, n), dtype=torch.float64, device="cuda"); K = torch.empty_like(J)
+        engs[0].finalize_device(acc_sum.data_ptr(), (1, 0, 0), J.data_ptr(), K.data_ptr(), None, None, None)
+        torch.cuda.synchronize()
+        outs.append((J.cpu().numpy().copy(), K.cpu().numpy().copy()))
+        for e in engs:
+            e.close()
+    for J, K in outs[1:]:
+        assert (J == outs[0][0]).all() and (K == outs[0][1]).all()
+
+
+def test_scf_energy_sn2_golden(Int4C2E, oracle):
+    """RHF/cc-pVDZ CH3ClF-: the engine inside the SCF loop reproduces Chinium's recorded energy
+    (tools/sn2/sn2.cnm.log:204) and the oracle's SCF energy from the same guess to 1e-8 Eh."""
+    mol, fb = load_fixture_molecule("sn2")
+    S, T, V = oracle.one_electron(fb, mol.Z, mol.xyz_bohr)
+    enuc = H.nuclear_repulsion(mol.Z, mol.xyz_bohr)
+    eng = _engine(Int4C2E, fb)
+    E_gpu, *_ = H.rhf(S, T + V, 18, lambda d, a, b: eng.ContractInts(d, a, b, 1, 0), enuc)
+    h = oracle.store_build(fb)
+    E_cpu, *_ = H.rhf(S, T + V, 18, lambda d, a, b: oracle.store_contract(h, fb.nbf, d, a, b), enuc)
+    oracle.store_free(h)
+    eng.close()
+    assert abs(E_gpu - E_cpu) < 1e-8
+    assert abs(E_gpu - (-598.514802895)) < 1e-7
+
+
+def test_scf_energy_h2o_uhf_triplet(Int4C2E, oracle):
+    """Open-shell path (J, Ka, Kb): triplet CH2 / cc-pVDZ (examples/ch2.inp) UHF energy vs the oracle's."""
+    mol, fb = load_fixture_molecule("ch2")
+    S, T, V = oracle.one_electron(fb, mol.Z, mol.xyz_bohr)
+    enuc = H.nuclear_repulsion(mol.Z, mol.xyz_bohr)
+    na, nb = mol.nalpha_nbeta
+    eng = _engine(Int4C2E, fb)
+    E_gpu, *_ = H.uhf(S, T + V, na, nb, lambda d, a, b: eng.ContractInts(d, a, b, 1, 0), enuc)
+    E_cpu, *_ = H.uhf(S, T + V, na, nb, lambda d, a, b: oracle.direct_jk(fb, d, a, b)[:4], enuc)
+    eng.close()
+    assert abs(E_gpu - E_cpu) < 1e-8
+
+
+def test_multi_density(Int4C2E, oracle):
+    """ContractInts(std::vector<EigenMatrix>&) (Int4C2E.cpp:685-745): G_k = J[2 D_k] - EXX K[D_k]."""
+    mol, fb = load_fixture_molecule("h2o")
+    Ds = [H.random_symmetric_density(fb.nbf, s) for s in range(3)]
+    eng = _engine(Int4C2E, fb, exx=0.5)
+    Gs = eng.ContractInts(Ds, 1, 0)
+    for D, G in zip(Ds, Gs):
+        J, K, _, _, _ = oracle.direct_jk(fb, D, exx=0.5)
+        assert np.abs(G - (J - K)).max() < TOL
+    eng.close()
+
+
+def test_fe4s4_uhf_blocks(Int4C2E, oracle):
+    """fe4s4 / 6-31G* (d, f shells, deep contractions, UHF-type call): sampled exact blocks."""
+    mol, fb = load_fixture_molecule("fe4s4")
+    n = fb.nbf
+    Da, Db = H.random_symmetric_density(n, 1), H.random_symmetric_density(n, 2)
+    eng = _engine(Int4C2E, fb)
+    J, _, Ka, Kb = eng.ContractInts(None, Da, Db, 1, 0)
+    nfe = 12  # shells per Fe
+    for sa, sb in ((0, 0), (11, 5), (nfe * 4 + 3, 9), (nfe + 10, nfe * 2 + 11)):
+        Jb, Kab = oracle.jk_block(fb, Da + Db, Da, sa, sb)
+        ia, ib = fb.shell2bf[sa], fb.shell2bf[sb]
+        assert np.abs(Jb - J[ia:ia + fb.nfun[sa], ib:ib + fb.nfun[sb]]).max() < TOL, (sa, sb)
+        assert np.abs(Kab - Ka[ia:ia + fb.nfun[sa], ib:ib + fb.nfun[sb]]).max() < TOL, (sa, sb)
+    eng.close()

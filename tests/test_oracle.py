@@ -1,0 +1,158 @@
+"""CPU tests of the oracle (oracle/oracle.c) against every known answer available for this path.
+
+The reference ships no tests and no golden vectors for the J/K path; the anchors are
+  * the only number Chinium ever recorded: RHF/cc-pVDZ energy of CH3ClF- in tools/sn2/sn2.cnm.log:204,
+  * textbook values (Szabo-Ostlund H2/STO-3G integrals, Crawford's H2O/STO-3G energy),
+  * first principles (Boys function vs mpmath, Racah solid harmonics vs the polynomials the reference
+    itself uses on the DFT grid, src/Grid/AO/PureD.hpp / PureF.hpp / PureG.hpp, permutational symmetry,
+    dense einsum).
+"""
+import math
+
+import numpy as np
+import pytest
+
+import scf_harness as H
+from chinium_b200.inputs import load_fixture_molecule, normalize_shell
+
+
+def test_boys_against_mpmath(oracle):
+    import mpmath as mp
+    mp.mp.dps = 40
+    for T in (0.0, 1e-9, 0.03, 0.9, 5.5, 17.0, 33.3, 49.9, 75.0, 240.0):
+        F = oracle.boys(24, T)
+        for m in (0, 1, 5, 12, 24):
+            ref = mp.hyp1f1(m + 0.5, m + 1.5, -T) / (2 * m + 1)
+            assert abs(F[m] - float(ref)) <= 2e-14 * float(ref) + 1e-300, (T, m)
+
+
+def _monomials(l, x, y, z):
+    return np.array([x ** lx * y ** ly * z ** (l - lx - ly) for lx in range(l, -1, -1) for ly in range(l - lx, -1, -1)])
+
+
+def test_pure_functions_match_reference_polynomials(oracle):
+    """The reference evaluates the same basis functions on the DFT grid; its explicit polynomials
+    (src/Grid/AO/PureD.hpp:1-5, PureF.hpp:1-7, PureG.hpp:1-9) fix ordering, sign and normalisation."""
+    rng = np.random.default_rng(3)
+    s = math.sqrt
+    for _ in range(5):
+        x, y, z = rng.uniform(-1.5, 1.5, 3)
+        r2 = x * x + y * y + z * z
+        d = [x * y * s(3), y * z * s(3), (3 * z * z - r2) / 2, x * z * s(3), (x * x - y * y) * s(3) / 2]
+        f = [y * (3 * x * x - y * y) * s(10) / 4, x * y * z * s(15), y * (5 * z * z - r2) * s(6) / 4, (5 * z ** 3 - 3 * z * r2) / 2,
+             x * (5 * z * z - r2) * s(6) / 4, (x * x - y * y) * z * s(15) / 2, x * (x * x - 3 * y * y) * s(10) / 4]
+        g = [x * y * (x * x - y * y) * s(35) / 2, y * (3 * x * x - y * y) * z * s(70) / 4, x * y * (7 * z * z - r2) * s(5) / 2,
+             y * (7 * z ** 3 - 3 * z * r2) * s(10) / 4, (35 * z ** 4 - 30 * z * z * r2 + 3 * r2 * r2) / 8,
+             x * (7 * z ** 3 - 3 * z * r2) * s(10) / 4, (x * x - y * y) * (7 * z * z - r2) * s(5) / 4,
+             x * (x * x - 3 * y * y) * z * s(70) / 4, (x * x * (x * x - 3 * y * y) - y * y * (3 * x * x - y * y)) * s(35) / 8]
+        p = [y, z, x]  # pure P order (src/Grid/AO/PureP.hpp:1-3)
+        for l, ref in ((1, p), (2, d), (3, f), (4, g)):
+            got = oracle.pure_matrix(l) @ _monomials(l, x, y, z)
+            assert np.allclose(got, ref, rtol=1e-13, atol=1e-13), l
+
+
+def test_normalisation_unit_self_overlap(oracle):
+    for name in ("h2o", "hf_tz", "fe4s4"):
+        mol, fb = load_fixture_molecule(name)
+        S, T, V = oracle.one_electron(fb, mol.Z, mol.xyz_bohr)
+        assert np.abs(np.diag(S) - 1).max() < 5e-14
+        assert np.abs(S - S.T).max() < 1e-14 and np.abs(T - T.T).max() < 1e-12 and np.abs(V - V.T).max() < 1e-12
+
+
+def test_szabo_ostlund_h2(oracle):
+    mol, fb = load_fixture_molecule("h2_sto3g")
+    eri = oracle.eri_full(fb)
+    assert abs(eri[0, 0, 0, 0] - 0.7746) < 1e-4 and abs(eri[0, 0, 1, 1] - 0.5697) < 1e-4
+    assert abs(eri[1, 0, 0, 0] - 0.4441) < 1e-4 and abs(eri[1, 0, 1, 0] - 0.2970) < 1e-4
+    S, T, V = oracle.one_electron(fb, mol.Z, mol.xyz_bohr)
+    E, *_ = H.rhf(S, T + V, 1, lambda d, a, b: oracle.reference_jk(fb, d, a, b)[:4], H.nuclear_repulsion(mol.Z, mol.xyz_bohr))
+    assert abs(E - (-1.1167)) < 1e-4
+
+
+def test_crawford_h2o_sto3g(oracle):
+    mol, fb = load_fixture_molecule("h2o_sto3g")
+    S, T, V = oracle.one_electron(fb, mol.Z, mol.xyz_bohr)
+    enuc = H.nuclear_repulsion(mol.Z, mol.xyz_bohr)
+    assert abs(enuc - 8.002367061810) < 1e-9
+    E, *_ = H.rhf(S, T + V, 5, lambda d, a, b: oracle.reference_jk(fb, d, a, b)[:4], enuc)
+    assert abs(E - (-74.942079928192)) < 1e-8
+
+
+def test_sn2_golden_energy(oracle):
+    """tools/sn2/sn2.cnm.log:204 -- the only output of Chinium recorded in the reference tree."""
+    mol, fb = load_fixture_molecule("sn2")
+    assert fb.nbf == 61
+    S, T, V = oracle.one_electron(fb, mol.Z, mol.xyz_bohr)
+    h = oracle.store_build(fb)
+    try:
+        E, *_ = H.rhf(S, T + V, 18, lambda d, a, b: oracle.store_contract(h, fb.nbf, d, a, b), H.nuclear_repulsion(mol.Z, mol.xyz_bohr))
+    finally:
+        oracle.store_free(h)
+    assert abs(E - (-598.514802895)) < 1e-7, E
+
+
+def test_reference_counts_h2o(oracle):
+    """RepulsionLength = number of unique basis-function quartets (Int4C2E.cpp:516-526), unscreened."""
+    mol, fb = load_fixture_molecule("h2o")
+    D = H.random_symmetric_density(fb.nbf, 0)
+    *_, counts = oracle.reference_jk(fb, D)
+    npair = fb.nbf * (fb.nbf + 1) // 2
+    assert counts[0] == npair * (npair + 1) // 2 == 45150
+    *_, cnt = oracle.direct_jk(fb, D)
+    assert cnt[0] == 3081   # canonical shell quartets, SURVEY 8d
+
+
+def test_stored_path_equals_direct_and_einsum(oracle):
+    mol, fb = load_fixture_molecule("h2o")
+    n = fb.nbf
+    Dd, Da, Db = (H.random_symmetric_density(n, s) for s in (0, 1, 2))
+    eri = oracle.eri_full(fb)
+    # permutational symmetry of the oracle's ERIs
+    assert np.abs(eri - eri.transpose(1, 0, 2, 3)).max() < 1e-13
+    assert np.abs(eri - eri.transpose(2, 3, 0, 1)).max() < 1e-13
+    exx = 0.2
+    J, Kd, Ka, Kb, _ = oracle.reference_jk(fb, Dd, Da, Db, exx=exx)
+    Dtot = 2 * Dd + Da + Db
+    assert np.abs(J - np.einsum("ijkl,kl->ij", eri, Dtot)).max() < 1e-12
+    for K, D in ((Kd, Dd), (Ka, Da), (Kb, Db)):
+        assert np.abs(K - exx * np.einsum("ijkl,jl->ik", eri, D)).max() < 1e-12
+    J2, Kd2, Ka2, Kb2, _ = oracle.direct_jk(fb, Dd, Da, Db, exx=exx)
+    assert max(np.abs(J - J2).max(), np.abs(Kd - Kd2).max(), np.abs(Ka - Ka2).max(), np.abs(Kb - Kb2).max()) < 1e-12
+    # EXX <= 0: K's are zeros (Int4C2E.cpp:638)
+    _, K0, _, _, _ = oracle.reference_jk(fb, Dd, None, None, exx=0.0)
+    assert np.abs(K0).max() == 0.0
+
+
+def test_threshold_screening_semantics(oracle):
+    """threshold > 0 drops quartets whose Schwarz bound is below it (Int4C2E.cpp:108-113)."""
+    mol, fb = load_fixture_molecule("h2o")
+    D = H.random_symmetric_density(fb.nbf, 0)
+    J0, K0, _, _, c0 = oracle.reference_jk(fb, D, threshold=-1.0)
+    J1, K1, _, _, c1 = oracle.reference_jk(fb, D, threshold=1e-3)
+    assert c1[0] < c0[0] and c1[1] < c0[1]
+    assert np.abs(J1 - J0).max() < 0.05
+
+
+def test_golden_fixture_reproducible(oracle):
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "jk_golden.npz"))
+    mol, fb = load_fixture_molecule("h2o")
+    D = H.random_symmetric_density(fb.nbf, 0)
+    J, K, _, _, _ = oracle.reference_jk(fb, D)
+    assert np.abs(J - g["h2o_J"]).max() < 1e-13 and np.abs(K - g["h2o_K"]).max() < 1e-13
+
+
+def test_jk_block_matches_full(oracle):
+    mol, fb = load_fixture_molecule("h2o")
+    D = H.random_symmetric_density(fb.nbf, 0)
+    J, K, _, _, _ = oracle.reference_jk(fb, D)
+    for sa, sb in ((11, 3), (4, 4), (7, 10)):
+        Jb, Kb = oracle.jk_block(fb, 2 * D, D, sa, sb)
+        ia, ib = fb.shell2bf[sa], fb.shell2bf[sb]
+        assert np.abs(Jb - J[ia:ia + fb.nfun[sa], ib:ib + fb.nfun[sb]]).max() < 1e-12
+        assert np.abs(Kb - K[ia:ia + fb.nfun[sa], ib:ib + fb.nfun[sb]]).max() < 1e-12
+
+
+def test_normalize_shell_matches_unit_norm():
+    # s primitive: (2a/pi)^(3/4)
+    c = normalize_shell(0, [0.5], [1.0])
+    assert abs(c[0] - (2 * 0.5 / math.pi) ** 0.75) < 1e-15
