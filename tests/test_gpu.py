@@ -119,7 +119,9 @@ def test_size_independent_properties_c18(Int4C2E):
     D1, D2 = H.random_symmetric_density(n, 0), H.random_symmetric_density(n, 7)
     full = _engine(Int4C2E, fb, pair_cutoff=1e-300)     # nothing dropped: the reference's unscreened counts
     st = full.stats
-    assert st["canonical_quartets"] == 132690195 and st["unique_integrals"] == 10668085485
+    npair_bf = n * (n + 1) // 2
+    # unscreened RepulsionLength = N(N+1)/2 with N = nbf(nbf+1)/2 (SURVEY 8d prints 10 668 085 485: a transcription slip)
+    assert st["canonical_quartets"] == 132690195 and st["unique_integrals"] == npair_bf * (npair_bf + 1) // 2 == 10668295485
     assert abs(st["flops_alg_jk"][1] / 2.365e12 - 1) < 5e-3
     full.close()
     eng = _engine(Int4C2E, fb)
