@@ -5,40 +5,53 @@
 
 #define CF_LMAX_DEV 3            // highest shell l the instantiated kernels cover (f); tables go to 9 roots
 #define CF_NCLS ((CF_LMAX_DEV + 1) * (CF_LMAX_DEV + 2) / 2)   // pair classes (la>=lb)
+#define CF_PSTRIDE 32            // primitive pairs of 32 consecutive shell pairs are interleaved (coalesced per warp)
+
+// Boys-function table F_m(T_i), T_i = i * BOYS_DT, i = 0..BOYS_NROW-1, m = 0..BOYS_NCOL-1 (row-major)
+#define BOYS_DT 0.125
+#define BOYS_NROW 289            // T in [0, 36]
+#define BOYS_NCOL 12
+#define BOYS_TMAX 36.0
 
 __host__ __device__ constexpr int cf_ncart(int l) { return (l + 1) * (l + 2) / 2; }
 __host__ __device__ constexpr int cf_pair_class(int la, int lb) { return la * (la + 1) / 2 + lb; }  // la>=lb
 
-// Shell pairs of one class (la,lb), Schwarz-sorted (descending).  SoA, device pointers.
+// Shell pairs of one class (la,lb), sorted by (primitive count desc, Schwarz bound desc).  SoA, device pointers.
+// Primitive pair i of shell pair n lives in slot pbase[n] + i*CF_PSTRIDE of the primitive arrays: pairs are
+// grouped in blocks of 32 and their primitives interleaved, so a warp whose lanes hold 32 consecutive pairs reads
+// primitive i of all of them with one coalesced request.  Padding slots have c = 0.
 struct PairClassDev {
     int npair;
     const int* sa;          // [npair] shell with the larger l (ties: larger index)
     const int* sb;
     const int* cao_a;       // [npair] first Cartesian AO of shell a / b
     const int* cao_b;
-    const int* prim_off;    // [npair] first primitive pair
+    const int* pbase;       // [npair] slot of the first primitive pair
     const int* nprim;       // [npair] surviving primitive pairs
     const double* A;        // [npair*3] centre of a
     const double* AB;       // [npair*3] A - B
-    const double* Q;        // [npair] Schwarz bound max_ij sqrt((ij|ij)) over Cartesian functions
-    // primitive pairs (shared pool of the class)
+    const double* Q;        // [npair] Schwarz bound max_ij sqrt((ij|ij)) over the shell pair's basis functions
+    // primitive pairs (slots)
     const double* p;        // exponent sum
-    const double* P;        // [*3] product centre
+    const double* hp;       // 0.5 / p
+    const double* Px;       // product centre
+    const double* Py;
+    const double* Pz;
     const double* c;        // ca*cb*exp(-ab/p |AB|^2) * sqrt(2) pi^(5/4) / p
 };
 
 struct RysTablesDev {
     const double* table;
     const double* asym;
+    const double* boys;     // [BOYS_NROW][BOYS_NCOL]
 };
 
 // One launch = one (bra class, ket class) rectangle/triangle of the pair x pair grid.
 struct QuartetTask {
     PairClassDev bra, ket;
-    const long long* qoff;  // [bra.npair+1] prefix sum of ket counts per bra pair (kets form a prefix of the sorted list)
+    const long long* qoff;  // [bra.npair+1] prefix sum of ket counts per bra pair (generic kernels)
     long long nquartet;     // qoff[bra.npair]
-    long long q_begin, q_end;   // this rank's slice (chunk-interleaved, see engine.cu)
-    int chunk;              // quartets per work chunk
+    int chunk;              // quartets per work chunk (generic kernels)
     int rank, world;
     int same_class;         // bra class == ket class (triangular, diagonal weight 1/2)
     int ncart;              // leading dimension of the Cartesian matrices
@@ -52,5 +65,9 @@ struct QuartetTask {
     int diag;               // Schwarz mode: quartet q is (pair q | pair q)
     RysTablesDev rys;
     double prim_cut;        // skip primitive quartets with |c_ab c_cd| below this
+    double thr;             // Cauchy-Schwarz threshold on Q_ab * Q_cd (<= 0: none), reference Int4C2E.cpp:108-113
+    // thread-per-quartet kernels: work item = (bra pair, chunk of TPQ ket pairs)
+    const long long* item_off;  // [bra.npair+1] first item of each bra pair (same_class only; else item = ib*nchunk_ket + chunk)
+    long long nitem;
+    int nchunk_ket;
 };
-

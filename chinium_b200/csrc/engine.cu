@@ -23,6 +23,7 @@
 #include "../../include/chinium_fock.h"
 #include "cf_common.cuh"
 #include "eri_generic.cuh"     // rys_tmax/rys_off (host constexpr) -- no kernels instantiated here
+#include "eri_tpq.cuh"         // TPQ_THREADS
 #include "rys_tables_data.h"
 
 #define CUDA_TRY(x)                                                                             \
@@ -35,9 +36,9 @@
     } while (0)
 
 // launchers from eri_inst.cu (one translation unit per bra class)
-#define DECL_BRA(n) cudaError_t cf_launch_bra##n(int, const QuartetTask&, int, int, cudaStream_t, int*, size_t*);
+#define DECL_BRA(n) cudaError_t cf_launch_bra##n(int, const QuartetTask&, int, int, cudaStream_t, int*, size_t*, int*);
 DECL_BRA(0) DECL_BRA(1) DECL_BRA(2) DECL_BRA(3) DECL_BRA(4) DECL_BRA(5) DECL_BRA(6) DECL_BRA(7) DECL_BRA(8) DECL_BRA(9)
-typedef cudaError_t (*bra_launch_fn)(int, const QuartetTask&, int, int, cudaStream_t, int*, size_t*);
+typedef cudaError_t (*bra_launch_fn)(int, const QuartetTask&, int, int, cudaStream_t, int*, size_t*, int*);
 static bra_launch_fn g_bra_launch[CF_NCLS] = {cf_launch_bra0, cf_launch_bra1, cf_launch_bra2, cf_launch_bra3, cf_launch_bra4,
                                               cf_launch_bra5, cf_launch_bra6, cf_launch_bra7, cf_launch_bra8, cf_launch_bra9};
 
@@ -63,44 +64,78 @@ struct DevBuf {
 
 struct PairClassHost {
     int la = 0, lb = 0;
+    // canonical host storage: pairs in creation order, primitives contiguous per pair (prim_off / nprim)
     std::vector<int> sa, sb, cao_a, cao_b, prim_off, nprim, nprim_full;
     std::vector<double> A, AB, Q, Qpure, p, P, c;
-    DevBuf<int> d_sa, d_sb, d_cao_a, d_cao_b, d_prim_off, d_nprim;
-    DevBuf<double> d_A, d_AB, d_Q, d_p, d_P, d_c;
+    std::vector<int> order;          // device position -> canonical pair index
+    DevBuf<int> d_sa, d_sb, d_cao_a, d_cao_b, d_pbase, d_nprim;
+    DevBuf<double> d_A, d_AB, d_Q, d_Qcart, d_p, d_hp, d_Px, d_Py, d_Pz, d_c;
     int npair() const { return (int)sa.size(); }
     PairClassDev dev() const {
         PairClassDev d;
         d.npair = npair();
         d.sa = d_sa.p; d.sb = d_sb.p; d.cao_a = d_cao_a.p; d.cao_b = d_cao_b.p;
-        d.prim_off = d_prim_off.p; d.nprim = d_nprim.p; d.A = d_A.p; d.AB = d_AB.p; d.Q = d_Q.p;
-        d.p = d_p.p; d.P = d_P.p; d.c = d_c.p;
+        d.pbase = d_pbase.p; d.nprim = d_nprim.p; d.A = d_A.p; d.AB = d_AB.p; d.Q = d_Q.p;
+        d.p = d_p.p; d.hp = d_hp.p; d.Px = d_Px.p; d.Py = d_Py.p; d.Pz = d_Pz.p; d.c = d_c.p;
         return d;
     }
+    // device layout for the pair order `order`: blocks of CF_PSTRIDE pairs with interleaved primitives
     cudaError_t upload() {
+        const int np = npair();
+        if ((int)order.size() != np) { order.resize(np); std::iota(order.begin(), order.end(), 0); }
+        std::vector<int> o_sa(np), o_sb(np), o_ca(np), o_cb(np), o_pbase(np), o_np(np);
+        std::vector<double> o_A(3 * (size_t)np), o_AB(3 * (size_t)np), o_Q(np);
+        size_t nslot = 0;
+        for (int b0 = 0; b0 < np; b0 += CF_PSTRIDE) {
+            int mx = 0;
+            for (int i = b0; i < std::min(np, b0 + CF_PSTRIDE); i++) mx = std::max(mx, nprim[order[i]]);
+            for (int i = b0; i < std::min(np, b0 + CF_PSTRIDE); i++) o_pbase[i] = (int)(nslot + (i - b0));
+            nslot += (size_t)mx * CF_PSTRIDE;
+        }
+        if (nslot > 0x7fffffffull) return cudaErrorInvalidValue;
+        std::vector<double> o_p(nslot, 1.0), o_hp(nslot, 0.5), o_Px(nslot, 0.0), o_Py(nslot, 0.0), o_Pz(nslot, 0.0), o_c(nslot, 0.0);
+        for (int i = 0; i < np; i++) {
+            const int s = order[i];
+            o_sa[i] = sa[s]; o_sb[i] = sb[s]; o_ca[i] = cao_a[s]; o_cb[i] = cao_b[s]; o_np[i] = nprim[s]; o_Q[i] = Qpure[s];
+            for (int x = 0; x < 3; x++) { o_A[3 * (size_t)i + x] = A[3 * (size_t)s + x]; o_AB[3 * (size_t)i + x] = AB[3 * (size_t)s + x]; }
+            for (int k = 0; k < nprim[s]; k++) {
+                const size_t slot = (size_t)o_pbase[i] + (size_t)k * CF_PSTRIDE, src = (size_t)prim_off[s] + k;
+                o_p[slot] = p[src]; o_hp[slot] = 0.5 / p[src]; o_c[slot] = c[src];
+                o_Px[slot] = P[3 * src]; o_Py[slot] = P[3 * src + 1]; o_Pz[slot] = P[3 * src + 2];
+            }
+        }
         cudaError_t e;
-        if ((e = d_sa.upload(sa)) != cudaSuccess) return e;
-        if ((e = d_sb.upload(sb)) != cudaSuccess) return e;
-        if ((e = d_cao_a.upload(cao_a)) != cudaSuccess) return e;
-        if ((e = d_cao_b.upload(cao_b)) != cudaSuccess) return e;
-        if ((e = d_prim_off.upload(prim_off)) != cudaSuccess) return e;
-        if ((e = d_nprim.upload(nprim)) != cudaSuccess) return e;
-        if ((e = d_A.upload(A)) != cudaSuccess) return e;
-        if ((e = d_AB.upload(AB)) != cudaSuccess) return e;
-        if ((e = d_Q.upload(Q)) != cudaSuccess) return e;
-        if ((e = d_p.upload(p)) != cudaSuccess) return e;
-        if ((e = d_P.upload(P)) != cudaSuccess) return e;
-        return d_c.upload(c);
+        if ((e = d_sa.upload(o_sa)) != cudaSuccess) return e;
+        if ((e = d_sb.upload(o_sb)) != cudaSuccess) return e;
+        if ((e = d_cao_a.upload(o_ca)) != cudaSuccess) return e;
+        if ((e = d_cao_b.upload(o_cb)) != cudaSuccess) return e;
+        if ((e = d_pbase.upload(o_pbase)) != cudaSuccess) return e;
+        if ((e = d_nprim.upload(o_np)) != cudaSuccess) return e;
+        if ((e = d_A.upload(o_A)) != cudaSuccess) return e;
+        if ((e = d_AB.upload(o_AB)) != cudaSuccess) return e;
+        if ((e = d_Q.upload(o_Q)) != cudaSuccess) return e;
+        if ((e = d_p.upload(o_p)) != cudaSuccess) return e;
+        if ((e = d_hp.upload(o_hp)) != cudaSuccess) return e;
+        if ((e = d_Px.upload(o_Px)) != cudaSuccess) return e;
+        if ((e = d_Py.upload(o_Py)) != cudaSuccess) return e;
+        if ((e = d_Pz.upload(o_Pz)) != cudaSuccess) return e;
+        return d_c.upload(o_c);
     }
     void release() {
-        d_sa.release(); d_sb.release(); d_cao_a.release(); d_cao_b.release(); d_prim_off.release(); d_nprim.release();
-        d_A.release(); d_AB.release(); d_Q.release(); d_p.release(); d_P.release(); d_c.release();
+        d_sa.release(); d_sb.release(); d_cao_a.release(); d_cao_b.release(); d_pbase.release(); d_nprim.release();
+        d_A.release(); d_AB.release(); d_Q.release(); d_Qcart.release(); d_p.release(); d_hp.release(); d_Px.release(); d_Py.release();
+        d_Pz.release(); d_c.release();
     }
 };
 
 struct ClassPairTask {
     int bra = 0, ket = 0;
-    long long nquartet = 0;
-    DevBuf<long long> d_qoff;
+    long long nquartet = 0;          // all canonical quartets of the class pair (before Schwarz screening)
+    DevBuf<long long> d_qoff;        // generic kernels: first quartet of each bra pair
+    DevBuf<long long> d_item_off;    // thread-per-quartet kernels, same class: first work item of each bra pair
+    long long nitem = 0;
+    int nchunk_ket = 0;
+    int kind = 0;                    // 0 generic (CTA per quartet), 1 thread per quartet
     int G = 32;
     size_t smem[4] = {0, 0, 0, 0};   // by nk
     double flops_eri = 0;            // F_alg without the digestion term
@@ -120,7 +155,7 @@ struct cf_handle {
     DevBuf<int> d_ct_off, d_bf_off, d_cao_off, d_nfun, d_ncartsh;
     PairClassHost cls[CF_NCLS];
     std::vector<ClassPairTask*> tasks;
-    DevBuf<double> d_rys_table, d_rys_asym;
+    DevBuf<double> d_rys_table, d_rys_asym, d_boys;
     // per-build work space
     DevBuf<double> d_Dpure[3], d_Dcart[4] /* 0: Dtot, 1..3: Dk */, d_out[4] /* pure J,Kd,Ka,Kb */, d_partial, d_scales, d_diag;
     DevBuf<long long> d_acc;
@@ -350,21 +385,44 @@ static int launch_task(cf_handle* h, ClassPairTask* t, QuartetTask& qt, int stor
     const PairClassHost& K = h->cls[t->ket];
     qt.bra = B.dev(); qt.ket = K.dev();
     qt.qoff = t->d_qoff.p; qt.nquartet = t->nquartet;
+    qt.item_off = t->d_item_off.p; qt.nitem = t->nitem; qt.nchunk_ket = t->nchunk_ket;
     qt.same_class = (t->bra == t->ket);
+    qt.thr = h->opt.threshold > 0 ? h->opt.threshold : 0.0;
     const long long nq = qt.nquartet;
     if (nq == 0) return CF_OK;
-    // chunk: enough chunks to fill the machine ~8x over, at most 64 quartets each
-    long long chunk = nq / (148LL * 32 * std::max(1, qt.world));
-    chunk = std::max(1LL, std::min(64LL, chunk));
-    qt.chunk = (int)chunk;
-    const long long nchunk_total = (nq + chunk - 1) / chunk;
-    const long long nchunk_local = (nchunk_total - qt.rank + qt.world - 1) / qt.world;
-    if (nchunk_local <= 0) return CF_OK;
-    const int grid = (int)std::min<long long>(nchunk_local, 148LL * 32);
-    cudaError_t e = g_bra_launch[t->bra](t->ket, qt, store, grid, s, nullptr, nullptr);
+    int grid;
+    if (t->kind == 1 && !store) {
+        const long long nlocal = (t->nitem - qt.rank + qt.world - 1) / qt.world;
+        if (nlocal <= 0) return CF_OK;
+        grid = (int)std::min<long long>(nlocal, 148LL * 16);
+    } else {
+        // chunk: enough chunks to fill the machine ~8x over, at most 64 quartets each
+        long long chunk = nq / (148LL * 32 * std::max(1, qt.world));
+        chunk = std::max(1LL, std::min(64LL, chunk));
+        qt.chunk = (int)chunk;
+        const long long nchunk_total = (nq + chunk - 1) / chunk;
+        const long long nchunk_local = (nchunk_total - qt.rank + qt.world - 1) / qt.world;
+        if (nchunk_local <= 0) return CF_OK;
+        grid = (int)std::min<long long>(nchunk_local, 148LL * 32);
+    }
+    cudaError_t e = g_bra_launch[t->bra](t->ket, qt, store, grid, s, nullptr, nullptr, nullptr);
     if (e != cudaSuccess) { set_error(h, std::string("ERI kernel launch failed: ") + cudaGetErrorString(e)); return CF_ERR_CUDA; }
     h->stats.n_launches_last++;
     return CF_OK;
+}
+
+// F_m(T) for m = 0..mmax by the (all-positive) series e^-T sum_k (2T)^k / ((2m+1)(2m+3)...(2m+2k+1)), long double
+static void boys_reference(double T, int mmax, double* out) {
+    const long double t = T, e = expl(-t);
+    for (int m = 0; m <= mmax; m++) {
+        long double term = 1.0L / (2 * m + 1), sum = term;
+        for (int k = 1; k < 400; k++) {
+            term *= 2.0L * t / (2 * m + 2 * k + 1);
+            sum += term;
+            if (term < 1e-22L * sum) break;
+        }
+        out[m] = (double)(e * sum);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -417,9 +475,9 @@ extern "C" void cf_destroy(cf_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (auto& c : h->cls) c.release();
-    for (auto* t : h->tasks) { t->d_qoff.release(); delete t; }
+    for (auto* t : h->tasks) { t->d_qoff.release(); t->d_item_off.release(); delete t; }
     h->d_ctrans.release(); h->d_ct_off.release(); h->d_bf_off.release(); h->d_cao_off.release(); h->d_nfun.release(); h->d_ncartsh.release();
-    h->d_rys_table.release(); h->d_rys_asym.release();
+    h->d_rys_table.release(); h->d_rys_asym.release(); h->d_boys.release();
     for (auto& b : h->d_Dpure) b.release();
     for (auto& b : h->d_Dcart) b.release();
     for (auto& b : h->d_out) b.release();
@@ -433,6 +491,7 @@ extern "C" void cf_destroy(cf_handle* h) {
 static void fill_rys(QuartetTask& qt, const cf_handle* h) {
     qt.rys.table = h->d_rys_table.p;
     qt.rys.asym = h->d_rys_asym.p;
+    qt.rys.boys = h->d_boys.p;
 }
 
 extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
@@ -499,6 +558,9 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     {
         std::vector<double> tab(rys_table_h, rys_table_h + RYS_TABLE_LEN), asym(rys_asym_h, rys_asym_h + RYS_NMAX * (RYS_NMAX + 1));
         UP(h->d_rys_table, tab); UP(h->d_rys_asym, asym);
+        std::vector<double> boys((size_t)BOYS_NROW * BOYS_NCOL);
+        for (int i = 0; i < BOYS_NROW; i++) boys_reference(i * BOYS_DT, BOYS_NCOL - 1, &boys[(size_t)i * BOYS_NCOL]);
+        UP(h->d_boys, boys);
     }
 
     // ---- shell pairs by class
@@ -550,45 +612,48 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
         // in slabs so the store buffer stays below ~1 GiB
         const int slab = (int)std::max<size_t>(1, std::min<size_t>(np, (1ull << 27) / nout));
         DevBuf<double> blocks, qpure;
-        if (blocks.alloc(nout * slab) != cudaSuccess || qpure.alloc(np) != cudaSuccess) return fail("cudaMalloc failed (Schwarz)");
+        if (blocks.alloc(nout * slab) != cudaSuccess || qpure.alloc(np) != cudaSuccess || c.d_Qcart.alloc(np) != cudaSuccess) return fail("cudaMalloc failed (Schwarz)");
         for (int p0 = 0; p0 < np; p0 += slab) {
             const int cnt = std::min(slab, np - p0);
             QuartetTask qt{};
             PairClassDev d = c.dev();
             // shift the pair arrays so that local pair q maps to global pair p0+q
-            d.npair = cnt; d.sa += p0; d.sb += p0; d.cao_a += p0; d.cao_b += p0; d.prim_off += p0; d.nprim += p0; d.A += 3 * p0; d.AB += 3 * p0; d.Q += p0;
+            d.npair = cnt; d.sa += p0; d.sb += p0; d.cao_a += p0; d.cao_b += p0; d.pbase += p0; d.nprim += p0; d.A += 3 * p0; d.AB += 3 * p0; d.Q += p0;
             qt.bra = d; qt.ket = d; qt.qoff = nullptr; qt.nquartet = cnt; qt.chunk = 1; qt.rank = 0; qt.world = 1;
-            qt.same_class = 1; qt.ncart = ncart; qt.nk = 0; qt.store = blocks.p; qt.diag = 1; qt.prim_cut = 0.0;
+            qt.same_class = 1; qt.ncart = ncart; qt.nk = 0; qt.store = blocks.p; qt.diag = 1; qt.prim_cut = 0.0; qt.thr = 0.0;
             fill_rys(qt, h);
-            cudaError_t e = g_bra_launch[ci](ci, qt, 1, cnt, 0, nullptr, nullptr);
+            cudaError_t e = g_bra_launch[ci](ci, qt, 1, cnt, 0, nullptr, nullptr, nullptr);
             if (e != cudaSuccess) return fail(std::string("Schwarz launch failed: ") + cudaGetErrorString(e));
             schwarz_kernel<<<cnt, 128>>>(cnt, nca, ncb, blocks.p, c.d_sa.p + p0, c.d_sb.p + p0, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
-                                         h->d_nfun.p, nbf, c.d_Q.p + p0, qpure.p + p0, h->d_diag.p);
+                                         h->d_nfun.p, nbf, c.d_Qcart.p + p0, qpure.p + p0, h->d_diag.p);
         }
-        if (cudaMemcpy(c.Q.data(), c.d_Q.p, sizeof(double) * np, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        if (cudaMemcpy(c.Q.data(), c.d_Qcart.p, sizeof(double) * np, cudaMemcpyDeviceToHost) != cudaSuccess ||
             cudaMemcpy(c.Qpure.data(), qpure.p, sizeof(double) * np, cudaMemcpyDeviceToHost) != cudaSuccess)
             return fail(std::string("Schwarz kernels failed: ") + cudaGetErrorString(cudaGetLastError()));
         blocks.release(); qpure.release();
     }
     h->diag_ready = true;
 
-    // ---- sort each class by the (pure-function) Schwarz bound, descending; re-upload
+    // ---- sort each class by (primitive count desc, pure-function Schwarz bound desc); re-upload in that order.
+    // Equal primitive counts inside a warp keep the per-thread primitive loops of the thread-per-quartet kernels
+    // convergent; heavy pairs first gives the static schedule a short tail.
     h->qmax_cart = 0;
     for (auto& c : h->cls) {
         const int np = c.npair();
         if (np == 0) continue;
-        std::vector<int> perm(np);
-        std::iota(perm.begin(), perm.end(), 0);
-        std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return c.Qpure[x] > c.Qpure[y]; });
-        auto permute_i = [&](std::vector<int>& v, int w) { std::vector<int> o(v.size()); for (int i = 0; i < np; i++) for (int k = 0; k < w; k++) o[(size_t)i * w + k] = v[(size_t)perm[i] * w + k]; v.swap(o); };
-        auto permute_d = [&](std::vector<double>& v, int w) { std::vector<double> o(v.size()); for (int i = 0; i < np; i++) for (int k = 0; k < w; k++) o[(size_t)i * w + k] = v[(size_t)perm[i] * w + k]; v.swap(o); };
-        permute_i(c.sa, 1); permute_i(c.sb, 1); permute_i(c.cao_a, 1); permute_i(c.cao_b, 1); permute_i(c.prim_off, 1);
-        permute_i(c.nprim, 1); permute_i(c.nprim_full, 1); permute_d(c.A, 3); permute_d(c.AB, 3); permute_d(c.Q, 1); permute_d(c.Qpure, 1);
+        c.order.resize(np);
+        std::iota(c.order.begin(), c.order.end(), 0);
+        std::stable_sort(c.order.begin(), c.order.end(), [&](int x, int y) {
+            if (c.nprim[x] != c.nprim[y]) return c.nprim[x] > c.nprim[y];
+            return c.Qpure[x] > c.Qpure[y];
+        });
         for (double q : c.Q) h->qmax_cart = std::max(h->qmax_cart, q);
         if (c.upload() != cudaSuccess) return fail("pair re-upload failed");
     }
 
-    // ---- class-pair tasks: per bra pair the kets are a prefix of the sorted ket list
+    // ---- class-pair tasks.  Quartet (ib, ik) of a task is canonical iff ik <= ib when bra class == ket class.
+    // Schwarz screening (threshold > 0, Int4C2E.cpp:108-113) is a per-quartet test Q_b * Q_k > thr inside the kernels;
+    // the statistics below count exactly the quartets that pass it.
     const double thr = h->opt.threshold;
     cf_stats& st = h->stats;
     st = cf_stats{};
@@ -603,43 +668,69 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
             ClassPairTask* t = new ClassPairTask();
             t->bra = cb; t->ket = ck;
             const int nb = B.npair(), nk = K.npair();
-            std::vector<long long> qoff(nb + 1, 0);
-            // prefix sums over the ket list for the statistics
-            std::vector<double> pre_prim(nk + 1, 0.0), pre_primfull(nk + 1, 0.0), pre_uniq(nk + 1, 0.0);
-            const int nfc = h->nfun[K.sa[0]], nfd = h->nfun[K.sb[0]];
+            const bool same = (cb == ck);
+            const int nfa = h->nfun[B.sa[0]], nfb = h->nfun[B.sb[0]], nfc = h->nfun[K.sa[0]], nfd = h->nfun[K.sb[0]];
+            // kets by descending Q with prefix sums of the per-pair weights
+            std::vector<int> kq(nk);
+            std::iota(kq.begin(), kq.end(), 0);
+            std::sort(kq.begin(), kq.end(), [&](int x, int y) { return K.Qpure[x] > K.Qpure[y]; });
+            std::vector<double> qs(nk), pre_prim(nk + 1, 0.0), pre_primfull(nk + 1, 0.0), pre_uniq(nk + 1, 0.0);
+            auto nfun_pair = [](bool diag, int n1, int n2) { return diag ? n1 * (n1 + 1) / 2.0 : (double)n1 * n2; };
             for (int k = 0; k < nk; k++) {
-                pre_prim[k + 1] = pre_prim[k] + K.nprim[k];
-                pre_primfull[k + 1] = pre_primfull[k] + K.nprim_full[k];
-                const double ncd = (K.sa[k] == K.sb[k]) ? nfc * (nfc + 1) / 2.0 : (double)nfc * nfd;
-                pre_uniq[k + 1] = pre_uniq[k] + ncd;
+                const int s = kq[k];
+                qs[k] = K.Qpure[s];
+                pre_prim[k + 1] = pre_prim[k] + K.nprim[s];
+                pre_primfull[k + 1] = pre_primfull[k] + K.nprim_full[s];
+                pre_uniq[k + 1] = pre_uniq[k] + nfun_pair(K.sa[s] == K.sb[s], nfc, nfd);
             }
-            const int nfa = h->nfun[B.sa[0]], nfb = h->nfun[B.sb[0]];
             const int L = B.la + B.lb + K.la + K.lb, nr = L / 2 + 1;
             const double per_prim = nr * (40.0 + 12.0 * (B.la + B.lb + 1) * (K.la + K.lb + 1) +
                                           3.0 * cf_ncart(B.la) * cf_ncart(B.lb) * cf_ncart(K.la) * cf_ncart(K.lb));
-            double uniq = 0, primq = 0, primq_full = 0;
+            double nq = 0, uniq = 0, primq = 0, primq_full = 0;        // over ordered (bra, ket) combinations
+            double dq = 0, duniq = 0, dprimq = 0, dprimq_full = 0;     // diagonal (i, i) part, same class only
+            double uniq_fix = 0;
             for (int i = 0; i < nb; i++) {
                 int cnt = nk;
-                if (thr > 0) {   // kets with Qb*Qk > thr form a prefix (Q sorted descending); Int4C2E.cpp:108-113
+                if (thr > 0) {
                     const double need = thr / std::max(B.Qpure[i], 1e-300);
-                    cnt = (int)(std::partition_point(K.Qpure.begin(), K.Qpure.end(), [&](double q) { return q > need; }) - K.Qpure.begin());
+                    cnt = (int)(std::partition_point(qs.begin(), qs.end(), [&](double q) { return q > need; }) - qs.begin());
                 }
-                if (cb == ck) cnt = std::min(cnt, i + 1);
-                qoff[i + 1] = qoff[i] + cnt;
-                const double nab = (B.sa[i] == B.sb[i]) ? nfa * (nfa + 1) / 2.0 : (double)nfa * nfb;
-                uniq += nab * pre_uniq[cnt];
-                if (cb == ck && cnt == i + 1) uniq -= nab * nab - nab * (nab + 1) / 2.0;   // diagonal quartet (ab|ab)
-                primq += (double)B.nprim[i] * pre_prim[cnt];
-                primq_full += (double)B.nprim_full[i] * pre_primfull[cnt];
+                const double nab = nfun_pair(B.sa[i] == B.sb[i], nfa, nfb);
+                nq += cnt; uniq += nab * pre_uniq[cnt];
+                primq += (double)B.nprim[i] * pre_prim[cnt]; primq_full += (double)B.nprim_full[i] * pre_primfull[cnt];
+                if (same && (thr <= 0 || B.Qpure[i] * B.Qpure[i] > thr)) {
+                    dq += 1; duniq += nab * nab; dprimq += (double)B.nprim[i] * B.nprim[i];
+                    dprimq_full += (double)B.nprim_full[i] * B.nprim_full[i];
+                    uniq_fix += nab * nab - nab * (nab + 1) / 2.0;   // (ab|ab): only the upper triangle of functions is unique
+                }
             }
-            t->nquartet = qoff[nb];
-            if (t->nquartet == 0) { delete t; continue; }
-            if (t->d_qoff.upload(qoff) != cudaSuccess) { delete t; return fail("qoff upload failed"); }
+            if (same) {
+                nq = 0.5 * (nq + dq); uniq = 0.5 * (uniq + duniq) - uniq_fix;
+                primq = 0.5 * (primq + dprimq); primq_full = 0.5 * (primq_full + dprimq_full);
+            }
+            t->nquartet = same ? (long long)nb * (nb + 1) / 2 : (long long)nb * nk;
+            const long long nq_kept = (long long)(nq + 0.5);
+            if (nq_kept == 0) { delete t; continue; }
             QuartetTask dummy{};
-            for (int k = 0; k < 4; k++) { dummy.nk = k; g_bra_launch[cb](ck, dummy, 0, 0, 0, &t->G, &t->smem[k]); }
+            for (int k = 0; k < 4; k++) { dummy.nk = k; g_bra_launch[cb](ck, dummy, 0, 0, 0, &t->G, &t->smem[k], &t->kind); }
+            if (t->kind == 1) {     // work items: (bra pair, chunk of TPQ_THREADS ket pairs)
+                t->nchunk_ket = (nk + TPQ_THREADS - 1) / TPQ_THREADS;
+                if (same) {
+                    std::vector<long long> ioff(nb + 1, 0);
+                    for (int i = 0; i < nb; i++) ioff[i + 1] = ioff[i] + i / TPQ_THREADS + 1;
+                    t->nitem = ioff[nb];
+                    if (t->d_item_off.upload(ioff) != cudaSuccess) { delete t; return fail("item_off upload failed"); }
+                } else {
+                    t->nitem = (long long)nb * t->nchunk_ket;
+                }
+            } else {
+                std::vector<long long> qoff(nb + 1, 0);
+                for (int i = 0; i < nb; i++) qoff[i + 1] = qoff[i] + (same ? i + 1 : nk);
+                if (t->d_qoff.upload(qoff) != cudaSuccess) { delete t; return fail("qoff upload failed"); }
+            }
             t->flops_eri = primq_full * per_prim;
-            t->nfun_sum = (double)t->nquartet * nfa * nfb * nfc * nfd;
-            st.canonical_quartets += t->nquartet;
+            t->nfun_sum = (double)nq_kept * nfa * nfb * nfc * nfd;
+            st.canonical_quartets += nq_kept;
             st.unique_integrals += (long long)(uniq + 0.5);
             st.primitive_quartets += (long long)(primq + 0.5);
             for (int k = 0; k < 4; k++) st.flops_alg_jk[k] += t->flops_eri + 2.0 * (2 + 4 * k) * t->nfun_sum;

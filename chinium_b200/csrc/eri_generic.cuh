@@ -177,8 +177,9 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
             const double ABx = t.bra.AB[3 * ib], ABy = t.bra.AB[3 * ib + 1], ABz = t.bra.AB[3 * ib + 2];
             const double Cx = t.ket.A[3 * ik], Cy = t.ket.A[3 * ik + 1], Cz = t.ket.A[3 * ik + 2];
             const double CDx = t.ket.AB[3 * ik], CDy = t.ket.AB[3 * ik + 1], CDz = t.ket.AB[3 * ik + 2];
-            const int pab0 = t.bra.prim_off[ib], npab = t.bra.nprim[ib];
-            const int pcd0 = t.ket.prim_off[ik], npcd = t.ket.nprim[ik];
+            if (t.thr > 0.0 && !(t.bra.Q[ib] * t.ket.Q[ik] > t.thr)) continue;   // uniform across the CTA
+            const int pab0 = t.bra.pbase[ib], npab = t.bra.nprim[ib];
+            const int pcd0 = t.ket.pbase[ik], npcd = t.ket.nprim[ik];
             double wgt = (sa == sb ? 1.0 : 2.0) * (sc == sd ? 1.0 : 2.0);
             wgt *= (t.same_class && ib == ik) ? 1.0 : 2.0;
 
@@ -187,13 +188,15 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
             for (int m = 0; m < NPL; m++) gout[m] = 0.0;
 
             for (int iab = 0; iab < npab; iab++) {
-                const double p = t.bra.p[pab0 + iab], cab = t.bra.c[pab0 + iab];
-                const double Px = t.bra.P[3 * (pab0 + iab)], Py = t.bra.P[3 * (pab0 + iab) + 1], Pz = t.bra.P[3 * (pab0 + iab) + 2];
+                const int sab = pab0 + iab * CF_PSTRIDE;
+                const double p = t.bra.p[sab], cab = t.bra.c[sab];
+                const double Px = t.bra.Px[sab], Py = t.bra.Py[sab], Pz = t.bra.Pz[sab];
                 for (int icd = 0; icd < npcd; icd++) {
-                    const double ccd = t.ket.c[pcd0 + icd];
+                    const int scd = pcd0 + icd * CF_PSTRIDE;
+                    const double ccd = t.ket.c[scd];
                     if (fabs(cab * ccd) < t.prim_cut) continue;   // uniform across the CTA
-                    const double qe = t.ket.p[pcd0 + icd];
-                    const double Qx = t.ket.P[3 * (pcd0 + icd)], Qy = t.ket.P[3 * (pcd0 + icd) + 1], Qz = t.ket.P[3 * (pcd0 + icd) + 2];
+                    const double qe = t.ket.p[scd];
+                    const double Qx = t.ket.Px[scd], Qy = t.ket.Py[scd], Qz = t.ket.Pz[scd];
                     const double pq = p + qe;
                     const double rho = p * qe / pq;
                     const double PQx = Px - Qx, PQy = Py - Qy, PQz = Pz - Qz;

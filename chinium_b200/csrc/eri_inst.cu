@@ -1,6 +1,7 @@
 // eri_inst.cu -- instantiates the generic quartet kernel for ONE bra pair class (-DCF_BRA=0..9) against
 // every ket class <= bra.  Compiled once per bra class so the 55 class pairs build in parallel.
 #include "eri_generic.cuh"
+#include "eri_tpq.cuh"
 
 #ifndef CF_BRA
 #error "compile with -DCF_BRA=<bra class index>"
@@ -21,15 +22,30 @@ template <> struct ClassL<9> { static constexpr int a = 3, b = 3; };
 constexpr int group_size(int nout) { return nout <= 640 ? 32 : nout <= 1600 ? 64 : nout <= 3600 ? 128 : 256; }
 
 template <int BRA, int KET>
-static cudaError_t launch_pair(const QuartetTask& t, int store, int grid, cudaStream_t s, int* g_out, size_t* smem_out) {
+static cudaError_t launch_pair(const QuartetTask& t, int store, int grid, cudaStream_t s, int* g_out, size_t* smem_out, int* kind_out) {
     constexpr int LA = ClassL<BRA>::a, LB = ClassL<BRA>::b, LC = ClassL<KET>::a, LD = ClassL<KET>::b;
     constexpr int NOUT = cf_ncart(LA) * cf_ncart(LB) * cf_ncart(LC) * cf_ncart(LD);
+    constexpr int NROOTS = (LA + LB + LC + LD) / 2 + 1;
+    cudaError_t e;
+    if constexpr (tpq_ok(LA, LB, LC, LD)) {
+        if (!store) {   // thread-per-quartet family: grid counts work items (bra pair x 128 kets)
+            constexpr size_t smem = tpq_smem(NROOTS);
+            if (g_out) *g_out = TPQ_THREADS;
+            if (smem_out) *smem_out = smem;
+            if (kind_out) *kind_out = 1;
+            if (grid <= 0) return cudaSuccess;
+            auto k = eri_jk_tpq<LA, LB, LC, LD>;
+            if (smem > 48 * 1024) { e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+            k<<<grid, TPQ_THREADS, smem, s>>>(t);
+            return cudaGetLastError();
+        }
+    }
     constexpr int G = group_size(NOUT);
     const size_t smem = eri_generic_smem<LA, LB, LC, LD>(store ? 0 : t.nk);
     if (g_out) *g_out = G;
     if (smem_out) *smem_out = smem;
+    if (kind_out) *kind_out = 0;
     if (grid <= 0) return cudaSuccess;   // query only
-    cudaError_t e;
     if (store) {
         auto k = eri_jk_generic<LA, LB, LC, LD, G, true>;
         if (smem > 48 * 1024) { e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
@@ -44,19 +60,19 @@ static cudaError_t launch_pair(const QuartetTask& t, int store, int grid, cudaSt
 
 template <int BRA, int KET>
 struct Dispatch {
-    static cudaError_t go(int ket, const QuartetTask& t, int store, int grid, cudaStream_t s, int* g, size_t* sm) {
-        if (ket == KET) return launch_pair<BRA, KET>(t, store, grid, s, g, sm);
-        return Dispatch<BRA, KET - 1>::go(ket, t, store, grid, s, g, sm);
+    static cudaError_t go(int ket, const QuartetTask& t, int store, int grid, cudaStream_t s, int* g, size_t* sm, int* kind) {
+        if (ket == KET) return launch_pair<BRA, KET>(t, store, grid, s, g, sm, kind);
+        return Dispatch<BRA, KET - 1>::go(ket, t, store, grid, s, g, sm, kind);
     }
 };
 template <int BRA>
 struct Dispatch<BRA, -1> {
-    static cudaError_t go(int, const QuartetTask&, int, int, cudaStream_t, int*, size_t*) { return cudaErrorInvalidValue; }
+    static cudaError_t go(int, const QuartetTask&, int, int, cudaStream_t, int*, size_t*, int*) { return cudaErrorInvalidValue; }
 };
 
 #define CF_CAT2(a, b) a##b
 #define CF_CAT(a, b) CF_CAT2(a, b)
-// cf_launch_bra<N>(ket_class, task, store, grid, stream, &G, &smem)
-cudaError_t CF_CAT(cf_launch_bra, CF_BRA)(int ket, const QuartetTask& t, int store, int grid, cudaStream_t s, int* g, size_t* sm) {
-    return Dispatch<CF_BRA, CF_BRA>::go(ket, t, store, grid, s, g, sm);
+// cf_launch_bra<N>(ket_class, task, store, grid, stream, &G, &smem, &kind)   kind: 0 generic (grid = CTAs over quartet chunks), 1 thread-per-quartet
+cudaError_t CF_CAT(cf_launch_bra, CF_BRA)(int ket, const QuartetTask& t, int store, int grid, cudaStream_t s, int* g, size_t* sm, int* kind) {
+    return Dispatch<CF_BRA, CF_BRA>::go(ket, t, store, grid, s, g, sm, kind);
 }
