@@ -135,7 +135,9 @@ struct ClassPairTask {
     DevBuf<long long> d_item_off;    // thread-per-quartet kernels, same class: first work item of each bra pair
     long long nitem = 0;
     int nchunk_ket = 0;
-    int kind = 0;                    // 0 generic (CTA per quartet), 1 thread per quartet
+    int kind = 0;                    // 0 generic (CTA per quartet), 1 thread per quartet, 2 sliced thread per quartet
+    int nq_item = 0;                 // kinds 1,2,3: ket pairs per work item
+    int swap = 0;                    // kind 3: the LOWER class is handed to the kernel as the CTA-uniform pair
     int G = 32;
     size_t smem[4] = {0, 0, 0, 0};   // by nk
     double flops_eri = 0;            // F_alg without the digestion term
@@ -384,6 +386,7 @@ static int launch_task(cf_handle* h, ClassPairTask* t, QuartetTask& qt, int stor
     const PairClassHost& B = h->cls[t->bra];
     const PairClassHost& K = h->cls[t->ket];
     qt.bra = B.dev(); qt.ket = K.dev();
+    if (t->swap && !store) { qt.bra = K.dev(); qt.ket = B.dev(); }
     qt.qoff = t->d_qoff.p; qt.nquartet = t->nquartet;
     qt.item_off = t->d_item_off.p; qt.nitem = t->nitem; qt.nchunk_ket = t->nchunk_ket;
     qt.same_class = (t->bra == t->ket);
@@ -391,7 +394,7 @@ static int launch_task(cf_handle* h, ClassPairTask* t, QuartetTask& qt, int stor
     const long long nq = qt.nquartet;
     if (nq == 0) return CF_OK;
     int grid;
-    if (t->kind == 1 && !store) {
+    if (t->kind >= 1 && !store) {
         const long long nlocal = (t->nitem - qt.rank + qt.world - 1) / qt.world;
         if (nlocal <= 0) return CF_OK;
         grid = (int)std::min<long long>(nlocal, 148LL * 16);
@@ -713,11 +716,15 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
             if (nq_kept == 0) { delete t; continue; }
             QuartetTask dummy{};
             for (int k = 0; k < 4; k++) { dummy.nk = k; g_bra_launch[cb](ck, dummy, 0, 0, 0, &t->G, &t->smem[k], &t->kind); }
-            if (t->kind == 1) {     // work items: (bra pair, chunk of TPQ_THREADS ket pairs)
-                t->nchunk_ket = (nk + TPQ_THREADS - 1) / TPQ_THREADS;
+            t->nq_item = t->kind >> 4; t->swap = (t->kind >> 3) & 1; t->kind &= 7;
+            if (t->kind >= 1 && t->swap) {   // rectangular task with the roles exchanged
+                t->nchunk_ket = (nb + t->nq_item - 1) / t->nq_item;
+                t->nitem = (long long)nk * t->nchunk_ket;
+            } else if (t->kind >= 1) {     // work items: (bra pair, chunk of nq_item ket pairs)
+                t->nchunk_ket = (nk + t->nq_item - 1) / t->nq_item;
                 if (same) {
                     std::vector<long long> ioff(nb + 1, 0);
-                    for (int i = 0; i < nb; i++) ioff[i + 1] = ioff[i] + i / TPQ_THREADS + 1;
+                    for (int i = 0; i < nb; i++) ioff[i + 1] = ioff[i] + i / t->nq_item + 1;
                     t->nitem = ioff[nb];
                     if (t->d_item_off.upload(ioff) != cudaSuccess) { delete t; return fail("item_off upload failed"); }
                 } else {

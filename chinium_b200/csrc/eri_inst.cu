@@ -1,7 +1,9 @@
 // eri_inst.cu -- instantiates the generic quartet kernel for ONE bra pair class (-DCF_BRA=0..9) against
 // every ket class <= bra.  Compiled once per bra class so the 55 class pairs build in parallel.
+#include <type_traits>
 #include "eri_generic.cuh"
 #include "eri_tpq.cuh"
+#include "eri_wg.cuh"
 
 #ifndef CF_BRA
 #error "compile with -DCF_BRA=<bra class index>"
@@ -32,11 +34,46 @@ static cudaError_t launch_pair(const QuartetTask& t, int store, int grid, cudaSt
             constexpr size_t smem = tpq_smem(NROOTS);
             if (g_out) *g_out = TPQ_THREADS;
             if (smem_out) *smem_out = smem;
-            if (kind_out) *kind_out = 1;
+            if (kind_out) *kind_out = 1 + 16 * TPQ_THREADS;
             if (grid <= 0) return cudaSuccess;
             auto k = eri_jk_tpq<LA, LB, LC, LD>;
             if (smem > 48 * 1024) { e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
             k<<<grid, TPQ_THREADS, smem, s>>>(t);
+            return cudaGetLastError();
+        }
+    }
+    if constexpr (wg_cfg(BRA, KET) != 0) {
+        if (!store) {   // warp-group cooperative family
+            constexpr int MK = wg_cfg(BRA, KET) & 255;
+            constexpr bool SWAP = (wg_cfg(BRA, KET) >> 8) != 0;
+            using C = typename std::conditional<SWAP, WgCfg<LC, LD, LA, LB, MK>, WgCfg<LA, LB, LC, LD, MK>>::type;
+            if (g_out) *g_out = 32 * WG_WARPS;
+            if (smem_out) *smem_out = C::SMEM;
+            if (kind_out) *kind_out = 3 + (SWAP ? 8 : 0) + 16 * C::NQ;
+            if (grid <= 0) return cudaSuccess;
+            if constexpr (SWAP) {
+                auto k = eri_jk_wg<LC, LD, LA, LB, MK>;
+                e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); if (e != cudaSuccess) return e;
+                k<<<grid, 32 * WG_WARPS, C::SMEM, s>>>(t);
+            } else {
+                auto k = eri_jk_wg<LA, LB, LC, LD, MK>;
+                e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); if (e != cudaSuccess) return e;
+                k<<<grid, 32 * WG_WARPS, C::SMEM, s>>>(t);
+            }
+            return cudaGetLastError();
+        }
+    }
+    if constexpr (tpqs_gs(LA, LB, LC, LD) > 0) {
+        if (!store) {   // sliced thread-per-quartet family: GS threads per quartet, work item = bra pair x NQ kets
+            constexpr int GS = tpqs_gs(LA, LB, LC, LD);
+            constexpr size_t smem = tpqs_smem(NROOTS, GS);
+            if (g_out) *g_out = GS * tpqs_nq(GS);
+            if (smem_out) *smem_out = smem;
+            if (kind_out) *kind_out = 2 + 16 * tpqs_nq(GS);
+            if (grid <= 0) return cudaSuccess;
+            auto k = eri_jk_tpqs<LA, LB, LC, LD, GS>;
+            if (smem > 48 * 1024) { e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+            k<<<grid, GS * tpqs_nq(GS), smem, s>>>(t);
             return cudaGetLastError();
         }
     }

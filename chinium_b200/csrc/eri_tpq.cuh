@@ -134,8 +134,11 @@ __device__ __forceinline__ void tpq_roots(const double* __restrict__ tab, double
     }
 }
 
+#ifndef TPQ_MINB
+#define TPQ_MINB 2
+#endif
 template <int LA, int LB, int LC, int LD>
-__global__ void __launch_bounds__(TPQ_THREADS) eri_jk_tpq(const QuartetTask t) {
+__global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const QuartetTask t) {
     constexpr int NA = cf_ncart(LA), NB = cf_ncart(LB), NC = cf_ncart(LC), ND = cf_ncart(LD);
     constexpr int NAB = NA * NB, NCD = NC * ND, NOUT = NAB * NCD;
     constexpr int NROOTS = (LA + LB + LC + LD) / 2 + 1;
@@ -344,6 +347,358 @@ __global__ void __launch_bounds__(TPQ_THREADS) eri_jk_tpq(const QuartetTask t) {
                         fixed_add(acc + (cd0 + l) * ld + cb + j, s, t.scaleK);
                     }
             }
+        }
+    }
+}
+
+// ================================================================================================
+// Sliced variant for larger classes: GS threads (in GS different warps of the CTA) share one quartet.
+// Thread `s` owns the MA = NA/GS Cartesian components ia = s*MA .. s*MA+MA-1 of shell a and ALL components of
+// b, c, d.  Roots, the VRR and the bra transfer are recomputed by each of the GS threads (FP64 is the cheap
+// resource; shared memory is not), the a-exponent of an owned component is picked from the register arrays by
+// select chains, so ONE instruction stream serves every slice.  J(a,b), K(a,c), K(a,d) are complete per thread;
+// the J(c,d), K(b,c), K(b,d) partial sums are combined across the GS threads through shared memory (fixed
+// order) before the fixed-point atomics.
+// ================================================================================================
+#define TPQS_PART_BYTES (40 * 1024)
+
+__host__ __device__ constexpr int tpqs_nq(int gs) { return gs <= 2 ? 64 : 32; }
+__host__ __device__ constexpr int tpqs_vc(int gs) { return TPQS_PART_BYTES / (gs * tpqs_nq(gs) * 8); }
+__host__ __device__ constexpr size_t tpqs_smem(int nroots, int gs) {
+    return sizeof(double) * (size_t)(tpq_table_len(nroots) + TPQ_NBRA * TPQ_MAXBP + tpqs_vc(gs) * gs * tpqs_nq(gs));
+}
+// slices per quartet for a class (0: not covered by the sliced kernels); per-thread outputs <= 60
+__host__ __device__ constexpr int tpqs_gs(int la, int lb, int lc, int ld) {
+    const int na = cf_ncart(la), rest = cf_ncart(lb) * cf_ncart(lc) * cf_ncart(ld);
+    if (na * rest <= TPQ_MAX_NOUT) return 0;       // plain thread-per-quartet
+    for (int gs = 2; gs <= na; gs++)
+        if (na % gs == 0 && (na / gs) * rest <= 60) return gs;
+    return 0;
+}
+
+template <int N>
+__device__ __forceinline__ double sel_reg(const double* v, int idx) {
+    double r = v[0];
+#pragma unroll
+    for (int i = 1; i < N; i++) r = (idx == i) ? v[i] : r;
+    return r;
+}
+
+// VRR + bra transfer of one root and one Cartesian direction: b[j][i][k] = [i j | k 0], k <= LC+LD
+template <int LA, int LB, int LCD>
+__device__ __forceinline__ void rys_2d_bra(double w0, double c00, double c00p, double b10, double b01, double b00, double ab,
+                                           double (&b)[LB + 1][LA + 1][LCD + 1]) {
+    constexpr int LAB = LA + LB;
+    double a[LAB + 1][LCD + 1];
+    a[0][0] = w0;
+    if (LAB > 0) a[1][0] = c00 * w0;
+#pragma unroll
+    for (int i = 1; i < LAB; i++) a[i + 1][0] = fma(c00, a[i][0], (i * b10) * a[i - 1][0]);
+#pragma unroll
+    for (int k = 0; k < LCD; k++) {
+#pragma unroll
+        for (int i = 0; i <= LAB; i++) {
+            double v = c00p * a[i][k];
+            if (k > 0) v = fma(k * b01, a[i][k - 1], v);
+            if (i > 0) v = fma(i * b00, a[i - 1][k], v);
+            a[i][k + 1] = v;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k <= LCD; k++) {
+        double h[LAB + 1];
+#pragma unroll
+        for (int i = 0; i <= LAB; i++) h[i] = a[i][k];
+#pragma unroll
+        for (int i = 0; i <= LA; i++) b[0][i][k] = h[i];
+#pragma unroll
+        for (int j = 1; j <= LB; j++) {
+#pragma unroll
+            for (int i = 0; i <= LAB - j; i++) h[i] = fma(ab, h[i], h[i + 1]);
+#pragma unroll
+            for (int i = 0; i <= LA; i++) b[j][i][k] = h[i];
+        }
+    }
+}
+
+// pick a-exponent `ai` (runtime), then the ket transfer: g[j][k][l] = [ai j | k l]
+template <int LA, int LB, int LC, int LD>
+__device__ __forceinline__ void rys_2d_ket(const double (&b)[LB + 1][LA + 1][LC + LD + 1], int ai, double cd,
+                                           double (&g)[LB + 1][LC + 1][LD + 1]) {
+    constexpr int LCD = LC + LD;
+#pragma unroll
+    for (int j = 0; j <= LB; j++) {
+        double c[LCD + 1];
+#pragma unroll
+        for (int k = 0; k <= LCD; k++) {
+            double cand[LA + 1];
+#pragma unroll
+            for (int i = 0; i <= LA; i++) cand[i] = b[j][i][k];
+            c[k] = sel_reg<LA + 1>(cand, ai);
+        }
+#pragma unroll
+        for (int l = 0; l <= LD; l++) {
+            if (l > 0) {
+#pragma unroll
+                for (int k = 0; k <= LCD - l; k++) c[k] = fma(cd, c[k], c[k + 1]);
+            }
+#pragma unroll
+            for (int k = 0; k <= LC; k++) g[j][k][l] = c[k];
+        }
+    }
+}
+
+#ifndef TPQS_MINB
+#define TPQS_MINB(nt) 1
+#endif
+template <int LA, int LB, int LC, int LD, int GS>
+__global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS))) eri_jk_tpqs(const QuartetTask t) {
+    constexpr int NA = cf_ncart(LA), NB = cf_ncart(LB), NC = cf_ncart(LC), ND = cf_ncart(LD);
+    constexpr int NCD = NC * ND, NBCD = NB * NCD;
+    constexpr int MA = NA / GS, NOUT_T = MA * NBCD;
+    constexpr int NROOTS = (LA + LB + LC + LD) / 2 + 1;
+    constexpr int LCD = LC + LD;
+    constexpr int TABLEN = tpq_table_len(NROOTS);
+    constexpr int NQ = tpqs_nq(GS), NT = GS * NQ, VC = tpqs_vc(GS);
+    static_assert(NA % GS == 0, "slices must divide the components of shell a");
+    extern __shared__ double smem[];
+    double* tab = smem;
+    double* sbra = smem + TABLEN;                   // [TPQ_NBRA][TPQ_MAXBP]
+    double* part = sbra + TPQ_NBRA * TPQ_MAXBP;     // [VC][GS][NQ]
+
+    if constexpr (NROOTS <= 2) {
+        constexpr int M = 2 * NROOTS - 1;
+        for (int e = threadIdx.x; e < BOYS_NROW * 8; e += NT) tab[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
+    } else {
+        constexpr int NTAB = (rys_tmax(NROOTS) / 2) * 2 * NROOTS * RYS_NC;
+        const double* src = t.rys.table + rys_off(NROOTS);
+        for (int e = threadIdx.x; e < NTAB; e += NT) tab[e] = src[e];
+        if (threadIdx.x < 2 * NROOTS) tab[NTAB + threadIdx.x] = t.rys.asym[rys_asym_off(NROOTS) + threadIdx.x];
+    }
+
+    const int q = threadIdx.x % NQ, s = threadIdx.x / NQ;   // s is warp-uniform
+    int eax[MA], eay[MA], eaz[MA];
+#pragma unroll
+    for (int m = 0; m < MA; m++) {
+        const int ia = s * MA + m;
+        eax[m] = cart_lx(LA, ia); eay[m] = cart_ly(LA, ia); eaz[m] = cart_lz(LA, ia);
+    }
+
+    const long long nitem_local = (t.nitem - t.rank + t.world - 1) / t.world;
+    for (long long li = blockIdx.x; li < nitem_local; li += gridDim.x) {
+        const long long item = li * t.world + t.rank;
+        int ib, chunk;
+        if (t.same_class) {
+            int lo = 0, hi = t.bra.npair;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (t.item_off[mid] <= item) lo = mid; else hi = mid;
+            }
+            ib = lo; chunk = (int)(item - t.item_off[lo]);
+        } else {
+            ib = (int)(item / t.nchunk_ket); chunk = (int)(item - (long long)ib * t.nchunk_ket);
+        }
+        const int ik = chunk * NQ + q;
+        bool active = ik < t.ket.npair && (!t.same_class || ik <= ib);
+        if (active && t.thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > t.thr;
+
+        const int sa = t.bra.sa[ib], sb = t.bra.sb[ib];
+        const double Ax = t.bra.A[3 * ib], Ay = t.bra.A[3 * ib + 1], Az = t.bra.A[3 * ib + 2];
+        const double ABx = t.bra.AB[3 * ib], ABy = t.bra.AB[3 * ib + 1], ABz = t.bra.AB[3 * ib + 2];
+        const int pab0 = t.bra.pbase[ib], npab = t.bra.nprim[ib];
+
+        int sc = 0, sd = 0, pcd0 = 0, npcd = 0;
+        double Cx = 0, Cy = 0, Cz = 0, CDx = 0, CDy = 0, CDz = 0;
+        if (active) {
+            sc = t.ket.sa[ik]; sd = t.ket.sb[ik];
+            Cx = t.ket.A[3 * ik]; Cy = t.ket.A[3 * ik + 1]; Cz = t.ket.A[3 * ik + 2];
+            CDx = t.ket.AB[3 * ik]; CDy = t.ket.AB[3 * ik + 1]; CDz = t.ket.AB[3 * ik + 2];
+            pcd0 = t.ket.pbase[ik]; npcd = t.ket.nprim[ik];
+        }
+        double wgt = (sa == sb ? 1.0 : 2.0) * (sc == sd ? 1.0 : 2.0);
+        wgt *= (t.same_class && ib == ik) ? 1.0 : 2.0;
+
+        double gout[NOUT_T];
+#pragma unroll
+        for (int n = 0; n < NOUT_T; n++) gout[n] = 0.0;
+
+        for (int b0 = 0; b0 < npab; b0 += TPQ_MAXBP) {
+            const int nb = min(TPQ_MAXBP, npab - b0);
+            __syncthreads();
+            if (threadIdx.x < nb) {
+                const int sl = pab0 + (b0 + threadIdx.x) * CF_PSTRIDE;
+                const double px = t.bra.Px[sl], py = t.bra.Py[sl], pz = t.bra.Pz[sl];
+                sbra[0 * TPQ_MAXBP + threadIdx.x] = t.bra.p[sl];
+                sbra[1 * TPQ_MAXBP + threadIdx.x] = t.bra.hp[sl];
+                sbra[2 * TPQ_MAXBP + threadIdx.x] = px;
+                sbra[3 * TPQ_MAXBP + threadIdx.x] = py;
+                sbra[4 * TPQ_MAXBP + threadIdx.x] = pz;
+                sbra[5 * TPQ_MAXBP + threadIdx.x] = t.bra.c[sl];
+                sbra[6 * TPQ_MAXBP + threadIdx.x] = px - Ax;
+                sbra[7 * TPQ_MAXBP + threadIdx.x] = py - Ay;
+                sbra[8 * TPQ_MAXBP + threadIdx.x] = pz - Az;
+            }
+            __syncthreads();
+            if (!active) continue;
+            for (int icd = 0; icd < npcd; icd++) {
+                const int scd = pcd0 + icd * CF_PSTRIDE;
+                const double qe = t.ket.p[scd], hq = t.ket.hp[scd], ccd = t.ket.c[scd] * wgt;
+                const double Qx = t.ket.Px[scd], Qy = t.ket.Py[scd], Qz = t.ket.Pz[scd];
+                const double QCx = Qx - Cx, QCy = Qy - Cy, QCz = Qz - Cz;
+                for (int iab = 0; iab < nb; iab++) {
+                    const double cc = sbra[5 * TPQ_MAXBP + iab] * ccd;
+                    if (fabs(cc) < t.prim_cut) continue;
+                    const double p = sbra[iab], hp = sbra[TPQ_MAXBP + iab];
+                    const double PQx = sbra[2 * TPQ_MAXBP + iab] - Qx, PQy = sbra[3 * TPQ_MAXBP + iab] - Qy,
+                                 PQz = sbra[4 * TPQ_MAXBP + iab] - Qz;
+                    const double PAx = sbra[6 * TPQ_MAXBP + iab], PAy = sbra[7 * TPQ_MAXBP + iab], PAz = sbra[8 * TPQ_MAXBP + iab];
+                    const double pq = p + qe;
+                    const double rs = rsqrt(pq), ipq = rs * rs;
+                    const double T = (p * qe * ipq) * fma(PQx, PQx, fma(PQy, PQy, PQz * PQz));
+                    const double pref = cc * rs;
+                    double rx[NROOTS], rw[NROOTS];
+                    tpq_roots<NROOTS>(tab, T, rx, rw);
+                    const double qi = qe * ipq, pi_ = p * ipq, hi = 0.5 * ipq;
+#pragma unroll
+                    for (int r = 0; r < NROOTS; r++) {
+                        const double xr = rx[r];
+                        const double rxp = xr * qi, rxq = xr * pi_, b00 = xr * hi;
+                        const double b10 = fma(-rxp, hp, hp), b01 = fma(-rxq, hq, hq);
+                        double bx[LB + 1][LA + 1][LCD + 1], by[LB + 1][LA + 1][LCD + 1], bz[LB + 1][LA + 1][LCD + 1];
+                        rys_2d_bra<LA, LB, LCD>(1.0, fma(-rxp, PQx, PAx), fma(rxq, PQx, QCx), b10, b01, b00, ABx, bx);
+                        rys_2d_bra<LA, LB, LCD>(1.0, fma(-rxp, PQy, PAy), fma(rxq, PQy, QCy), b10, b01, b00, ABy, by);
+                        rys_2d_bra<LA, LB, LCD>(rw[r] * pref, fma(-rxp, PQz, PAz), fma(rxq, PQz, QCz), b10, b01, b00, ABz, bz);
+#pragma unroll
+                        for (int m = 0; m < MA; m++) {
+                            double gx[LB + 1][LC + 1][LD + 1], gy[LB + 1][LC + 1][LD + 1], gz[LB + 1][LC + 1][LD + 1];
+                            rys_2d_ket<LA, LB, LC, LD>(bx, eax[m], CDx, gx);
+                            rys_2d_ket<LA, LB, LC, LD>(by, eay[m], CDy, gy);
+                            rys_2d_ket<LA, LB, LC, LD>(bz, eaz[m], CDz, gz);
+#pragma unroll
+                            for (int n = 0; n < NBCD; n++) {
+                                const int id = n % ND, ic = (n / ND) % NC, jb = n / NCD;
+                                gout[m * NBCD + n] = fma(gx[cart_lx(LB, jb)][cart_lx(LC, ic)][cart_lx(LD, id)] *
+                                                             gy[cart_ly(LB, jb)][cart_ly(LC, ic)][cart_ly(LD, id)],
+                                                         gz[cart_lz(LB, jb)][cart_lz(LC, ic)][cart_lz(LD, id)], gout[m * NBCD + n]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- digestion ----------------------------------------------------------------------------
+        int ca = 0, cb = 0, cc0 = 0, cd0 = 0;
+        if (active) { ca = t.bra.cao_a[ib]; cb = t.bra.cao_b[ib]; cc0 = t.ket.cao_a[ik]; cd0 = t.ket.cao_b[ik]; }
+        const size_t ld = (size_t)t.ncart;
+        const int ia0 = s * MA;
+        // cross-slice sum of NV partial values through shared memory, chunk by chunk, then one fixed-point add each
+        auto reduce_add = [&](auto nv_tag, const double* pv, auto&& addr_of, long long* acc, double scale) {
+            constexpr int NV = decltype(nv_tag)::value;
+#pragma unroll
+            for (int c0 = 0; c0 < NV; c0 += VC) {
+                constexpr int dummy = 0; (void)dummy;
+                const int cn = (NV - c0) < VC ? (NV - c0) : VC;
+                __syncthreads();
+#pragma unroll
+                for (int v = 0; v < VC; v++)
+                    if (c0 + v < NV) part[(v * GS + s) * NQ + q] = pv[c0 + v];
+                __syncthreads();
+                if (active)
+                    for (int v = s; v < cn; v += GS) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int s2 = 0; s2 < GS; s2++) sum += part[(v * GS + s2) * NQ + q];
+                        fixed_add(acc + addr_of(c0 + v), sum, scale);
+                    }
+            }
+        };
+        {   // J(a,b) complete; J(c,d) partial over the owned a components
+            double dcd[NCD], jcd[NCD];
+#pragma unroll
+            for (int kl = 0; kl < NCD; kl++) { dcd[kl] = active ? t.Dtot[(cd0 + kl % ND) * ld + cc0 + kl / ND] : 0.0; jcd[kl] = 0.0; }
+#pragma unroll
+            for (int m = 0; m < MA; m++)
+#pragma unroll
+                for (int j = 0; j < NB; j++) {
+                    const size_t off = (cb + j) * ld + ca + ia0 + m;
+                    const double dab = active ? t.Dtot[off] : 0.0;
+                    double sum = 0.0;
+#pragma unroll
+                    for (int kl = 0; kl < NCD; kl++) {
+                        sum = fma(gout[(m * NB + j) * NCD + kl], dcd[kl], sum);
+                        jcd[kl] = fma(gout[(m * NB + j) * NCD + kl], dab, jcd[kl]);
+                    }
+                    if (active) fixed_add(t.accJ + off, sum, t.scaleJ);
+                }
+            reduce_add(std::integral_constant<int, NCD>{}, jcd,
+                       [&](int kl) { return (size_t)(cd0 + kl % ND) * ld + cc0 + kl / ND; }, t.accJ, t.scaleJ);
+        }
+        for (int x = 0; x < t.nk; x++) {
+            const double* __restrict__ D = t.Dk[x];
+            long long* acc = t.accK[x];
+            if (active) {
+                {   // K(a,c) += sum_bd V D(b,d)   (complete)
+                    double d[NB * ND];
+#pragma unroll
+                    for (int e = 0; e < NB * ND; e++) d[e] = D[(cd0 + e % ND) * ld + cb + e / ND];
+#pragma unroll
+                    for (int m = 0; m < MA; m++)
+#pragma unroll
+                        for (int k = 0; k < NC; k++) {
+                            double sum = 0.0;
+#pragma unroll
+                            for (int j = 0; j < NB; j++)
+#pragma unroll
+                                for (int l = 0; l < ND; l++) sum = fma(gout[((m * NB + j) * NC + k) * ND + l], d[j * ND + l], sum);
+                            fixed_add(acc + (cc0 + k) * ld + ca + ia0 + m, sum, t.scaleK);
+                        }
+                }
+                {   // K(a,d) += sum_bc V D(b,c)   (complete)
+                    double d[NB * NC];
+#pragma unroll
+                    for (int e = 0; e < NB * NC; e++) d[e] = D[(cc0 + e % NC) * ld + cb + e / NC];
+#pragma unroll
+                    for (int m = 0; m < MA; m++)
+#pragma unroll
+                        for (int l = 0; l < ND; l++) {
+                            double sum = 0.0;
+#pragma unroll
+                            for (int j = 0; j < NB; j++)
+#pragma unroll
+                                for (int k = 0; k < NC; k++) sum = fma(gout[((m * NB + j) * NC + k) * ND + l], d[j * NC + k], sum);
+                            fixed_add(acc + (cd0 + l) * ld + ca + ia0 + m, sum, t.scaleK);
+                        }
+                }
+            }
+            // K(b,c) += sum_ad V D(a,d) ; K(b,d) += sum_ac V D(a,c)   (partial over the owned a components)
+            double kp[NB * NC + NB * ND];
+#pragma unroll
+            for (int e = 0; e < NB * NC + NB * ND; e++) kp[e] = 0.0;
+#pragma unroll
+            for (int m = 0; m < MA; m++) {
+                double dad[ND], dac[NC];
+#pragma unroll
+                for (int l = 0; l < ND; l++) dad[l] = active ? D[(cd0 + l) * ld + ca + ia0 + m] : 0.0;
+#pragma unroll
+                for (int k = 0; k < NC; k++) dac[k] = active ? D[(cc0 + k) * ld + ca + ia0 + m] : 0.0;
+#pragma unroll
+                for (int j = 0; j < NB; j++)
+#pragma unroll
+                    for (int k = 0; k < NC; k++)
+#pragma unroll
+                        for (int l = 0; l < ND; l++) {
+                            const double v = gout[((m * NB + j) * NC + k) * ND + l];
+                            kp[j * NC + k] = fma(v, dad[l], kp[j * NC + k]);
+                            kp[NB * NC + j * ND + l] = fma(v, dac[k], kp[NB * NC + j * ND + l]);
+                        }
+            }
+            reduce_add(std::integral_constant<int, NB * NC + NB * ND>{}, kp,
+                       [&](int e) {
+                           if (e < NB * NC) return (size_t)(cc0 + e % NC) * ld + cb + e / NC;
+                           const int f = e - NB * NC;
+                           return (size_t)(cd0 + f % ND) * ld + cb + f / ND;
+                       }, acc, t.scaleK);
         }
     }
 }

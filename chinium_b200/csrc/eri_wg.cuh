@@ -1,0 +1,444 @@
+// eri_wg.cuh -- warp-group cooperative Rys kernels with fused J/K digestion for the large classes.
+//
+// A group of GS lanes of one warp owns one shell quartet (QW = 32/GS quartets per warp).  Notation: H = the
+// CTA-uniform ("held") shell pair (a,b): every lane keeps ALL NA*NB Cartesian components of it as register
+// accumulators; S = the per-quartet ("spread") shell pair (c,d): its NC*ND components are spread over the lanes of
+// the group, MK per lane.  The engine may hand the classes over in either order (integrals are symmetric in
+// (ab|cd) <-> (cd|ab)), so H is whichever pair gives the better register/lane fit.
+// Per primitive quartet the group works in three warp-synchronous phases (no CTA barrier in the primitive loop):
+//   A  2*NROOTS root/weight values, spread over the lanes (Chebyshev tables staged in shared memory)
+//   B  3*NROOTS (root, direction) tasks spread over the lanes: VRR + S-side transfer -> shared memory,
+//      laid out [c-exp][d-exp][i = 0..LA+LB] so that phase C reads contiguous columns
+//   C  every lane: per root and owned S component, 3 columns from shared memory, H-side transfer in registers,
+//      then 2*NA*NB DFMAs of assembly with compile-time indices (>= 4 DFMA per shared-memory double, which is
+//      the FP64 : shared-memory balance point of the SM)
+// Digestion: J(c,d) is complete per lane; J(a,b) and the four K blocks are combined across the lanes of the group
+// through the same shared-memory scratch (fixed order), then added as 64-bit fixed point.
+// Replaces libint2's engine.compute + the reference's stored-integral digestion
+// (src/Integral/Int4C2E.cpp:233-302 and :601-671).
+#pragma once
+#include "eri_tpq.cuh"
+
+#define WG_WARPS 4
+
+template <int LA, int LB, int LC, int LD, int MK>
+struct WgCfg {
+    static constexpr int NA = cf_ncart(LA), NB = cf_ncart(LB), NC = cf_ncart(LC), ND = cf_ncart(LD);
+    static constexpr int NAB = NA * NB, NCD = NC * ND;
+    static constexpr int NROOTS = (LA + LB + LC + LD) / 2 + 1;
+    static constexpr int LAB = LA + LB, LCD = LC + LD;
+    static constexpr int GS = (NCD + MK - 1) / MK;
+    static constexpr int QW = 32 / GS;
+    static constexpr int NQ = QW * WG_WARPS;
+    static constexpr int LABP = (LAB + 2) & ~1;                    // column length padded to an even count
+    static constexpr int TSZ = (LC + 1) * (LD + 1) * LABP;         // one (root, direction)
+    static constexpr int RWP = (2 * NROOTS + 1) & ~1;
+    static constexpr int TQ = NROOTS * 3 * TSZ + RWP;
+    static constexpr int R1 = NAB * GS, R2 = (NA + NB) * NCD;
+    static constexpr int SCR = ((TQ > R1 ? (TQ > R2 ? TQ : R2) : (R1 > R2 ? R1 : R2)) + 1) & ~1;   // doubles per quartet
+    static constexpr int TABLEN = tpq_table_len(NROOTS);
+    static constexpr size_t SMEM = sizeof(double) * (size_t)(TABLEN + TPQ_NBRA * TPQ_MAXBP + WG_WARPS * QW * SCR);
+    static_assert(GS >= 1 && GS <= 32, "group does not fit a warp");
+};
+
+// one root/weight value (index v: roots 0..n-1, weights n..2n-1) from the staged Chebyshev table
+template <int NROOTS>
+__device__ __forceinline__ double wg_rys_value(const double* __restrict__ tab, double T, int v) {
+    constexpr int NV = 2 * NROOTS;
+    if (T >= (double)rys_tmax(NROOTS)) {
+        const double a = tab[(rys_tmax(NROOTS) / 2) * NV * RYS_NC + v];
+        const double rs = rsqrt(T);
+        return v < NROOTS ? a * rs * rs : a * rs;
+    }
+    const int it = (int)(T * 0.5);
+    const double u = T - (2.0 * it + 1.0), u2 = u + u;
+    const double2* cs = reinterpret_cast<const double2*>(tab + (size_t)(it * NV + v) * RYS_NC);
+    double2 c[RYS_NC / 2];
+#pragma unroll
+    for (int k = 0; k < RYS_NC / 2; k++) c[k] = cs[k];
+    double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+    for (int k = RYS_NC - 1; k >= 1; k--) {
+        const double ck = (k & 1) ? c[k >> 1].y : c[k >> 1].x;
+        const double tt = fma(u2, b1, ck - b2);
+        b2 = b1;
+        b1 = tt;
+    }
+    return fma(u, b1, c[0].x - b2);
+}
+
+// VRR + S-side (c->d) transfer of one root and one direction; out[(k*(LD+1)+l)*LABP + i] = [i 0 | k l]
+template <int LAB, int LC, int LD, int LABP>
+__device__ __forceinline__ void wg_vrr_ket(double w0, double c00, double c00p, double b10, double b01, double b00, double cd,
+                                           double* __restrict__ out) {
+    constexpr int LCD = LC + LD;
+    double a[LAB + 1][LCD + 1];
+    a[0][0] = w0;
+    if (LAB > 0) a[1][0] = c00 * w0;
+#pragma unroll
+    for (int i = 1; i < LAB; i++) a[i + 1][0] = fma(c00, a[i][0], (i * b10) * a[i - 1][0]);
+#pragma unroll
+    for (int k = 0; k < LCD; k++) {
+#pragma unroll
+        for (int i = 0; i <= LAB; i++) {
+            double v = c00p * a[i][k];
+            if (k > 0) v = fma(k * b01, a[i][k - 1], v);
+            if (i > 0) v = fma(i * b00, a[i - 1][k], v);
+            a[i][k + 1] = v;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l <= LD; l++) {
+        if (l > 0) {
+#pragma unroll
+            for (int k = 0; k <= LCD - l; k++)
+#pragma unroll
+                for (int i = 0; i <= LAB; i++) a[i][k] = fma(cd, a[i][k], a[i][k + 1]);
+        }
+#pragma unroll
+        for (int k = 0; k <= LC; k++) {
+            double* o = out + (k * (LD + 1) + l) * LABP;
+            if constexpr (((LAB + 1) & 1) == 0) {
+#pragma unroll
+                for (int i = 0; i <= LAB; i += 2) *reinterpret_cast<double2*>(o + i) = make_double2(a[i][k], a[i + 1][k]);
+            } else {
+#pragma unroll
+                for (int i = 0; i + 1 <= LAB; i += 2) *reinterpret_cast<double2*>(o + i) = make_double2(a[i][k], a[i + 1][k]);
+                o[LAB] = a[LAB][k];
+            }
+        }
+    }
+}
+
+// column [i = 0..LAB] -> H-side (a->b) transfer: g[j][i] = [i j | . .], i <= LA, j <= LB
+template <int LA, int LB, int LABP>
+__device__ __forceinline__ void wg_bra_hrr(const double* __restrict__ col, double ab, double (&g)[LB + 1][LA + 1]) {
+    constexpr int LAB = LA + LB;
+    double h[LABP];
+#pragma unroll
+    for (int i = 0; i < LABP; i += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(col + i);
+        h[i] = v.x; h[i + 1] = v.y;
+    }
+#pragma unroll
+    for (int i = 0; i <= LA; i++) g[0][i] = h[i];
+#pragma unroll
+    for (int j = 1; j <= LB; j++) {
+#pragma unroll
+        for (int i = 0; i <= LAB - j; i++) h[i] = fma(ab, h[i], h[i + 1]);
+#pragma unroll
+        for (int i = 0; i <= LA; i++) g[j][i] = h[i];
+    }
+}
+
+template <int LA, int LB, int LC, int LD, int MK>
+__global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) {
+    using C = WgCfg<LA, LB, LC, LD, MK>;
+    constexpr int NA = C::NA, NB = C::NB, NC = C::NC, ND = C::ND, NAB = C::NAB, NCD = C::NCD;
+    constexpr int NROOTS = C::NROOTS, LAB = C::LAB, GS = C::GS, QW = C::QW, NQ = C::NQ, LABP = C::LABP, TSZ = C::TSZ;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ double smem[];
+    double* tab = smem;
+    double* sbra = smem + C::TABLEN;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = lane / GS, g = lane - qi * GS;
+    const bool lane_ok = qi < QW;
+    double* myq = sbra + TPQ_NBRA * TPQ_MAXBP + (size_t)(warp * QW + (lane_ok ? qi : 0)) * C::SCR;   // this quartet's scratch
+    double* myrw = myq + NROOTS * 3 * TSZ;
+
+    // ---- stage the root tables ------------------------------------------------------------------
+    if constexpr (NROOTS <= 2) {
+        constexpr int M = 2 * NROOTS - 1;
+        for (int e = threadIdx.x; e < BOYS_NROW * 8; e += 32 * WG_WARPS) tab[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
+    } else {
+        constexpr int NTAB = (rys_tmax(NROOTS) / 2) * 2 * NROOTS * RYS_NC;
+        const double* src = t.rys.table + rys_off(NROOTS);
+        for (int e = threadIdx.x; e < NTAB; e += 32 * WG_WARPS) tab[e] = src[e];
+        if (threadIdx.x < 2 * NROOTS) tab[NTAB + threadIdx.x] = t.rys.asym[rys_asym_off(NROOTS) + threadIdx.x];
+    }
+
+    // owned S components f = g*MK + m = (ic, id); their exponents and column offsets inside one (root, direction) block
+    int fic[MK], fid[MK], colx[MK], coly[MK], colz[MK];
+    bool fok[MK];
+#pragma unroll
+    for (int m = 0; m < MK; m++) {
+        const int f = g * MK + m;
+        fok[m] = lane_ok && f < NCD;
+        const int ff = fok[m] ? f : 0;
+        fic[m] = ff / ND; fid[m] = ff - fic[m] * ND;
+        colx[m] = (cart_lx(LC, fic[m]) * (LD + 1) + cart_lx(LD, fid[m])) * LABP;
+        coly[m] = (cart_ly(LC, fic[m]) * (LD + 1) + cart_ly(LD, fid[m])) * LABP;
+        colz[m] = (cart_lz(LC, fic[m]) * (LD + 1) + cart_lz(LD, fid[m])) * LABP;
+    }
+
+    const long long nitem_local = (t.nitem - t.rank + t.world - 1) / t.world;
+    for (long long li = blockIdx.x; li < nitem_local; li += gridDim.x) {
+        const long long item = li * t.world + t.rank;
+        int ib, chunk;
+        if (t.same_class) {
+            int lo = 0, hi = t.bra.npair;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (t.item_off[mid] <= item) lo = mid; else hi = mid;
+            }
+            ib = lo; chunk = (int)(item - t.item_off[lo]);
+        } else {
+            ib = (int)(item / t.nchunk_ket); chunk = (int)(item - (long long)ib * t.nchunk_ket);
+        }
+        const int ik = chunk * NQ + warp * QW + qi;
+        bool active = lane_ok && ik < t.ket.npair && (!t.same_class || ik <= ib);
+        if (active && t.thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > t.thr;
+
+        const int sa = t.bra.sa[ib], sb = t.bra.sb[ib];
+        const double Ax = t.bra.A[3 * ib], Ay = t.bra.A[3 * ib + 1], Az = t.bra.A[3 * ib + 2];
+        const double ABx = t.bra.AB[3 * ib], ABy = t.bra.AB[3 * ib + 1], ABz = t.bra.AB[3 * ib + 2];
+        const int pab0 = t.bra.pbase[ib], npab = t.bra.nprim[ib];
+
+        int sc = 0, sd = 0, pcd0 = 0, npcd = 0;
+        double Cx = 0, Cy = 0, Cz = 0, CDx = 0, CDy = 0, CDz = 0;
+        if (active) {
+            sc = t.ket.sa[ik]; sd = t.ket.sb[ik];
+            Cx = t.ket.A[3 * ik]; Cy = t.ket.A[3 * ik + 1]; Cz = t.ket.A[3 * ik + 2];
+            CDx = t.ket.AB[3 * ik]; CDy = t.ket.AB[3 * ik + 1]; CDz = t.ket.AB[3 * ik + 2];
+            pcd0 = t.ket.pbase[ik]; npcd = t.ket.nprim[ik];
+        }
+        double wgt = (sa == sb ? 1.0 : 2.0) * (sc == sd ? 1.0 : 2.0);
+        wgt *= (t.same_class && ib == ik) ? 1.0 : 2.0;
+        const int npcd_w = __reduce_max_sync(FULL, npcd);
+
+        double acc[MK][NAB];
+#pragma unroll
+        for (int m = 0; m < MK; m++)
+#pragma unroll
+            for (int e = 0; e < NAB; e++) acc[m][e] = 0.0;
+
+        for (int b0 = 0; b0 < npab; b0 += TPQ_MAXBP) {
+            const int nb = min(TPQ_MAXBP, npab - b0);
+            __syncthreads();
+            if (threadIdx.x < nb) {
+                const int sl = pab0 + (b0 + threadIdx.x) * CF_PSTRIDE;
+                const double px = t.bra.Px[sl], py = t.bra.Py[sl], pz = t.bra.Pz[sl];
+                sbra[0 * TPQ_MAXBP + threadIdx.x] = t.bra.p[sl];
+                sbra[1 * TPQ_MAXBP + threadIdx.x] = t.bra.hp[sl];
+                sbra[2 * TPQ_MAXBP + threadIdx.x] = px;
+                sbra[3 * TPQ_MAXBP + threadIdx.x] = py;
+                sbra[4 * TPQ_MAXBP + threadIdx.x] = pz;
+                sbra[5 * TPQ_MAXBP + threadIdx.x] = t.bra.c[sl];
+                sbra[6 * TPQ_MAXBP + threadIdx.x] = px - Ax;
+                sbra[7 * TPQ_MAXBP + threadIdx.x] = py - Ay;
+                sbra[8 * TPQ_MAXBP + threadIdx.x] = pz - Az;
+            }
+            __syncthreads();
+            for (int icd = 0; icd < npcd_w; icd++) {
+                const bool vk = active && icd < npcd;
+                double qe = 1.0, hq = 0.5, ccd = 0.0, Qx = 0.0, Qy = 0.0, Qz = 0.0;
+                if (vk) {
+                    const int scd = pcd0 + icd * CF_PSTRIDE;
+                    qe = t.ket.p[scd]; hq = t.ket.hp[scd]; ccd = t.ket.c[scd] * wgt;
+                    Qx = t.ket.Px[scd]; Qy = t.ket.Py[scd]; Qz = t.ket.Pz[scd];
+                }
+                const double QCx = Qx - Cx, QCy = Qy - Cy, QCz = Qz - Cz;
+                for (int iab = 0; iab < nb; iab++) {
+                    const double cc = sbra[5 * TPQ_MAXBP + iab] * ccd;
+                    const bool valid = vk && fabs(cc) >= t.prim_cut;
+                    if (!__any_sync(FULL, valid)) continue;      // warp-uniform
+                    const double p = sbra[iab], hp = sbra[TPQ_MAXBP + iab];
+                    const double PQx = sbra[2 * TPQ_MAXBP + iab] - Qx, PQy = sbra[3 * TPQ_MAXBP + iab] - Qy,
+                                 PQz = sbra[4 * TPQ_MAXBP + iab] - Qz;
+                    const double pq = p + qe;
+                    const double rs = rsqrt(pq), ipq = rs * rs;
+                    const double T = (p * qe * ipq) * fma(PQx, PQx, fma(PQy, PQy, PQz * PQz));
+                    // ---- A: roots and weights ---------------------------------------------------------------
+                    if (valid) {
+                        if constexpr (NROOTS <= 2) {
+                            if (g == 0) { double rx[NROOTS], rw[NROOTS]; tpq_roots<NROOTS>(tab, T, rx, rw);
+#pragma unroll
+                                for (int r = 0; r < NROOTS; r++) { myrw[r] = rx[r]; myrw[NROOTS + r] = rw[r]; } }
+                        } else {
+                            for (int v = g; v < 2 * NROOTS; v += GS) myrw[v] = wg_rys_value<NROOTS>(tab, T, v);
+                        }
+                    }
+                    __syncwarp();
+                    // ---- B: VRR + S-side transfer, one (root, direction) per lane-task ---------------------------
+                    if (valid) {
+                        const double pref = cc * rs;
+                        const double qi_ = qe * ipq, pi_ = p * ipq, hi = 0.5 * ipq;
+                        for (int tk = g; tk < 3 * NROOTS; tk += GS) {
+                            const int r = tk / 3, dim = tk - 3 * r;
+                            const double xr = myrw[r];
+                            const double rxp = xr * qi_, rxq = xr * pi_, b00 = xr * hi;
+                            const double b10 = fma(-rxp, hp, hp), b01 = fma(-rxq, hq, hq);
+                            const double PQd = dim == 0 ? PQx : dim == 1 ? PQy : PQz;
+                            const double PAd = sbra[(6 + dim) * TPQ_MAXBP + iab];
+                            const double QCd = dim == 0 ? QCx : dim == 1 ? QCy : QCz;
+                            const double CDd = dim == 0 ? CDx : dim == 1 ? CDy : CDz;
+                            const double w0 = dim == 2 ? myrw[NROOTS + r] * pref : 1.0;
+                            wg_vrr_ket<LAB, LC, LD, LABP>(w0, fma(-rxp, PQd, PAd), fma(rxq, PQd, QCd), b10, b01, b00, CDd, myq + tk * TSZ);
+                        }
+                    }
+                    __syncwarp();
+                    // ---- C: H-side transfer + assembly ------------------------------------------------------------
+                    if (valid) {
+#pragma unroll 1
+                        for (int r = 0; r < NROOTS; r++) {
+                            const double* blk = myq + r * 3 * TSZ;
+#pragma unroll
+                            for (int m = 0; m < MK; m++) {
+                                if (!fok[m]) continue;
+                                double gx[LB + 1][LA + 1], gy[LB + 1][LA + 1], gz[LB + 1][LA + 1];
+                                wg_bra_hrr<LA, LB, LABP>(blk + colx[m], ABx, gx);
+                                wg_bra_hrr<LA, LB, LABP>(blk + TSZ + coly[m], ABy, gy);
+                                wg_bra_hrr<LA, LB, LABP>(blk + 2 * TSZ + colz[m], ABz, gz);
+#pragma unroll
+                                for (int e = 0; e < NAB; e++) {
+                                    const int ia = e / NB, jb = e % NB;
+                                    acc[m][e] = fma(gx[cart_lx(LB, jb)][cart_lx(LA, ia)] * gy[cart_ly(LB, jb)][cart_ly(LA, ia)],
+                                                    gz[cart_lz(LB, jb)][cart_lz(LA, ia)], acc[m][e]);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+
+        // ---- digestion (warp-synchronous; the quartet's scratch is free now) -----------------------------------
+        int ca = 0, cb = 0, cc0 = 0, cd0 = 0;
+        ca = t.bra.cao_a[ib]; cb = t.bra.cao_b[ib];
+        if (active) { cc0 = t.ket.cao_a[ik]; cd0 = t.ket.cao_b[ik]; }
+        const size_t ld = (size_t)t.ncart;
+        {   // J(c,d) complete per lane; J(a,b) partial over the lanes of the group
+            double dcd[MK], jcd[MK];
+#pragma unroll
+            for (int m = 0; m < MK; m++) { dcd[m] = (active && fok[m]) ? t.Dtot[(cd0 + fid[m]) * ld + cc0 + fic[m]] : 0.0; jcd[m] = 0.0; }
+#pragma unroll
+            for (int e = 0; e < NAB; e++) {
+                const double dab = t.Dtot[(cb + e % NB) * ld + ca + e / NB];
+                double pab = 0.0;
+#pragma unroll
+                for (int m = 0; m < MK; m++) { pab = fma(acc[m][e], dcd[m], pab); jcd[m] = fma(acc[m][e], dab, jcd[m]); }
+                if (active) myq[e * GS + g] = pab;
+            }
+#pragma unroll
+            for (int m = 0; m < MK; m++)
+                if (active && fok[m]) fixed_add(t.accJ + (cd0 + fid[m]) * ld + cc0 + fic[m], jcd[m], t.scaleJ);
+            __syncwarp();
+            if (active)
+                for (int e = g; e < NAB; e += GS) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int g2 = 0; g2 < GS; g2++) s += myq[e * GS + g2];
+                    fixed_add(t.accJ + (cb + e % NB) * ld + ca + e / NB, s, t.scaleJ);
+                }
+            __syncwarp();
+        }
+        for (int x = 0; x < t.nk; x++) {
+            const double* __restrict__ D = t.Dk[x];
+            long long* accK = t.accK[x];
+            // half 1: K(a,c) += sum_bd V D(b,d) ; K(b,c) += sum_ad V D(a,d)   -> slots [.., ic, id], summed over id
+            if (active) {
+#pragma unroll
+                for (int m = 0; m < MK; m++) {
+                    if (!fok[m]) continue;
+                    double dbd[NB], dad[NA];
+#pragma unroll
+                    for (int j = 0; j < NB; j++) dbd[j] = D[(cd0 + fid[m]) * ld + cb + j];
+#pragma unroll
+                    for (int i = 0; i < NA; i++) dad[i] = D[(cd0 + fid[m]) * ld + ca + i];
+                    double kbc[NB];
+#pragma unroll
+                    for (int j = 0; j < NB; j++) kbc[j] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NA; i++) {
+                        double kac = 0.0;
+#pragma unroll
+                        for (int j = 0; j < NB; j++) { kac = fma(acc[m][i * NB + j], dbd[j], kac); kbc[j] = fma(acc[m][i * NB + j], dad[i], kbc[j]); }
+                        myq[(i * NC + fic[m]) * ND + fid[m]] = kac;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NB; j++) myq[NA * NCD + (j * NC + fic[m]) * ND + fid[m]] = kbc[j];
+                }
+            }
+            __syncwarp();
+            if (active)
+                for (int tg = g; tg < (NA + NB) * NC; tg += GS) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int l = 0; l < ND; l++) s += myq[tg * ND + l];
+                    const int row = tg < NA * NC ? ca + tg / NC : cb + (tg - NA * NC) / NC;
+                    const int k = tg < NA * NC ? tg % NC : (tg - NA * NC) % NC;
+                    fixed_add(accK + (cc0 + k) * ld + row, s, t.scaleK);
+                }
+            __syncwarp();
+            // half 2: K(a,d) += sum_bc V D(b,c) ; K(b,d) += sum_ac V D(a,c)   -> slots [.., id, ic], summed over ic
+            if (active) {
+#pragma unroll
+                for (int m = 0; m < MK; m++) {
+                    if (!fok[m]) continue;
+                    double dbc[NB], dac[NA];
+#pragma unroll
+                    for (int j = 0; j < NB; j++) dbc[j] = D[(cc0 + fic[m]) * ld + cb + j];
+#pragma unroll
+                    for (int i = 0; i < NA; i++) dac[i] = D[(cc0 + fic[m]) * ld + ca + i];
+                    double kbd[NB];
+#pragma unroll
+                    for (int j = 0; j < NB; j++) kbd[j] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NA; i++) {
+                        double kad = 0.0;
+#pragma unroll
+                        for (int j = 0; j < NB; j++) { kad = fma(acc[m][i * NB + j], dbc[j], kad); kbd[j] = fma(acc[m][i * NB + j], dac[i], kbd[j]); }
+                        myq[(i * ND + fid[m]) * NC + fic[m]] = kad;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NB; j++) myq[NA * NCD + (j * ND + fid[m]) * NC + fic[m]] = kbd[j];
+                }
+            }
+            __syncwarp();
+            if (active)
+                for (int tg = g; tg < (NA + NB) * ND; tg += GS) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NC; k++) s += myq[tg * NC + k];
+                    const int row = tg < NA * ND ? ca + tg / ND : cb + (tg - NA * ND) / ND;
+                    const int l = tg < NA * ND ? tg % ND : (tg - NA * ND) % ND;
+                    fixed_add(accK + (cd0 + l) * ld + row, s, t.scaleK);
+                }
+            __syncwarp();
+        }
+    }
+}
+
+// class-pair -> warp-group configuration: MK | (swap << 8); 0 = not covered.  Classes are (la*(la+1)/2 + lb);
+// `swap` means the launcher hands the LOWER class over as the CTA-uniform (H) pair.
+__host__ __device__ constexpr int wg_cfg(int bra_cls, int ket_cls) {
+#ifdef CF_NO_WG
+    return 0;
+#else
+    switch (bra_cls * 10 + ket_cls) {
+        case 42: return 3;          // dp|pp
+        case 44: return 3;          // dp|dp
+        case 52: return 1;          // dd|pp
+        case 53: return 1;          // dd|ds
+        case 54: return 2;          // dd|dp
+        case 55: return 2;          // dd|dd
+        case 64: return 3 | 256;    // fs|dp  (H = dp)
+        case 65: return 2 | 256;    // fs|dd  (H = dd)
+        case 72: return 2;          // fp|pp
+        case 73: return 2;          // fp|ds
+        case 74: return 2;          // fp|dp
+        case 75: return 2 | 256;    // fp|dd  (H = dd)
+        case 76: return 2;          // fp|fs
+        case 77: return 2;          // fp|fp
+        case 81: return 1;          // fd|ps
+        case 82: return 1;          // fd|pp
+        case 83: return 1;          // fd|ds
+        case 84: return 4 | 256;    // fd|dp  (H = dp)
+        case 85: return 2 | 256;    // fd|dd  (H = dd)
+        case 86: return 1;          // fd|fs
+        case 87: return 1;          // fd|fp
+        default: return 0;
+    }
+#endif
+}
