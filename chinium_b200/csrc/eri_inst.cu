@@ -45,18 +45,19 @@ static cudaError_t launch_pair(const QuartetTask& t, int store, int grid, cudaSt
     if constexpr (wg_cfg(BRA, KET) != 0) {
         if (!store) {   // warp-group cooperative family
             constexpr int MK = wg_cfg(BRA, KET) & 255;
-            constexpr bool SWAP = (wg_cfg(BRA, KET) >> 8) != 0;
-            using C = typename std::conditional<SWAP, WgCfg<LC, LD, LA, LB, MK>, WgCfg<LA, LB, LC, LD, MK>>::type;
+            constexpr bool SWAP = ((wg_cfg(BRA, KET) >> 8) & 1) != 0;
+            constexpr int HS = (wg_cfg(BRA, KET) >> 12) ? (wg_cfg(BRA, KET) >> 12) : 1;
+            using C = typename std::conditional<SWAP, WgCfg<LC, LD, LA, LB, MK, HS>, WgCfg<LA, LB, LC, LD, MK, HS>>::type;
             if (g_out) *g_out = 32 * WG_WARPS;
             if (smem_out) *smem_out = C::SMEM;
             if (kind_out) *kind_out = 3 + (SWAP ? 8 : 0) + 16 * C::NQ;
             if (grid <= 0) return cudaSuccess;
             if constexpr (SWAP) {
-                auto k = eri_jk_wg<LC, LD, LA, LB, MK>;
+                auto k = eri_jk_wg<LC, LD, LA, LB, MK, HS>;
                 e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); if (e != cudaSuccess) return e;
                 k<<<grid, 32 * WG_WARPS, C::SMEM, s>>>(t);
             } else {
-                auto k = eri_jk_wg<LA, LB, LC, LD, MK>;
+                auto k = eri_jk_wg<LA, LB, LC, LD, MK, HS>;
                 e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); if (e != cudaSuccess) return e;
                 k<<<grid, 32 * WG_WARPS, C::SMEM, s>>>(t);
             }

@@ -21,7 +21,12 @@
 
 #define WG_WARPS 4
 
-template <int LA, int LB, int LC, int LD, int MK>
+template <int B, int E, class F>
+__device__ __forceinline__ void wg_static_for(F&& f) {
+    if constexpr (B < E) { f(std::integral_constant<int, B>{}); wg_static_for<B + 1, E>(f); }
+}
+
+template <int LA, int LB, int LC, int LD, int MK, int HS = 1>
 struct WgCfg {
     static constexpr int NA = cf_ncart(LA), NB = cf_ncart(LB), NC = cf_ncart(LC), ND = cf_ncart(LD);
     static constexpr int NAB = NA * NB, NCD = NC * ND;
@@ -30,15 +35,21 @@ struct WgCfg {
     static constexpr int GS = (NCD + MK - 1) / MK;
     static constexpr int QW = 32 / GS;
     static constexpr int NQ = QW * WG_WARPS;
-    static constexpr int LABP = (LAB + 2) & ~1;                    // column length padded to an even count
-    static constexpr int TSZ = (LC + 1) * (LD + 1) * LABP;         // one (root, direction)
+    // strides are kept == 2 (mod 4) doubles, i.e. an odd number of 16-byte chunks, so that the 8 lanes of a
+    // quarter-warp LDS.128/STS.128 phase that address different columns / blocks / quartets land in different banks
+    static constexpr int wg_pad(int n) { return n + ((6 - n % 4) % 4); }
+    static constexpr int LABP = wg_pad(LAB + 1);                   // column stride
+    static constexpr int TSZ = wg_pad((LC + 1) * (LD + 1) * LABP); // one (root, direction)
     static constexpr int RWP = (2 * NROOTS + 1) & ~1;
     static constexpr int TQ = NROOTS * 3 * TSZ + RWP;
-    static constexpr int R1 = NAB * GS, R2 = (NA + NB) * NCD;
-    static constexpr int SCR = ((TQ > R1 ? (TQ > R2 ? TQ : R2) : (R1 > R2 ? R1 : R2)) + 1) & ~1;   // doubles per quartet
+    static constexpr int NAP = NA / HS;                             // components of shell a handled per pass
+    static constexpr int NE = NAP * NB;                             // register accumulators per owned S component
+    static constexpr int R1 = NE * GS, R2 = (NAP + NB) * NCD;
+    static constexpr int SCR = wg_pad(TQ > R1 ? (TQ > R2 ? TQ : R2) : (R1 > R2 ? R1 : R2));   // doubles per quartet
     static constexpr int TABLEN = tpq_table_len(NROOTS);
     static constexpr size_t SMEM = sizeof(double) * (size_t)(TABLEN + TPQ_NBRA * TPQ_MAXBP + WG_WARPS * QW * SCR);
     static_assert(GS >= 1 && GS <= 32, "group does not fit a warp");
+    static_assert(NA % HS == 0, "passes must split the components of shell a evenly");
 };
 
 // one root/weight value (index v: roots 0..n-1, weights n..2n-1) from the staged Chebyshev table
@@ -114,9 +125,9 @@ __device__ __forceinline__ void wg_vrr_ket(double w0, double c00, double c00p, d
 template <int LA, int LB, int LABP>
 __device__ __forceinline__ void wg_bra_hrr(const double* __restrict__ col, double ab, double (&g)[LB + 1][LA + 1]) {
     constexpr int LAB = LA + LB;
-    double h[LABP];
+    double h[LAB + 2];
 #pragma unroll
-    for (int i = 0; i < LABP; i += 2) {
+    for (int i = 0; i <= LAB; i += 2) {
         const double2 v = *reinterpret_cast<const double2*>(col + i);
         h[i] = v.x; h[i + 1] = v.y;
     }
@@ -131,9 +142,12 @@ __device__ __forceinline__ void wg_bra_hrr(const double* __restrict__ col, doubl
     }
 }
 
-template <int LA, int LB, int LC, int LD, int MK>
+// HS > 1: the H components are processed in HS passes over the primitive loop (NA/HS components of shell a per pass),
+// so that the accumulators of one pass fit the register file; phases A and B are repeated per pass.
+template <int LA, int LB, int LC, int LD, int MK, int HS>
 __global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) {
-    using C = WgCfg<LA, LB, LC, LD, MK>;
+    using C = WgCfg<LA, LB, LC, LD, MK, HS>;
+    constexpr int NAP = C::NAP, NE = C::NE;
     constexpr int NA = C::NA, NB = C::NB, NC = C::NC, ND = C::ND, NAB = C::NAB, NCD = C::NCD;
     constexpr int NROOTS = C::NROOTS, LAB = C::LAB, GS = C::GS, QW = C::QW, NQ = C::NQ, LABP = C::LABP, TSZ = C::TSZ;
     constexpr unsigned FULL = 0xffffffffu;
@@ -206,11 +220,18 @@ __global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) 
         wgt *= (t.same_class && ib == ik) ? 1.0 : 2.0;
         const int npcd_w = __reduce_max_sync(FULL, npcd);
 
-        double acc[MK][NAB];
+        int ca = 0, cb = 0, cc0 = 0, cd0 = 0;
+        ca = t.bra.cao_a[ib]; cb = t.bra.cao_b[ib];
+        if (active) { cc0 = t.ket.cao_a[ik]; cd0 = t.ket.cao_b[ik]; }
+        const size_t ld = (size_t)t.ncart;
+
+        wg_static_for<0, HS>([&](auto hp_tag) {
+        constexpr int IA0 = decltype(hp_tag)::value * NAP;     // first component of shell a of this pass
+        double acc[MK][NE];
 #pragma unroll
         for (int m = 0; m < MK; m++)
 #pragma unroll
-            for (int e = 0; e < NAB; e++) acc[m][e] = 0.0;
+            for (int e = 0; e < NE; e++) acc[m][e] = 0.0;
 
         for (int b0 = 0; b0 < npab; b0 += TPQ_MAXBP) {
             const int nb = min(TPQ_MAXBP, npab - b0);
@@ -290,8 +311,8 @@ __global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) 
                                 wg_bra_hrr<LA, LB, LABP>(blk + TSZ + coly[m], ABy, gy);
                                 wg_bra_hrr<LA, LB, LABP>(blk + 2 * TSZ + colz[m], ABz, gz);
 #pragma unroll
-                                for (int e = 0; e < NAB; e++) {
-                                    const int ia = e / NB, jb = e % NB;
+                                for (int e = 0; e < NE; e++) {
+                                    const int ia = IA0 + e / NB, jb = e % NB;
                                     acc[m][e] = fma(gx[cart_lx(LB, jb)][cart_lx(LA, ia)] * gy[cart_ly(LB, jb)][cart_ly(LA, ia)],
                                                     gz[cart_lz(LB, jb)][cart_lz(LA, ia)], acc[m][e]);
                                 }
@@ -304,17 +325,13 @@ __global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) 
         }
 
         // ---- digestion (warp-synchronous; the quartet's scratch is free now) -----------------------------------
-        int ca = 0, cb = 0, cc0 = 0, cd0 = 0;
-        ca = t.bra.cao_a[ib]; cb = t.bra.cao_b[ib];
-        if (active) { cc0 = t.ket.cao_a[ik]; cd0 = t.ket.cao_b[ik]; }
-        const size_t ld = (size_t)t.ncart;
         {   // J(c,d) complete per lane; J(a,b) partial over the lanes of the group
             double dcd[MK], jcd[MK];
 #pragma unroll
             for (int m = 0; m < MK; m++) { dcd[m] = (active && fok[m]) ? t.Dtot[(cd0 + fid[m]) * ld + cc0 + fic[m]] : 0.0; jcd[m] = 0.0; }
 #pragma unroll
-            for (int e = 0; e < NAB; e++) {
-                const double dab = t.Dtot[(cb + e % NB) * ld + ca + e / NB];
+            for (int e = 0; e < NE; e++) {
+                const double dab = t.Dtot[(cb + e % NB) * ld + ca + IA0 + e / NB];
                 double pab = 0.0;
 #pragma unroll
                 for (int m = 0; m < MK; m++) { pab = fma(acc[m][e], dcd[m], pab); jcd[m] = fma(acc[m][e], dab, jcd[m]); }
@@ -325,11 +342,11 @@ __global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) 
                 if (active && fok[m]) fixed_add(t.accJ + (cd0 + fid[m]) * ld + cc0 + fic[m], jcd[m], t.scaleJ);
             __syncwarp();
             if (active)
-                for (int e = g; e < NAB; e += GS) {
+                for (int e = g; e < NE; e += GS) {
                     double s = 0.0;
 #pragma unroll
                     for (int g2 = 0; g2 < GS; g2++) s += myq[e * GS + g2];
-                    fixed_add(t.accJ + (cb + e % NB) * ld + ca + e / NB, s, t.scaleJ);
+                    fixed_add(t.accJ + (cb + e % NB) * ld + ca + IA0 + e / NB, s, t.scaleJ);
                 }
             __syncwarp();
         }
@@ -341,33 +358,33 @@ __global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) 
 #pragma unroll
                 for (int m = 0; m < MK; m++) {
                     if (!fok[m]) continue;
-                    double dbd[NB], dad[NA];
+                    double dbd[NB], dad[NAP];
 #pragma unroll
                     for (int j = 0; j < NB; j++) dbd[j] = D[(cd0 + fid[m]) * ld + cb + j];
 #pragma unroll
-                    for (int i = 0; i < NA; i++) dad[i] = D[(cd0 + fid[m]) * ld + ca + i];
+                    for (int i = 0; i < NAP; i++) dad[i] = D[(cd0 + fid[m]) * ld + ca + IA0 + i];
                     double kbc[NB];
 #pragma unroll
                     for (int j = 0; j < NB; j++) kbc[j] = 0.0;
 #pragma unroll
-                    for (int i = 0; i < NA; i++) {
+                    for (int i = 0; i < NAP; i++) {
                         double kac = 0.0;
 #pragma unroll
                         for (int j = 0; j < NB; j++) { kac = fma(acc[m][i * NB + j], dbd[j], kac); kbc[j] = fma(acc[m][i * NB + j], dad[i], kbc[j]); }
                         myq[(i * NC + fic[m]) * ND + fid[m]] = kac;
                     }
 #pragma unroll
-                    for (int j = 0; j < NB; j++) myq[NA * NCD + (j * NC + fic[m]) * ND + fid[m]] = kbc[j];
+                    for (int j = 0; j < NB; j++) myq[NAP * NCD + (j * NC + fic[m]) * ND + fid[m]] = kbc[j];
                 }
             }
             __syncwarp();
             if (active)
-                for (int tg = g; tg < (NA + NB) * NC; tg += GS) {
+                for (int tg = g; tg < (NAP + NB) * NC; tg += GS) {
                     double s = 0.0;
 #pragma unroll
                     for (int l = 0; l < ND; l++) s += myq[tg * ND + l];
-                    const int row = tg < NA * NC ? ca + tg / NC : cb + (tg - NA * NC) / NC;
-                    const int k = tg < NA * NC ? tg % NC : (tg - NA * NC) % NC;
+                    const int row = tg < NAP * NC ? ca + IA0 + tg / NC : cb + (tg - NAP * NC) / NC;
+                    const int k = tg < NAP * NC ? tg % NC : (tg - NAP * NC) % NC;
                     fixed_add(accK + (cc0 + k) * ld + row, s, t.scaleK);
                 }
             __syncwarp();
@@ -376,41 +393,42 @@ __global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) 
 #pragma unroll
                 for (int m = 0; m < MK; m++) {
                     if (!fok[m]) continue;
-                    double dbc[NB], dac[NA];
+                    double dbc[NB], dac[NAP];
 #pragma unroll
                     for (int j = 0; j < NB; j++) dbc[j] = D[(cc0 + fic[m]) * ld + cb + j];
 #pragma unroll
-                    for (int i = 0; i < NA; i++) dac[i] = D[(cc0 + fic[m]) * ld + ca + i];
+                    for (int i = 0; i < NAP; i++) dac[i] = D[(cc0 + fic[m]) * ld + ca + IA0 + i];
                     double kbd[NB];
 #pragma unroll
                     for (int j = 0; j < NB; j++) kbd[j] = 0.0;
 #pragma unroll
-                    for (int i = 0; i < NA; i++) {
+                    for (int i = 0; i < NAP; i++) {
                         double kad = 0.0;
 #pragma unroll
                         for (int j = 0; j < NB; j++) { kad = fma(acc[m][i * NB + j], dbc[j], kad); kbd[j] = fma(acc[m][i * NB + j], dac[i], kbd[j]); }
                         myq[(i * ND + fid[m]) * NC + fic[m]] = kad;
                     }
 #pragma unroll
-                    for (int j = 0; j < NB; j++) myq[NA * NCD + (j * ND + fid[m]) * NC + fic[m]] = kbd[j];
+                    for (int j = 0; j < NB; j++) myq[NAP * NCD + (j * ND + fid[m]) * NC + fic[m]] = kbd[j];
                 }
             }
             __syncwarp();
             if (active)
-                for (int tg = g; tg < (NA + NB) * ND; tg += GS) {
+                for (int tg = g; tg < (NAP + NB) * ND; tg += GS) {
                     double s = 0.0;
 #pragma unroll
                     for (int k = 0; k < NC; k++) s += myq[tg * NC + k];
-                    const int row = tg < NA * ND ? ca + tg / ND : cb + (tg - NA * ND) / ND;
-                    const int l = tg < NA * ND ? tg % ND : (tg - NA * ND) % ND;
+                    const int row = tg < NAP * ND ? ca + IA0 + tg / ND : cb + (tg - NAP * ND) / ND;
+                    const int l = tg < NAP * ND ? tg % ND : (tg - NAP * ND) % ND;
                     fixed_add(accK + (cd0 + l) * ld + row, s, t.scaleK);
                 }
             __syncwarp();
         }
+        });   // passes over the H components
     }
 }
 
-// class-pair -> warp-group configuration: MK | (swap << 8); 0 = not covered.  Classes are (la*(la+1)/2 + lb);
+// class-pair -> warp-group configuration: MK | (swap << 8) | (HS << 12); 0 = not covered (HS field 0 means 1).  Classes are (la*(la+1)/2 + lb);
 // `swap` means the launcher hands the LOWER class over as the CTA-uniform (H) pair.
 __host__ __device__ constexpr int wg_cfg(int bra_cls, int ket_cls) {
 #ifdef CF_NO_WG
@@ -438,6 +456,15 @@ __host__ __device__ constexpr int wg_cfg(int bra_cls, int ket_cls) {
         case 85: return 2 | 256;    // fd|dd  (H = dd)
         case 86: return 1;          // fd|fs
         case 87: return 1;          // fd|fp
+        case 88: return 2 | (2 << 12);          // fd|fd  two passes of 5 a-components
+        case 91: return 1 | (2 << 12);          // ff|ps
+        case 92: return 1 | (2 << 12);          // ff|pp
+        case 93: return 1 | (2 << 12);          // ff|ds
+        case 94: return 4 | 256;                // ff|dp  (H = dp)
+        case 95: return 4 | 256 | (2 << 12);    // ff|dd  (H = dd, two passes)
+        case 96: return 1 | (2 << 12);          // ff|fs
+        case 97: return 4 | 256 | (2 << 12);    // ff|fp  (H = fp, two passes)
+        case 98: return 2 | (5 << 12);          // ff|fd  five passes of 2 a-components
         default: return 0;
     }
 #endif
