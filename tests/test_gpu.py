@@ -239,3 +239,28 @@ def test_fe4s4_uhf_blocks(Int4C2E, oracle):
         assert np.abs(Jb - J[ia:ia + fb.nfun[sa], ib:ib + fb.nfun[sb]]).max() < TOL, (sa, sb)
         assert np.abs(Kab - Ka[ia:ia + fb.nfun[sa], ib:ib + fb.nfun[sb]]).max() < TOL, (sa, sb)
     eng.close()
+
+
+def test_cpp_adaptor_matches_oracle(Int4C2E, oracle, tmp_path):
+    """The C++ adaptor class (chinium_b200/cpp/Int4C2E_b200.hpp), driven like SelfConsistentField.cpp:47-53 +
+    Restricted/SP.cpp:47 by tests/cpp/adaptor_test.cpp, against the oracle."""
+    import subprocess
+    import cpp_adaptor
+    exe = cpp_adaptor.build()
+    mol, fb = load_fixture_molecule("h2o")
+    n = fb.nbf
+    D = H.random_symmetric_density(n, 0)
+    inp, outp = tmp_path / "in.txt", tmp_path / "out.txt"
+    cpp_adaptor.write_input(str(inp), fb, D)
+    r = subprocess.run([exe, str(inp), str(outp)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Done in" in r.stdout and "After screening" in r.stdout
+    lines = open(outp).read().split()
+    assert int(lines[0]) == 45150 and int(lines[1]) == 3081        # SURVEY 8d counts for h2o
+    v = np.array([float(x) for x in lines[2:]])
+    J = v[:n * n].reshape(n, n, order="F"); K = v[n * n:2 * n * n].reshape(n, n, order="F")
+    G = v[2 * n * n:3 * n * n].reshape(n, n, order="F")
+    Jo, Ko, _, _, _ = oracle.direct_jk(fb, D, exx=0.5)
+    assert np.abs(J - Jo).max() < TOL and np.abs(K - Ko).max() < TOL
+    assert np.abs(G - (Jo - Ko)).max() < TOL
+    assert v[3 * n * n] == 0.0      # absent Ka -> zeros

@@ -102,3 +102,18 @@ def test_bench_reference_arm_runs_on_cpu():
     import json
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and "cpu_baseline" in line
+
+
+def test_cpp_adaptor_compiles_and_fails_loudly_without_gpu(tmp_path, have_gpu):
+    """The C++ adaptor (reference's Int4C2E method names) builds against the C ABI; with no GPU it throws
+    instead of falling back."""
+    import cpp_adaptor
+    exe = cpp_adaptor.build()
+    if have_gpu:
+        pytest.skip("GPU present (covered by the gpu test)")
+    mol, fb = load_fixture_molecule("h2o")
+    inp = tmp_path / "in.txt"
+    cpp_adaptor.write_input(str(inp), fb, H.random_symmetric_density(fb.nbf, 0))
+    out = subprocess.run([exe, str(inp), str(tmp_path / "out.txt")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 3, (out.returncode, out.stderr)
+    assert "no CPU fallback" in out.stderr or "no CUDA device" in out.stderr
