@@ -66,8 +66,9 @@ struct QuartetTask {
     RysTablesDev rys;
     double prim_cut;        // skip primitive quartets with |c_ab c_cd| below this
     double thr;             // Cauchy-Schwarz threshold on Q_ab * Q_cd (<= 0: none), reference Int4C2E.cpp:108-113
-    // thread-per-quartet kernels: work item = (bra pair, chunk of TPQ ket pairs)
-    const long long* item_off;  // [bra.npair+1] first item of each bra pair (same_class only; else item = ib*nchunk_ket + chunk)
+    // work items of the thread-per-quartet / sliced / warp-group kernels: item = (x: bra pair, y: first ket pair,
+    // z: number of consecutive ket pairs <= NQ of the kernel).  The list is built on the device at setup from the
+    // Schwarz bounds (only ket runs that can pass Q_ab * Q_cd > thr are listed; triangular limit folded in).
+    const int4* items;
     long long nitem;
-    int nchunk_ket;
 };

@@ -68,7 +68,8 @@ struct PairClassHost {
     std::vector<int> sa, sb, cao_a, cao_b, prim_off, nprim, nprim_full;
     std::vector<double> A, AB, Q, Qpure, p, P, c;
     std::vector<int> order;          // device position -> canonical pair index
-    DevBuf<int> d_sa, d_sb, d_cao_a, d_cao_b, d_pbase, d_nprim;
+    std::vector<int> seg;            // device positions where the primitive count changes (+ npair): Q descends inside a segment
+    DevBuf<int> d_sa, d_sb, d_cao_a, d_cao_b, d_pbase, d_nprim, d_seg;
     DevBuf<double> d_A, d_AB, d_Q, d_Qcart, d_p, d_hp, d_Px, d_Py, d_Pz, d_c;
     int npair() const { return (int)sa.size(); }
     PairClassDev dev() const {
@@ -119,10 +120,14 @@ struct PairClassHost {
         if ((e = d_Px.upload(o_Px)) != cudaSuccess) return e;
         if ((e = d_Py.upload(o_Py)) != cudaSuccess) return e;
         if ((e = d_Pz.upload(o_Pz)) != cudaSuccess) return e;
+        seg.clear();
+        for (int i = 0; i < np; i++) if (i == 0 || o_np[i] != o_np[i - 1]) seg.push_back(i);
+        seg.push_back(np);
+        if ((e = d_seg.upload(seg)) != cudaSuccess) return e;
         return d_c.upload(o_c);
     }
     void release() {
-        d_sa.release(); d_sb.release(); d_cao_a.release(); d_cao_b.release(); d_pbase.release(); d_nprim.release();
+        d_sa.release(); d_sb.release(); d_cao_a.release(); d_cao_b.release(); d_pbase.release(); d_nprim.release(); d_seg.release();
         d_A.release(); d_AB.release(); d_Q.release(); d_Qcart.release(); d_p.release(); d_hp.release(); d_Px.release(); d_Py.release();
         d_Pz.release(); d_c.release();
     }
@@ -132,9 +137,8 @@ struct ClassPairTask {
     int bra = 0, ket = 0;
     long long nquartet = 0;          // all canonical quartets of the class pair (before Schwarz screening)
     DevBuf<long long> d_qoff;        // generic kernels: first quartet of each bra pair
-    DevBuf<long long> d_item_off;    // thread-per-quartet kernels, same class: first work item of each bra pair
+    DevBuf<int4> d_items;            // kinds 1,2,3: work items (uniform pair, first spread pair, count), built on the device
     long long nitem = 0;
-    int nchunk_ket = 0;
     int kind = 0;                    // 0 generic (CTA per quartet), 1 thread per quartet, 2 sliced thread per quartet
     int nq_item = 0;                 // kinds 1,2,3: ket pairs per work item
     int swap = 0;                    // kind 3: the LOWER class is handed to the kernel as the CTA-uniform pair
@@ -318,6 +322,47 @@ __global__ void schwarz_kernel(int npair, int nca, int ncb, const double* __rest
     if (threadIdx.x == 0) { Qcart[ip] = red[0][0]; Qpure[ip] = red[1][0]; }
 }
 
+// Work-item lists (SURVEY 8a a4-a6 replaced): one thread per CTA-uniform pair ih walks the primitive-count segments
+// of the spread class; inside a segment Q descends, so the pairs that can pass Q_H * Q_S > thr are a prefix found by
+// bisection.  Prefixes of adjacent segments are merged into contiguous runs (no screening: ONE run), and the runs are
+// cut into pieces of <= nq pairs = work items.  counts-only pass when items == nullptr.
+__global__ void item_list_kernel(int nH, const double* __restrict__ QH, const double* __restrict__ QS, const int* __restrict__ seg,
+                                 int nseg, int nq, double thr, int same, long long* __restrict__ counts,
+                                 const long long* __restrict__ offs, int4* __restrict__ items) {
+    const int ih = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ih >= nH) return;
+    const double need = thr > 0.0 ? thr / fmax(QH[ih], 1e-300) : -1.0;
+    long long n = 0;
+    int4* out = items ? items + offs[ih] : nullptr;
+    int run_lo = 0, run_hi = 0;                  // surviving prefixes of adjacent segments are merged into one run
+    auto flush = [&]() {
+        for (int k = run_lo; k < run_hi; k += nq) {
+            if (out) out[n] = make_int4(ih, k, min(nq, run_hi - k), 0);
+            n++;
+        }
+    };
+    for (int s = 0; s < nseg; s++) {
+        const int lo = seg[s];
+        int hi = seg[s + 1];
+        if (same) hi = min(hi, ih + 1);          // canonical quartets of a triangular task: spread pair <= uniform pair
+        if (hi <= lo) continue;
+        int len = hi - lo;
+        if (thr > 0.0) {                         // largest prefix with Q > need
+            int a = 0, b = len;
+            while (a < b) {
+                const int mid = (a + b) >> 1;
+                if (QS[lo + mid] > need) a = mid + 1; else b = mid;
+            }
+            len = a;
+        }
+        if (len == 0) continue;
+        if (run_hi == lo) run_hi = lo + len;
+        else { flush(); run_lo = lo; run_hi = lo + len; }
+    }
+    flush();
+    if (counts) counts[ih] = n;
+}
+
 // register-resident DFMA loop: the FP64 roofline denominator measured on the device itself
 __global__ void dfma_peak_kernel(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -388,15 +433,16 @@ static int launch_task(cf_handle* h, ClassPairTask* t, QuartetTask& qt, int stor
     qt.bra = B.dev(); qt.ket = K.dev();
     if (t->swap && !store) { qt.bra = K.dev(); qt.ket = B.dev(); }
     qt.qoff = t->d_qoff.p; qt.nquartet = t->nquartet;
-    qt.item_off = t->d_item_off.p; qt.nitem = t->nitem; qt.nchunk_ket = t->nchunk_ket;
+    qt.items = t->d_items.p; qt.nitem = t->nitem;
     qt.same_class = (t->bra == t->ket);
     qt.thr = h->opt.threshold > 0 ? h->opt.threshold : 0.0;
     const long long nq = qt.nquartet;
     if (nq == 0) return CF_OK;
     int grid;
     if (t->kind >= 1 && !store) {
-        const long long nlocal = (t->nitem - qt.rank + qt.world - 1) / qt.world;
+        long long nlocal = (t->nitem - qt.rank + qt.world - 1) / qt.world;
         if (nlocal <= 0) return CF_OK;
+        if (t->kind == 1) nlocal = (nlocal + TPQ_THREADS / 32 - 1) / (TPQ_THREADS / 32);   // warp-private items
         grid = (int)std::min<long long>(nlocal, 148LL * 16);
     } else {
         // chunk: enough chunks to fill the machine ~8x over, at most 64 quartets each
@@ -478,7 +524,7 @@ extern "C" void cf_destroy(cf_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (auto& c : h->cls) c.release();
-    for (auto* t : h->tasks) { t->d_qoff.release(); t->d_item_off.release(); delete t; }
+    for (auto* t : h->tasks) { t->d_qoff.release(); t->d_items.release(); delete t; }
     h->d_ctrans.release(); h->d_ct_off.release(); h->d_bf_off.release(); h->d_cao_off.release(); h->d_nfun.release(); h->d_ncartsh.release();
     h->d_rys_table.release(); h->d_rys_asym.release(); h->d_boys.release();
     for (auto& b : h->d_Dpure) b.release();
@@ -717,19 +763,26 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
             QuartetTask dummy{};
             for (int k = 0; k < 4; k++) { dummy.nk = k; g_bra_launch[cb](ck, dummy, 0, 0, 0, &t->G, &t->smem[k], &t->kind); }
             t->nq_item = t->kind >> 4; t->swap = (t->kind >> 3) & 1; t->kind &= 7;
-            if (t->kind >= 1 && t->swap) {   // rectangular task with the roles exchanged
-                t->nchunk_ket = (nb + t->nq_item - 1) / t->nq_item;
-                t->nitem = (long long)nk * t->nchunk_ket;
-            } else if (t->kind >= 1) {     // work items: (bra pair, chunk of nq_item ket pairs)
-                t->nchunk_ket = (nk + t->nq_item - 1) / t->nq_item;
-                if (same) {
-                    std::vector<long long> ioff(nb + 1, 0);
-                    for (int i = 0; i < nb; i++) ioff[i + 1] = ioff[i] + i / t->nq_item + 1;
-                    t->nitem = ioff[nb];
-                    if (t->d_item_off.upload(ioff) != cudaSuccess) { delete t; return fail("item_off upload failed"); }
-                } else {
-                    t->nitem = (long long)nb * t->nchunk_ket;
+            if (t->kind >= 1) {   // work items: (CTA-uniform pair, run of <= nq_item spread pairs); swap: roles exchanged
+                const PairClassHost& Hc = t->swap ? K : B;
+                const PairClassHost& Sc = t->swap ? B : K;
+                const int nH = Hc.npair(), nseg = (int)Sc.seg.size() - 1;
+                DevBuf<long long> d_cnt, d_off;
+                if (d_cnt.alloc(nH) != cudaSuccess || d_off.alloc(nH) != cudaSuccess) { delete t; return fail("cudaMalloc failed (item counts)"); }
+                const int tb = 128, gb = (nH + tb - 1) / tb;
+                item_list_kernel<<<gb, tb>>>(nH, Hc.d_Q.p, Sc.d_Q.p, Sc.d_seg.p, nseg, t->nq_item, thr, same ? 1 : 0, d_cnt.p, nullptr, nullptr);
+                std::vector<long long> cnt(nH), off(nH);
+                if (cudaMemcpy(cnt.data(), d_cnt.p, sizeof(long long) * nH, cudaMemcpyDeviceToHost) != cudaSuccess) { delete t; return fail("item count kernel failed"); }
+                long long tot = 0;
+                for (int i = 0; i < nH; i++) { off[i] = tot; tot += cnt[i]; }
+                t->nitem = tot;
+                if (tot > 0) {
+                    if (cudaMemcpy(d_off.p, off.data(), sizeof(long long) * nH, cudaMemcpyHostToDevice) != cudaSuccess ||
+                        t->d_items.alloc((size_t)tot) != cudaSuccess) { delete t; return fail("cudaMalloc failed (work items)"); }
+                    item_list_kernel<<<gb, tb>>>(nH, Hc.d_Q.p, Sc.d_Q.p, Sc.d_seg.p, nseg, t->nq_item, thr, same ? 1 : 0, nullptr, d_off.p, t->d_items.p);
+                    if (cudaDeviceSynchronize() != cudaSuccess) { delete t; return fail("item list kernel failed"); }
                 }
+                d_cnt.release(); d_off.release();
             } else {
                 std::vector<long long> qoff(nb + 1, 0);
                 for (int i = 0; i < nb; i++) qoff[i + 1] = qoff[i] + (same ? i + 1 : nk);

@@ -34,7 +34,7 @@ static cudaError_t launch_pair(const QuartetTask& t, int store, int grid, cudaSt
             constexpr size_t smem = tpq_smem(NROOTS);
             if (g_out) *g_out = TPQ_THREADS;
             if (smem_out) *smem_out = smem;
-            if (kind_out) *kind_out = 1 + 16 * TPQ_THREADS;
+            if (kind_out) *kind_out = 1 + 16 * 32;    // items of <= 32 kets, one per warp
             if (grid <= 0) return cudaSuccess;
             auto k = eri_jk_tpq<LA, LB, LC, LD>;
             if (smem > 48 * 1024) { e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }

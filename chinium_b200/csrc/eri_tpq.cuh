@@ -5,9 +5,9 @@
 // so any scheme that stages the 2-D Rys integrals in shared memory is LSU-bound by ~4x.  Here one thread owns one
 // shell quartet and keeps EVERYTHING in registers: roots, the 2-D recurrences of one root at a time, the
 // contracted Cartesian integrals and the digestion partial sums.  All index arithmetic is compile-time.
-//   work item  = (one bra shell pair, 128 consecutive ket shell pairs); bra primitive data is staged once per item
-//                in shared memory and read as warp-uniform broadcasts; ket primitives are interleaved in HBM so
-//                a warp reads them coalesced
+//   work item  = (one bra shell pair, <= 32 consecutive ket shell pairs), owned by ONE WARP (no CTA barrier in the
+//                item loop); bra primitive data is staged per warp in shared memory and read as warp-uniform
+//                broadcasts; ket primitives are interleaved in HBM so a warp reads them coalesced
 //   roots      = 1 or 2 roots: from Boys functions (8-term Taylor rows staged in shared memory + downward
 //                recursion, then the closed-form 1- and 2-point Gauss rules); >= 3 roots: Chebyshev tables
 //                staged in shared memory
@@ -21,7 +21,12 @@
 
 #define TPQ_THREADS 128
 #define TPQ_MAXBP 64
-#define TPQ_MAX_NOUT 64
+#ifndef TPQ_MAX_NOUT
+#define TPQ_MAX_NOUT 64  // largest Cartesian block one thread keeps in registers
+#endif
+#ifndef TPQS_MAX_T
+#define TPQS_MAX_T 60    // sliced kernels: largest per-thread share of the block
+#endif
 #define TPQ_NBRA 9       // p, hp, Px, Py, Pz, c, PAx, PAy, PAz
 
 __host__ __device__ constexpr bool tpq_ok(int la, int lb, int lc, int ld) {
@@ -30,8 +35,9 @@ __host__ __device__ constexpr bool tpq_ok(int la, int lb, int lc, int ld) {
 __host__ __device__ constexpr int tpq_table_len(int nroots) {
     return nroots <= 2 ? BOYS_NROW * 8 : (rys_tmax(nroots) / 2) * 2 * nroots * RYS_NC + 2 * nroots;
 }
+#define TPQ_WBP 32        // bra primitive pairs staged per pass and per warp by the thread-per-quartet kernel
 __host__ __device__ constexpr size_t tpq_smem(int nroots) {
-    return sizeof(double) * (size_t)(tpq_table_len(nroots) + TPQ_NBRA * TPQ_MAXBP);
+    return sizeof(double) * (size_t)(tpq_table_len(nroots) + (TPQ_THREADS / 32) * TPQ_NBRA * TPQ_WBP);
 }
 
 // Cartesian exponents of component n of angular momentum l (order: lx descending, then ly descending);
@@ -144,11 +150,13 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
     constexpr int NROOTS = (LA + LB + LC + LD) / 2 + 1;
     constexpr int GSZ = (LA + 1) * (LB + 1) * (LC + 1) * (LD + 1);
     constexpr int TABLEN = tpq_table_len(NROOTS);
+    constexpr int MAXBP = TPQ_WBP;
     extern __shared__ double smem[];
     double* tab = smem;
-    double* sbra = smem + TABLEN;   // [TPQ_NBRA][TPQ_MAXBP]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sbra = smem + TABLEN + warp * (TPQ_NBRA * MAXBP);   // this warp's [TPQ_NBRA][MAXBP]
 
-    // ---- stage the root tables ------------------------------------------------------------------
+    // ---- stage the root tables (once per CTA) ----------------------------------------------------
     if constexpr (NROOTS <= 2) {
         constexpr int M = 2 * NROOTS - 1;
         for (int e = threadIdx.x; e < BOYS_NROW * 8; e += TPQ_THREADS) tab[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
@@ -158,26 +166,22 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
         for (int e = threadIdx.x; e < NT; e += TPQ_THREADS) tab[e] = src[e];
         if (threadIdx.x < 2 * NROOTS) tab[NT + threadIdx.x] = t.rys.asym[rys_asym_off(NROOTS) + threadIdx.x];
     }
+    __syncthreads();
 
+    // ---- work items are WARP-private: (one bra pair) x (<= 32 consecutive ket pairs); no CTA barrier below -------
     const long long nitem_local = (t.nitem - t.rank + t.world - 1) / t.world;
-    for (long long li = blockIdx.x; li < nitem_local; li += gridDim.x) {
-        const long long item = li * t.world + t.rank;
-        int ib, chunk;
-        if (t.same_class) {
-            int lo = 0, hi = t.bra.npair;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (t.item_off[mid] <= item) lo = mid; else hi = mid;
-            }
-            ib = lo; chunk = (int)(item - t.item_off[lo]);
-        } else {
-            ib = (int)(item / t.nchunk_ket); chunk = (int)(item - (long long)ib * t.nchunk_ket);
-        }
-        const int ik = chunk * TPQ_THREADS + threadIdx.x;
-        bool active = ik < t.ket.npair && (!t.same_class || ik <= ib);
+    const long long gw = (long long)blockIdx.x * (TPQ_THREADS / 32) + warp, nw = (long long)gridDim.x * (TPQ_THREADS / 32);
+    int4 it_next = make_int4(0, 0, 0, 0);
+    if (gw < nitem_local) it_next = __ldg(t.items + gw * t.world + t.rank);
+    for (long long li = gw; li < nitem_local; li += nw) {
+        const int4 it = it_next;                      // descriptor of the next item is fetched one item ahead
+        if (li + nw < nitem_local) it_next = __ldg(t.items + (li + nw) * t.world + t.rank);
+        const int ib = it.x;
+        const int ik = it.y + lane;
+        bool active = lane < it.z;
         if (active && t.thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > t.thr;
 
-        // bra pair: uniform across the CTA
+        // bra pair: uniform across the warp
         const int sa = t.bra.sa[ib], sb = t.bra.sb[ib];
         const double Ax = t.bra.A[3 * ib], Ay = t.bra.A[3 * ib + 1], Az = t.bra.A[3 * ib + 2];
         const double ABx = t.bra.AB[3 * ib], ABy = t.bra.AB[3 * ib + 1], ABz = t.bra.AB[3 * ib + 2];
@@ -198,23 +202,23 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
 #pragma unroll
         for (int n = 0; n < NOUT; n++) gout[n] = 0.0;
 
-        for (int b0 = 0; b0 < npab; b0 += TPQ_MAXBP) {
-            const int nb = min(TPQ_MAXBP, npab - b0);
-            __syncthreads();   // tables staged / previous pass consumed
-            if (threadIdx.x < nb) {
-                const int s = pab0 + (b0 + threadIdx.x) * CF_PSTRIDE;
+        for (int b0 = 0; b0 < npab; b0 += MAXBP) {
+            const int nb = min(MAXBP, npab - b0);
+            __syncwarp();      // previous pass consumed
+            if (lane < nb) {
+                const int s = pab0 + (b0 + lane) * CF_PSTRIDE;
                 const double px = t.bra.Px[s], py = t.bra.Py[s], pz = t.bra.Pz[s];
-                sbra[0 * TPQ_MAXBP + threadIdx.x] = t.bra.p[s];
-                sbra[1 * TPQ_MAXBP + threadIdx.x] = t.bra.hp[s];
-                sbra[2 * TPQ_MAXBP + threadIdx.x] = px;
-                sbra[3 * TPQ_MAXBP + threadIdx.x] = py;
-                sbra[4 * TPQ_MAXBP + threadIdx.x] = pz;
-                sbra[5 * TPQ_MAXBP + threadIdx.x] = t.bra.c[s];
-                sbra[6 * TPQ_MAXBP + threadIdx.x] = px - Ax;
-                sbra[7 * TPQ_MAXBP + threadIdx.x] = py - Ay;
-                sbra[8 * TPQ_MAXBP + threadIdx.x] = pz - Az;
+                sbra[0 * MAXBP + lane] = t.bra.p[s];
+                sbra[1 * MAXBP + lane] = t.bra.hp[s];
+                sbra[2 * MAXBP + lane] = px;
+                sbra[3 * MAXBP + lane] = py;
+                sbra[4 * MAXBP + lane] = pz;
+                sbra[5 * MAXBP + lane] = t.bra.c[s];
+                sbra[6 * MAXBP + lane] = px - Ax;
+                sbra[7 * MAXBP + lane] = py - Ay;
+                sbra[8 * MAXBP + lane] = pz - Az;
             }
-            __syncthreads();
+            __syncwarp();
             if (!active) continue;
             for (int icd = 0; icd < npcd; icd++) {
                 const int scd = pcd0 + icd * CF_PSTRIDE;
@@ -222,12 +226,12 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
                 const double Qx = t.ket.Px[scd], Qy = t.ket.Py[scd], Qz = t.ket.Pz[scd];
                 const double QCx = Qx - Cx, QCy = Qy - Cy, QCz = Qz - Cz;
                 for (int iab = 0; iab < nb; iab++) {
-                    const double cc = sbra[5 * TPQ_MAXBP + iab] * ccd;
+                    const double cc = sbra[5 * MAXBP + iab] * ccd;
                     if (fabs(cc) < t.prim_cut) continue;
-                    const double p = sbra[iab], hp = sbra[TPQ_MAXBP + iab];
-                    const double PQx = sbra[2 * TPQ_MAXBP + iab] - Qx, PQy = sbra[3 * TPQ_MAXBP + iab] - Qy,
-                                 PQz = sbra[4 * TPQ_MAXBP + iab] - Qz;
-                    const double PAx = sbra[6 * TPQ_MAXBP + iab], PAy = sbra[7 * TPQ_MAXBP + iab], PAz = sbra[8 * TPQ_MAXBP + iab];
+                    const double p = sbra[iab], hp = sbra[MAXBP + iab];
+                    const double PQx = sbra[2 * MAXBP + iab] - Qx, PQy = sbra[3 * MAXBP + iab] - Qy,
+                                 PQz = sbra[4 * MAXBP + iab] - Qz;
+                    const double PAx = sbra[6 * MAXBP + iab], PAy = sbra[7 * MAXBP + iab], PAz = sbra[8 * MAXBP + iab];
                     const double pq = p + q;
                     const double rs = rsqrt(pq), ipq = rs * rs;
                     const double T = (p * q * ipq) * fma(PQx, PQx, fma(PQy, PQy, PQz * PQz));
@@ -372,7 +376,7 @@ __host__ __device__ constexpr int tpqs_gs(int la, int lb, int lc, int ld) {
     const int na = cf_ncart(la), rest = cf_ncart(lb) * cf_ncart(lc) * cf_ncart(ld);
     if (na * rest <= TPQ_MAX_NOUT) return 0;       // plain thread-per-quartet
     for (int gs = 2; gs <= na; gs++)
-        if (na % gs == 0 && (na / gs) * rest <= 60) return gs;
+        if (na % gs == 0 && (na / gs) * rest <= TPQS_MAX_T) return gs;
     return 0;
 }
 
@@ -485,21 +489,14 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
     }
 
     const long long nitem_local = (t.nitem - t.rank + t.world - 1) / t.world;
+    int4 it_next = make_int4(0, 0, 0, 0);
+    if ((long long)blockIdx.x < nitem_local) it_next = __ldg(t.items + (long long)blockIdx.x * t.world + t.rank);
     for (long long li = blockIdx.x; li < nitem_local; li += gridDim.x) {
-        const long long item = li * t.world + t.rank;
-        int ib, chunk;
-        if (t.same_class) {
-            int lo = 0, hi = t.bra.npair;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (t.item_off[mid] <= item) lo = mid; else hi = mid;
-            }
-            ib = lo; chunk = (int)(item - t.item_off[lo]);
-        } else {
-            ib = (int)(item / t.nchunk_ket); chunk = (int)(item - (long long)ib * t.nchunk_ket);
-        }
-        const int ik = chunk * NQ + q;
-        bool active = ik < t.ket.npair && (!t.same_class || ik <= ib);
+        const int4 it = it_next;                      // descriptor of the next item is fetched one item ahead
+        if (li + gridDim.x < nitem_local) it_next = __ldg(t.items + (li + gridDim.x) * t.world + t.rank);
+        const int ib = it.x;
+        const int ik = it.y + q;
+        bool active = q < it.z;
         if (active && t.thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > t.thr;
 
         const int sa = t.bra.sa[ib], sb = t.bra.sb[ib];

@@ -186,21 +186,14 @@ __global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) 
     }
 
     const long long nitem_local = (t.nitem - t.rank + t.world - 1) / t.world;
+    int4 it_next = make_int4(0, 0, 0, 0);
+    if ((long long)blockIdx.x < nitem_local) it_next = __ldg(t.items + (long long)blockIdx.x * t.world + t.rank);
     for (long long li = blockIdx.x; li < nitem_local; li += gridDim.x) {
-        const long long item = li * t.world + t.rank;
-        int ib, chunk;
-        if (t.same_class) {
-            int lo = 0, hi = t.bra.npair;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (t.item_off[mid] <= item) lo = mid; else hi = mid;
-            }
-            ib = lo; chunk = (int)(item - t.item_off[lo]);
-        } else {
-            ib = (int)(item / t.nchunk_ket); chunk = (int)(item - (long long)ib * t.nchunk_ket);
-        }
-        const int ik = chunk * NQ + warp * QW + qi;
-        bool active = lane_ok && ik < t.ket.npair && (!t.same_class || ik <= ib);
+        const int4 it = it_next;                      // descriptor of the next item is fetched one item ahead
+        if (li + gridDim.x < nitem_local) it_next = __ldg(t.items + (li + gridDim.x) * t.world + t.rank);
+        const int ib = it.x;
+        const int ik = it.y + warp * QW + qi;
+        bool active = lane_ok && warp * QW + qi < it.z;
         if (active && t.thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > t.thr;
 
         const int sa = t.bra.sa[ib], sb = t.bra.sb[ib];

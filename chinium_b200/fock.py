@@ -14,7 +14,8 @@ import os
 
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libchinium_fock.so")
+# CHINIUM_FOCK_LIB: developer override used for A/B measurements of kernel variants (still an in-tree CUDA build)
+LIB_PATH = os.environ.get("CHINIUM_FOCK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libchinium_fock.so")
 
 
 class FockEngineError(RuntimeError):
