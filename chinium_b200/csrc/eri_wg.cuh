@@ -334,13 +334,23 @@ __global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) 
             for (int m = 0; m < MK; m++)
                 if (active && fok[m]) fixed_add(t.accJ + (cd0 + fid[m]) * ld + cc0 + fic[m], jcd[m], t.scaleJ);
             __syncwarp();
-            if (active)
-                for (int e = g; e < NE; e += GS) {
+            // J(a,b) is common to every quartet of the item: sum over ALL active quartets of the warp (fixed order) and
+            // issue one add per element and warp; lanes map to consecutive rows i, i.e. consecutive addresses
+            {
+                const unsigned amask = __ballot_sync(FULL, active);
+                const double* wq = myq - (size_t)(lane_ok ? qi : 0) * C::SCR;      // scratch of quartet 0 of this warp
+                for (int e2 = lane; e2 < NE; e2 += 32) {
+                    const int j = e2 / NAP, i = e2 - j * NAP, e = i * NB + j;
                     double s = 0.0;
 #pragma unroll
-                    for (int g2 = 0; g2 < GS; g2++) s += myq[e * GS + g2];
-                    fixed_add(t.accJ + (cb + e % NB) * ld + ca + IA0 + e / NB, s, t.scaleJ);
+                    for (int q2 = 0; q2 < QW; q2++)
+                        if ((amask >> (q2 * GS)) & 1u) {
+#pragma unroll
+                            for (int g2 = 0; g2 < GS; g2++) s += wq[(size_t)q2 * C::SCR + e * GS + g2];
+                        }
+                    if (amask) fixed_add(t.accJ + (cb + j) * ld + ca + IA0 + i, s, t.scaleJ);
                 }
+            }
             __syncwarp();
         }
         for (int x = 0; x < t.nk; x++) {
@@ -372,12 +382,12 @@ __global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) 
             }
             __syncwarp();
             if (active)
-                for (int tg = g; tg < (NAP + NB) * NC; tg += GS) {
+                for (int tg = g; tg < (NAP + NB) * NC; tg += GS) {     // rows fastest: consecutive lanes -> consecutive addresses
+                    const int k = tg / (NAP + NB), r = tg - k * (NAP + NB);
                     double s = 0.0;
 #pragma unroll
-                    for (int l = 0; l < ND; l++) s += myq[tg * ND + l];
-                    const int row = tg < NAP * NC ? ca + IA0 + tg / NC : cb + (tg - NAP * NC) / NC;
-                    const int k = tg < NAP * NC ? tg % NC : (tg - NAP * NC) % NC;
+                    for (int l = 0; l < ND; l++) s += myq[(r * NC + k) * ND + l];
+                    const int row = r < NAP ? ca + IA0 + r : cb + (r - NAP);
                     fixed_add(accK + (cc0 + k) * ld + row, s, t.scaleK);
                 }
             __syncwarp();
@@ -408,11 +418,11 @@ __global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) 
             __syncwarp();
             if (active)
                 for (int tg = g; tg < (NAP + NB) * ND; tg += GS) {
+                    const int l = tg / (NAP + NB), r = tg - l * (NAP + NB);
                     double s = 0.0;
 #pragma unroll
-                    for (int k = 0; k < NC; k++) s += myq[tg * NC + k];
-                    const int row = tg < NAP * ND ? ca + IA0 + tg / ND : cb + (tg - NAP * ND) / ND;
-                    const int l = tg < NAP * ND ? tg % ND : (tg - NAP * ND) % ND;
+                    for (int k = 0; k < NC; k++) s += myq[(r * ND + l) * NC + k];
+                    const int row = r < NAP ? ca + IA0 + r : cb + (r - NAP);
                     fixed_add(accK + (cd0 + l) * ld + row, s, t.scaleK);
                 }
             __syncwarp();
