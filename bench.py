@@ -32,6 +32,7 @@ import numpy as np  # noqa: E402
 WORKLOADS = {  # name -> (fixture, kind)
     "h2o": ("h2o", "rhf"), "bo3h3": ("bo3h3", "rks_exx0.2"), "c18": ("c18", "rhf"), "fe4s4": ("fe4s4", "uhf"), "h2o64": ("h2o64", "rhf"),
 }
+DEFAULT_THRESHOLD = {"h2o64": 1e-13}
 CLASS_NAMES = ["ss", "ps", "pp", "ds", "dp", "dd", "fs", "fp", "fd", "ff"]
 
 
@@ -161,6 +162,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c18", choices=sorted(WORKLOADS))
+    ap.add_argument("--threshold", type=float, default=None,
+                    help="Cauchy-Schwarz threshold (Int4C2E's `threshold`); default: -1 (the reference's value, no screening) "
+                         "except h2o64, where the unscreened job is 2.7e11 quartets: 1e-13 (see DESIGN.md)")
     ap.add_argument("--per-class", action="store_true", help="also time every class-pair kernel alone (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -187,7 +191,8 @@ def main():
     fixture, kind = WORKLOADS[args.workload]
     mol, fb = load_fixture_molecule(fixture)
     t0 = time.perf_counter()
-    eng = DistributedInt4C2E(fb, exx_of(kind), -1.0)
+    thr = args.threshold if args.threshold is not None else DEFAULT_THRESHOLD.get(args.workload, -1.0)
+    eng = DistributedInt4C2E(fb, exx_of(kind), thr)
     setup_s = time.perf_counter() - t0
     Dd, Da, Db = densities(fb.nbf, kind)
     present = [D is not None for D in (Dd, Da, Db)]
@@ -255,6 +260,7 @@ def main():
             "config": {"workload": "%s (%s, nbf %d, %d canonical shell quartets, %d unique integrals)" % (
                            args.workload, kind, fb.nbf, total_q, st0["unique_integrals"]),
                        "densities": "seeded random symmetric (SURVEY 8d stress density), nK=%d, EXX=%.1f" % (nk, exx_of(kind)),
+                       "schwarz_threshold": thr,
                        "l2": "flushed between timed iterations (256 MiB write, outside the step events)",
                        "partition": "static chunk-interleaved split of every class-pair quartet range over %d rank(s); "
                                     "int64 all-reduce" % world,

@@ -163,7 +163,8 @@ struct cf_handle {
     std::vector<ClassPairTask*> tasks;
     DevBuf<double> d_rys_table, d_rys_asym, d_boys;
     // per-build work space
-    DevBuf<double> d_Dpure[3], d_Dcart[4] /* 0: Dtot, 1..3: Dk */, d_out[4] /* pure J,Kd,Ka,Kb */, d_partial, d_scales, d_diag;
+    DevBuf<double> d_Dpure[3], d_Dcart[4] /* 0: Dtot, 1..3: Dk */, d_out[4] /* pure J,Kd,Ka,Kb */, d_partial, d_scales, d_diag,
+        d_QS /* [nshell^2] Cartesian Schwarz bound per shell pair */, d_B /* [4][nshell^2] block 1-norms of |D_cart| */, d_rwork;
     DevBuf<long long> d_acc;
     double qmax_cart = 0;
     cudaEvent_t ev[4];
@@ -187,8 +188,10 @@ __global__ void pure_to_cart_kernel(int nshell, int nbf, int ncart, const double
                                     const double* __restrict__ Db, double fd, double fa, double fb,
                                     const double* __restrict__ ctrans, const int* __restrict__ ct_off, const int* __restrict__ bf_off,
                                     const int* __restrict__ cao_off, const int* __restrict__ nfun, const int* __restrict__ ncsh,
-                                    double* __restrict__ out) {
+                                    double* __restrict__ out, double* __restrict__ bnorm) {
     const int sa = blockIdx.x, sb = blockIdx.y;
+    __shared__ double sh[64];
+    double asum = 0.0;
     const int na = nfun[sa], nb = nfun[sb], nca = ncsh[sa], ncb = ncsh[sb];
     const double* Ca = ctrans + ct_off[sa];
     const double* Cb = ctrans + ct_off[sb];
@@ -208,7 +211,16 @@ __global__ void pure_to_cart_kernel(int nshell, int nbf, int ncart, const double
             }
         }
         out[(size_t)(cao_off[sb] + y) * ncart + cao_off[sa] + x] = s;
+        asum += fabs(s);
     }
+    // entrywise 1-norm of the Cartesian shell block (fixed-order tree: deterministic), used by the fixed-point scale bound
+    sh[threadIdx.x] = asum;
+    __syncthreads();
+    for (int w = 32; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bnorm[(size_t)sb * nshell + sa] = sh[0];
 }
 
 // out_pure(block) = factor * C_a [ (acc + acc^T) / scale ] C_b^T ; integer sum first (exact), one conversion.
@@ -243,32 +255,48 @@ __global__ void finalize_kernel(int nbf, int ncart, const long long* __restrict_
     }
 }
 
-// entrywise 1-norm partial sums in a FIXED order (deterministic): block b sums elements b, b+grid, ... per thread,
-// then a fixed tree in shared memory
-__global__ void norm1_partial_kernel(const double* __restrict__ a, size_t n, double* __restrict__ partial) {
-    __shared__ double sh[256];
-    double s = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += fabs(a[i]);
-    sh[threadIdx.x] = s;
+// Rigorous bounds on every partial sum the accumulators can hold, from the Cartesian Schwarz matrix
+// QS[a,b] >= sqrt((ij|ij)) for all i in a, j in b (0 for dropped pairs) and the block 1-norms B[c,d] of |D_cart|:
+//   block 0 (J):  sum_cd QS[c,d] B0[c,d]                    |rawJ_ij|  <= 8 QS_max * that
+//   block x (K):  max_a sum_b QS[a,b] r_b, r_b = sum_d Bx[b,d]     |rawK_ik|  <= 8 QS_max * that
+// All reductions run in a FIXED order (strided per thread, then a shared-memory tree): every rank derives bit-identical
+// scales from the same density.
+__global__ void bounds_kernel(int ns, const double* __restrict__ QS, const double* __restrict__ B, double* __restrict__ r_work,
+                              double* __restrict__ bounds) {
+    __shared__ double sh[1024];
+    const int x = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const double* Bx = B + (size_t)x * ns * ns;
+    double v = 0.0;
+    if (x == 0) {
+        for (size_t i = tid; i < (size_t)ns * ns; i += nt) v = fma(QS[i], Bx[i], v);
+    } else {
+        double* r = r_work + (size_t)x * ns;
+        for (int b = tid; b < ns; b += nt) {          // B is symmetric: column sums read contiguously
+            double sum = 0.0;
+            for (int d = 0; d < ns; d++) sum += Bx[(size_t)b * ns + d];
+            r[b] = sum;
+        }
+        __syncthreads();
+        for (int a = tid; a < ns; a += nt) {
+            double sum = 0.0;
+            for (int b = 0; b < ns; b++) sum = fma(QS[(size_t)a * ns + b], r[b], sum);
+            v = fmax(v, sum);
+        }
+    }
+    sh[tid] = v;
     __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
-        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    for (int w = nt / 2; w > 0; w >>= 1) {
+        if (tid < w) sh[tid] = (x == 0) ? sh[tid] + sh[tid + w] : fmax(sh[tid], sh[tid + w]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+    if (tid == 0) bounds[x] = sh[0];
 }
-// scales[0] = J scale, scales[1] = K scale (powers of two); bound = 16 * qmax^2 * ||D||_1
-__global__ void scales_kernel(const double* __restrict__ partial, int nblk, int nk, double qmax2, double* __restrict__ scales) {
+// scales[0] = J scale, scales[1] = K scale (powers of two), scales[2..3] = the bounds themselves
+__global__ void scales_kernel(const double* __restrict__ bounds, int nk, double qmax, double* __restrict__ scales) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double nj = 0.0;
-    for (int i = 0; i < nblk; i++) nj += partial[i];
     double nkmax = 0.0;
-    for (int x = 0; x < nk; x++) {
-        double s = 0.0;
-        for (int i = 0; i < nblk; i++) s += partial[(x + 1) * nblk + i];
-        nkmax = fmax(nkmax, s);
-    }
-    const double bj = 16.0 * qmax2 * nj, bk = 16.0 * qmax2 * nkmax;
+    for (int x = 0; x < nk; x++) nkmax = fmax(nkmax, bounds[1 + x]);
+    const double bj = 16.0 * qmax * bounds[0], bk = 16.0 * qmax * nkmax;
     int ej, ek;
     frexp(fmax(bj, 1e-300), &ej);
     frexp(fmax(bk, 1e-300), &ek);
@@ -531,6 +559,7 @@ extern "C" void cf_destroy(cf_handle* h) {
     for (auto& b : h->d_Dcart) b.release();
     for (auto& b : h->d_out) b.release();
     h->d_partial.release(); h->d_scales.release(); h->d_diag.release(); h->d_acc.release();
+    h->d_QS.release(); h->d_B.release(); h->d_rwork.release();
     for (auto& e : h->ev) cudaEventDestroy(e);
     for (int i = 0; i < 3; i++) { cudaStreamDestroy(h->side[i]); cudaEventDestroy(h->ev_join[i]); }
     cudaEventDestroy(h->ev_fork);
@@ -699,6 +728,16 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
         for (double q : c.Q) h->qmax_cart = std::max(h->qmax_cart, q);
         if (c.upload() != cudaSuccess) return fail("pair re-upload failed");
     }
+    {   // dense Cartesian Schwarz matrix over shell pairs (0 for pairs dropped by the primitive cutoff)
+        std::vector<double> QS((size_t)ns * ns, 0.0);
+        for (auto& c : h->cls)
+            for (int i = 0; i < c.npair(); i++) {
+                QS[(size_t)c.sa[i] * ns + c.sb[i]] = c.Q[i];
+                QS[(size_t)c.sb[i] * ns + c.sa[i]] = c.Q[i];
+            }
+        if (h->d_QS.upload(QS) != cudaSuccess || h->d_B.alloc(4 * (size_t)ns * ns) != cudaSuccess || h->d_rwork.alloc(4 * (size_t)ns) != cudaSuccess)
+            return fail("cudaMalloc failed (Schwarz matrix)");
+    }
 
     // ---- class-pair tasks.  Quartet (ib, ik) of a task is canonical iff ik <= ib when bra class == ket class.
     // Schwarz screening (threshold > 0, Int4C2E.cpp:108-113) is a per-quartet test Q_b * Q_k > thr inside the kernels;
@@ -866,21 +905,19 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
     CUDA_TRY(cudaEventRecord(h->ev[0], s));
     dim3 grid2(ns, ns);
     // total density 2Dd + Da + Db (Int4C2E.cpp:612-615) and the exchange densities, in the Cartesian working basis
+    const size_t ns2 = (size_t)ns * ns;
     pure_to_cart_kernel<<<grid2, 64, 0, s>>>(ns, nbf, ncart, Dd, Da, Db, 2.0, 1.0, 1.0, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
-                                             h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[0].p);
+                                             h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[0].p, h->d_B.p);
     h->stats.n_launches_last++;
     for (int x = 0; x < nk; x++) {
         pure_to_cart_kernel<<<grid2, 64, 0, s>>>(ns, nbf, ncart, dk[x], nullptr, nullptr, 1.0, 0.0, 0.0, h->d_ctrans.p, h->d_ct_off.p,
-                                                 h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[1 + x].p);
+                                                 h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[1 + x].p,
+                                                 h->d_B.p + (size_t)(1 + x) * ns2);
         h->stats.n_launches_last++;
     }
-    const int nblk = 256;
-    for (int x = 0; x <= nk; x++) {
-        norm1_partial_kernel<<<nblk, 256, 0, s>>>(h->d_Dcart[x].p, n2c, h->d_partial.p + (size_t)x * nblk);
-        h->stats.n_launches_last++;
-    }
-    scales_kernel<<<1, 32, 0, s>>>(h->d_partial.p, nblk, nk, h->qmax_cart * h->qmax_cart, h->d_scales.p);
-    h->stats.n_launches_last++;
+    bounds_kernel<<<1 + nk, 1024, 0, s>>>(ns, h->d_QS.p, h->d_B.p, h->d_rwork.p, h->d_partial.p);
+    scales_kernel<<<1, 32, 0, s>>>(h->d_partial.p, nk, h->qmax_cart, h->d_scales.p);
+    h->stats.n_launches_last += 2;
     CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * (1 + nk) * n2c, s));
     // the scales live on the device; the ERI kernels need them as values -> one small synchronous read
     double scales[4];

@@ -264,3 +264,43 @@ def test_cpp_adaptor_matches_oracle(Int4C2E, oracle, tmp_path):
     assert np.abs(J - Jo).max() < TOL and np.abs(K - Ko).max() < TOL
     assert np.abs(G - (Jo - Ko)).max() < TOL
     assert v[3 * n * n] == 0.0      # absent Ka -> zeros
+
+
+def test_h2o64_schwarz_screened_blocks(Int4C2E, oracle):
+    """(H2O)64 / def2-TZVP (nbf 2752; BASELINE config 5): the unscreened job is 2.7e11 quartets, so the engine runs it
+    with a Cauchy-Schwarz threshold (Int4C2E's `threshold`, Int4C2E.cpp:108-113) of 1e-13.  Sampled J/K blocks must still
+    match the UNSCREENED oracle to 1e-10 (the reference itself screens nothing)."""
+    mol, fb = load_fixture_molecule("h2o64")
+    n = fb.nbf
+    D = H.random_symmetric_density(n, 0)
+    eng = _engine(Int4C2E, fb, thr=1e-13)
+    st = eng.stats
+    assert 1.2e10 < st["canonical_quartets"] < 1.5e10          # 1.338e10 of 2.7375e11 survive
+    J, K, _, _ = eng.ContractInts(D, None, None, 1, 0)
+    assert np.abs(J - J.T).max() == 0 and np.abs(K - K.T).max() == 0
+    per = fb.nshell // 64   # shells per water molecule
+    for sa, sb in ((0, 0), (4, 7 * per + 2), (per * 20 + 9, per * 20 + 3), (per * 63 + 8, 5)):
+        Jb, Kb = oracle.jk_block(fb, 2 * D, D, sa, sb)
+        ia, ib = fb.shell2bf[sa], fb.shell2bf[sb]
+        assert np.abs(Jb - J[ia:ia + fb.nfun[sa], ib:ib + fb.nfun[sb]]).max() < TOL, (sa, sb)
+        assert np.abs(Kb - K[ia:ia + fb.nfun[sa], ib:ib + fb.nfun[sb]]).max() < TOL, (sa, sb)
+    eng.close()
+
+
+def test_schwarz_threshold_matches_reference_count(Int4C2E, oracle):
+    """threshold > 0: the surviving shell quartets / unique integrals follow the reference's predicate
+    sqrt(|Diag(bf1,bf2) Diag(bf3,bf4)|) > Threshold on the shell-pair maxima, and J/K stay within the bound."""
+    mol, fb = load_fixture_molecule("bo3h3")
+    D = H.random_symmetric_density(fb.nbf, 0)
+    full = _engine(Int4C2E, fb)
+    Jf, Kf, _, _ = full.ContractInts(D, None, None, 1, 0)
+    nfull = full.stats["canonical_quartets"]
+    full.close()
+    for thr in (1e-6, 1e-9):
+        eng = _engine(Int4C2E, fb, thr=thr)
+        st = eng.stats
+        assert 0 < st["canonical_quartets"] < nfull
+        J, K, _, _ = eng.ContractInts(D, None, None, 1, 0)
+        # every dropped quartet has |(ab|cd)| <= thr; at most nbf^2 of them touch one element, |D| <= 1/nbf
+        assert np.abs(J - Jf).max() < thr * fb.nbf * 4 and np.abs(K - Kf).max() < thr * fb.nbf * 4
+        eng.close()
