@@ -252,6 +252,14 @@ def main():
 
     if rank == 0:
         peak = measure_fp64_peak(local_rank)
+        traffic, traffic_note = None, None
+        try:   # DRAM bytes of one build from the committed ncu pass (profiles/ncu_traffic.json), not measured in this run
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+            if tj and world == 1:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                traffic_note = tj["source"] + "; ncu flushes L2 before every kernel, so this is an upper bound of the in-situ traffic"
+        except Exception:
+            pass
         flops = st0["flops_alg_jk"][nk] * world      # whole job (stats are per partition)
         line = {
             "metric": "ERI shell quartets/s (Fock J+K build)", "value": total_q / (ms_per_step * 1e-3), "unit": "quartets/s",
@@ -271,8 +279,10 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": flops / (eri_ms_last * 1e-3) / 1e12 / world, "peak": peak, "unit": "TFLOP/s",
-                         "frac": flops / (eri_ms_last * 1e-3) / 1e12 / world / peak, "traffic": None,
-                         "kernel": "eri_jk_generic<*> (all class-pair launches of one build, per GPU)", "ms": eri_ms_last,
+                         "frac": flops / (eri_ms_last * 1e-3) / 1e12 / world / peak, "traffic": traffic, "traffic_source": traffic_note,
+                         # D in + J/K out + 6 doubles per primitive pair (P pairs <-> P(P+1)/2 primitive quartets)
+                         "algorithmic_bytes": 2 * (1 + nk) * n2 + 48 * (2.0 * st0["primitive_quartets"]) ** 0.5,
+                         "kernel": "eri_jk_tpq/tpqs/wg<*> (all class-pair ERI+digestion launches of one build, per GPU)", "ms": eri_ms_last,
                          "flops_alg": flops, "peak_source": "measured in-run: register-resident DFMA loop (cf_measure_fp64_peak); "
                                                             "MEASURED_PEAKS.json has no FP64 entry"},
         }

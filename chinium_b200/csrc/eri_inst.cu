@@ -1,9 +1,22 @@
 // eri_inst.cu -- instantiates the generic quartet kernel for ONE bra pair class (-DCF_BRA=0..9) against
 // every ket class <= bra.  Compiled once per bra class so the 55 class pairs build in parallel.
+#include <cstdlib>
 #include <type_traits>
 #include "eri_generic.cuh"
 #include "eri_tpq.cuh"
 #include "eri_wg.cuh"
+
+// developer knob for A/B measurements of the warp-group configurations (see wg_cfg in eri_wg.cuh)
+static int cf_wg_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("CF_WG_VARIANT"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
+    return v;
+}
+
+template <int B, int E, class F>
+static inline void host_static_for(F&& f) {
+    if constexpr (B < E) { f(std::integral_constant<int, B>{}); host_static_for<B + 1, E>(f); }
+}
 
 #ifndef CF_BRA
 #error "compile with -DCF_BRA=<bra class index>"
@@ -43,25 +56,36 @@ static cudaError_t launch_pair(const QuartetTask& t, int store, int grid, cudaSt
         }
     }
     if constexpr (wg_cfg(BRA, KET) != 0) {
-        if (!store) {   // warp-group cooperative family
-            constexpr int MK = wg_cfg(BRA, KET) & 255;
-            constexpr bool SWAP = ((wg_cfg(BRA, KET) >> 8) & 1) != 0;
-            constexpr int HS = (wg_cfg(BRA, KET) >> 12) ? (wg_cfg(BRA, KET) >> 12) : 1;
-            using C = typename std::conditional<SWAP, WgCfg<LC, LD, LA, LB, MK, HS>, WgCfg<LA, LB, LC, LD, MK, HS>>::type;
-            if (g_out) *g_out = 32 * WG_WARPS;
-            if (smem_out) *smem_out = C::SMEM;
-            if (kind_out) *kind_out = 3 + (SWAP ? 8 : 0) + 16 * C::NQ;
-            if (grid <= 0) return cudaSuccess;
-            if constexpr (SWAP) {
-                auto k = eri_jk_wg<LC, LD, LA, LB, MK, HS>;
-                e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); if (e != cudaSuccess) return e;
-                k<<<grid, 32 * WG_WARPS, C::SMEM, s>>>(t);
-            } else {
-                auto k = eri_jk_wg<LA, LB, LC, LD, MK, HS>;
-                e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); if (e != cudaSuccess) return e;
-                k<<<grid, 32 * WG_WARPS, C::SMEM, s>>>(t);
-            }
-            return cudaGetLastError();
+        if (!store) {   // warp-group cooperative family; g_wg_variant picks among the compiled alternatives
+            bool done = false;
+            cudaError_t err = cudaSuccess;
+            host_static_for<0, CF_WG_NVAR>([&](auto vtag) {
+                constexpr int V = decltype(vtag)::value;
+                constexpr int CFG = wg_cfg(BRA, KET, V);
+                // identical configurations share one instantiation; the variant index only selects
+                if (done || (cf_wg_variant() % CF_WG_NVAR) != V) return;
+                done = true;
+                constexpr int MK = CFG & 255;
+                constexpr bool SWAP = ((CFG >> 8) & 1) != 0;
+                constexpr int HS = ((CFG >> 12) & 15) ? ((CFG >> 12) & 15) : 1;
+                constexpr int MINB = ((CFG >> 16) & 15) ? ((CFG >> 16) & 15) : 2;
+                using C = typename std::conditional<SWAP, WgCfg<LC, LD, LA, LB, MK, HS>, WgCfg<LA, LB, LC, LD, MK, HS>>::type;
+                if (g_out) *g_out = 32 * WG_WARPS;
+                if (smem_out) *smem_out = C::SMEM;
+                if (kind_out) *kind_out = 3 + (SWAP ? 8 : 0) + 16 * C::NQ;
+                if (grid <= 0) return;
+                if constexpr (SWAP) {
+                    auto k = eri_jk_wg<LC, LD, LA, LB, MK, HS, MINB>;
+                    err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); if (err != cudaSuccess) return;
+                    k<<<grid, 32 * WG_WARPS, C::SMEM, s>>>(t);
+                } else {
+                    auto k = eri_jk_wg<LA, LB, LC, LD, MK, HS, MINB>;
+                    err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); if (err != cudaSuccess) return;
+                    k<<<grid, 32 * WG_WARPS, C::SMEM, s>>>(t);
+                }
+                err = cudaGetLastError();
+            });
+            return err;
         }
     }
     if constexpr (tpqs_gs(LA, LB, LC, LD) > 0) {

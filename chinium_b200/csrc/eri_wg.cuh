@@ -144,8 +144,8 @@ __device__ __forceinline__ void wg_bra_hrr(const double* __restrict__ col, doubl
 
 // HS > 1: the H components are processed in HS passes over the primitive loop (NA/HS components of shell a per pass),
 // so that the accumulators of one pass fit the register file; phases A and B are repeated per pass.
-template <int LA, int LB, int LC, int LD, int MK, int HS>
-__global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) {
+template <int LA, int LB, int LC, int LD, int MK, int HS, int MINB = 2>
+__global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTask t) {
     using C = WgCfg<LA, LB, LC, LD, MK, HS>;
     constexpr int NAP = C::NAP, NE = C::NE;
     constexpr int NA = C::NA, NB = C::NB, NC = C::NC, ND = C::ND, NAB = C::NAB, NCD = C::NCD;
@@ -431,13 +431,18 @@ __global__ void __launch_bounds__(32 * WG_WARPS) eri_jk_wg(const QuartetTask t) 
     }
 }
 
-// class-pair -> warp-group configuration: MK | (swap << 8) | (HS << 12); 0 = not covered (HS field 0 means 1).  Classes are (la*(la+1)/2 + lb);
-// `swap` means the launcher hands the LOWER class over as the CTA-uniform (H) pair.
-__host__ __device__ constexpr int wg_cfg(int bra_cls, int ket_cls) {
-#ifdef CF_NO_WG
-    return 0;
-#else
-    switch (bra_cls * 10 + ket_cls) {
+// class-pair -> warp-group configuration: MK | (swap << 8) | (HS << 12) | (MINB << 16); 0 = not covered (HS field 0 means
+// 1, MINB field 0 means 2 resident CTAs per SM).  Classes are (la*(la+1)/2 + lb); `swap` means the launcher hands the LOWER
+// class over as the CTA-uniform (H) pair.  `variant` selects among alternatives compiled with -DCF_WG_NVAR=n for A/B
+// measurements (env CF_WG_VARIANT); the default build has only variant 0 = the measured best.
+// Measured (profiles/r01n_*): more resident CTAs with fewer quartets per warp do NOT help -- throughput follows the
+// number of quartets in flight per SM, so the large-H / large-MK shapes stay; three classes gain from MK = 1.
+#define WGC(mk, sw, hs, minb) ((mk) | ((sw) << 8) | ((hs) << 12) | ((minb) << 16))
+#ifndef CF_WG_NVAR
+#define CF_WG_NVAR 1
+#endif
+__host__ __device__ constexpr int wg_cfg_base(int key) {
+    switch (key) {
         case 42: return 3;          // dp|pp
         case 44: return 3;          // dp|dp
         case 52: return 1;          // dd|pp
@@ -445,9 +450,9 @@ __host__ __device__ constexpr int wg_cfg(int bra_cls, int ket_cls) {
         case 54: return 2;          // dd|dp
         case 55: return 2;          // dd|dd
         case 64: return 3 | 256;    // fs|dp  (H = dp)
-        case 65: return 2 | 256;    // fs|dd  (H = dd)
-        case 72: return 2;          // fp|pp
-        case 73: return 2;          // fp|ds
+        case 65: return WGC(1, 1, 1, 3);   // fs|dd  (H = dd), 10 lanes per quartet, 3 CTAs per SM
+        case 72: return WGC(1, 0, 1, 3);   // fp|pp
+        case 73: return WGC(1, 0, 1, 3);   // fp|ds
         case 74: return 2;          // fp|dp
         case 75: return 2 | 256;    // fp|dd  (H = dd)
         case 76: return 2;          // fp|fs
@@ -470,5 +475,22 @@ __host__ __device__ constexpr int wg_cfg(int bra_cls, int ket_cls) {
         case 98: return 2 | (5 << 12);          // ff|fd  five passes of 2 a-components
         default: return 0;
     }
+}
+__host__ __device__ constexpr int wg_cfg_alt1(int key) {   // scratch pad for the next A/B round
+    switch (key) {
+        default: return wg_cfg_base(key);
+    }
+}
+__host__ __device__ constexpr int wg_cfg_alt2(int key) {
+    switch (key) {
+        default: return wg_cfg_base(key);
+    }
+}
+__host__ __device__ constexpr int wg_cfg(int bra_cls, int ket_cls, int variant = 0) {
+#ifdef CF_NO_WG
+    return 0;
+#else
+    const int key = bra_cls * 10 + ket_cls;
+    return variant == 1 ? wg_cfg_alt1(key) : variant == 2 ? wg_cfg_alt2(key) : wg_cfg_base(key);
 #endif
 }
