@@ -60,7 +60,7 @@ struct QuartetTask {
     const double* Dk[3];    // Cartesian exchange densities
     long long* accJ;        // [ncart*ncart] fixed-point raw J
     long long* accK[3];
-    double scaleJ, scaleK;  // powers of two
+    const double* scales;   // device: [0] J scale, [1] K scale (powers of two, written by scales_kernel of this build)
     double* store;          // STORE mode: Cartesian blocks, NOUT doubles per quartet in flat order
     int diag;               // Schwarz mode: quartet q is (pair q | pair q)
     RysTablesDev rys;

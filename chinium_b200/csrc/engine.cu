@@ -167,6 +167,7 @@ struct cf_handle {
         d_QS /* [nshell^2] Cartesian Schwarz bound per shell pair */, d_B /* [4][nshell^2] block 1-norms of |D_cart| */, d_rwork;
     DevBuf<long long> d_acc;
     double qmax_cart = 0;
+    double scales_host[4] = {1, 1, 0, 0};   // copy of d_scales of the last synchronised build
     cudaEvent_t ev[4];
     cudaStream_t side[3];
     cudaEvent_t ev_fork, ev_join[3];
@@ -919,18 +920,8 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
     scales_kernel<<<1, 32, 0, s>>>(h->d_partial.p, nk, h->qmax_cart, h->d_scales.p);
     h->stats.n_launches_last += 2;
     CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * (1 + nk) * n2c, s));
-    // the scales live on the device; the ERI kernels need them as values -> one small synchronous read
-    double scales[4];
-    CUDA_TRY(cudaMemcpyAsync(scales, h->d_scales.p, sizeof(scales), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    h->stats.fixedpoint_scale_log2[0] = std::log2(scales[0]);
-    h->stats.fixedpoint_scale_log2[1] = std::log2(scales[1]);
-    // 62 bits below the rigorous bound are always available, i.e. ~1e-18 RELATIVE to the largest possible element;
-    // the only way to leave the representable range is a non-finite or absurdly large density
-    if (!(scales[0] > 0x1p-900) || !std::isfinite(scales[2]) || !std::isfinite(scales[3])) {
-        set_error(h, "fixed-point accumulator range exceeded: density contains non-finite or astronomically large entries");
-        return CF_ERR_RANGE;
-    }
+    // the scales stay on the device (kernels read them through QuartetTask::scales): no host synchronisation inside the
+    // build; the range check happens after the caller's synchronisation (check_scales)
     CUDA_TRY(cudaEventRecord(h->ev[1], s));
     // fan the class-pair kernels out over the caller's stream + 3 side streams (small launches overlap)
     CUDA_TRY(cudaEventRecord(h->ev_fork, s));
@@ -943,7 +934,7 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
         qt.Dtot = h->d_Dcart[0].p;
         for (int x = 0; x < nk; x++) { qt.Dk[x] = h->d_Dcart[1 + x].p; qt.accK[x] = (long long*)acc + (size_t)(1 + x) * n2c; }
         qt.accJ = (long long*)acc;
-        qt.scaleJ = scales[0]; qt.scaleK = scales[1];
+        qt.scales = h->d_scales.p;
         qt.store = nullptr; qt.diag = 0; qt.prim_cut = 1e-22;
         fill_rys(qt, h);
         cudaStream_t ts = (it % 4 == 0) ? s : h->side[it % 4 - 1];
@@ -999,6 +990,20 @@ extern "C" int cf_build_jk_device(cf_handle* h, int nbf, const double* Dd, const
     return rc;
 }
 
+// after a build has been synchronised: J/K scales and bounds of that build -> stats, and the range check.
+// 62 bits below the rigorous bound are always available; the only way to leave the representable range is a
+// non-finite or astronomically large density
+static int check_scales(cf_handle* h) {
+    const double* sc = h->scales_host;
+    h->stats.fixedpoint_scale_log2[0] = std::log2(sc[0]);
+    h->stats.fixedpoint_scale_log2[1] = std::log2(sc[1]);
+    if (!(sc[0] > 0x1p-900) || !(sc[1] > 0x1p-900) || !std::isfinite(sc[2]) || !std::isfinite(sc[3])) {
+        set_error(h, "fixed-point accumulator range exceeded: density contains non-finite or astronomically large entries");
+        return CF_ERR_RANGE;
+    }
+    return CF_OK;
+}
+
 static int fetch_times(cf_handle* h) {
     float a = 0, b = 0;
     if (cudaEventElapsedTime(&a, h->ev[0], h->ev[3]) == cudaSuccess) h->stats.ms_device_last = a;
@@ -1010,7 +1015,9 @@ static int fetch_times(cf_handle* h) {
 extern "C" int cf_sync_stats(cf_handle* h) {   // after a *_device call has been synchronised by the caller
     if (!h) return CF_ERR_BAD_ARGUMENT;
     cudaSetDevice(h->device);
-    return fetch_times(h);
+    fetch_times(h);
+    CUDA_TRY(cudaMemcpy(h->scales_host, h->d_scales.p, sizeof(h->scales_host), cudaMemcpyDeviceToHost));
+    return check_scales(h);
 }
 
 extern "C" int cf_build_jk(cf_handle* h, int nbf, const double* Dd, const double* Da, const double* Db, double exx,
@@ -1034,11 +1041,13 @@ extern "C" int cf_build_jk(cf_handle* h, int nbf, const double* Dd, const double
     double* outs[3] = {Kd, Ka, Kb};
     for (int k = 0; k < 3; k++)
         if (src[k]) CUDA_TRY(cudaMemcpyAsync(outs[k], h->d_out[1 + k].p, bytes, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpyAsync(h->scales_host, h->d_scales.p, sizeof(h->scales_host), cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaStreamSynchronize(0));
     CUDA_TRY(cudaGetLastError());
     fetch_times(h);
+    rc = check_scales(h);
     if (h->opt.verbose > 0) std::printf("Done in %f s\n", now_s() - t0);
-    return CF_OK;
+    return rc;
 }
 
 // Per-class-pair timing of the last densities' build (serialised, CUDA events): the measurement behind the
@@ -1049,8 +1058,6 @@ extern "C" int cf_profile_tasks(cf_handle* h, int nbf, const double* Dd_dev, con
     int rc = cf_accumulate_device(h, nbf, Dd_dev, Da_dev, Db_dev, exx, (int64_t*)h->d_acc.p, nullptr);   // sets densities + scales
     if (rc != CF_OK) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
-    double scales[4];
-    CUDA_TRY(cudaMemcpy(scales, h->d_scales.p, sizeof(scales), cudaMemcpyDeviceToHost));
     const double* dk[3]; int slot[3];
     const int nk = exchange_list(Dd_dev, Da_dev, Db_dev, exx, dk, slot);
     const size_t n2c = (size_t)h->ncart * h->ncart;
@@ -1063,7 +1070,7 @@ extern "C" int cf_profile_tasks(cf_handle* h, int nbf, const double* Dd_dev, con
         qt.rank = h->opt.rank; qt.world = h->opt.world_size; qt.ncart = h->ncart; qt.nk = nk;
         qt.Dtot = h->d_Dcart[0].p;
         for (int x = 0; x < nk; x++) { qt.Dk[x] = h->d_Dcart[1 + x].p; qt.accK[x] = h->d_acc.p + (size_t)(1 + x) * n2c; }
-        qt.accJ = h->d_acc.p; qt.scaleJ = scales[0]; qt.scaleK = scales[1]; qt.prim_cut = 1e-22;
+        qt.accJ = h->d_acc.p; qt.scales = h->d_scales.p; qt.prim_cut = 1e-22;
         fill_rys(qt, h);
         float best = 1e30f;
         for (int rep = 0; rep < 2; rep++) {

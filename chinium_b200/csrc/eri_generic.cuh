@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
     constexpr int NPL = (NOUT + G - 1) / G;   // outputs per lane
     // shared: rw[2*NROOTS] | g[NROOTS*3*GSZ] | V[NOUT] | D blocks
     extern __shared__ double smem[];
+    const double scaleJ = STORE ? 1.0 : __ldg(t.scales), scaleK = STORE ? 1.0 : __ldg(t.scales + 1);
     double* rw = smem;
     double* g = rw + 2 * NROOTS;
     double* V = g + NROOTS * 3 * GSZ;
@@ -272,11 +273,11 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
                 double s = 0.0;
                 if (e < NAB) {
                     for (int kl = 0; kl < NCD; kl++) s = fma(V[e * NCD + kl], Dcd[kl], s);
-                    fixed_add(t.accJ + (size_t)(cb + e % NB) * ld + ca + e / NB, s, t.scaleJ);
+                    fixed_add(t.accJ + (size_t)(cb + e % NB) * ld + ca + e / NB, s, scaleJ);
                 } else {
                     const int kl = e - NAB;
                     for (int ij = 0; ij < NAB; ij++) s = fma(V[ij * NCD + kl], Dab[ij], s);
-                    fixed_add(t.accJ + (size_t)(cdd + kl % ND) * ld + cc + kl / ND, s, t.scaleJ);
+                    fixed_add(t.accJ + (size_t)(cdd + kl % ND) * ld + cc + kl / ND, s, scaleJ);
                 }
             }
             // K targets, per density: ac, ad, bc, bd
@@ -292,22 +293,22 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
                         const int i = e / NC, k = e % NC;
                         for (int j = 0; j < NB; j++)
                             for (int l = 0; l < ND; l++) s = fma(V[((i * NB + j) * NC + k) * ND + l], dbd[j * ND + l], s);
-                        fixed_add(acc + (size_t)(cc + k) * ld + ca + i, s, t.scaleK);
+                        fixed_add(acc + (size_t)(cc + k) * ld + ca + i, s, scaleK);
                     } else if (e < NA * NC + NA * ND) {      // K(i,l) += sum_jk V D(j,k)
                         const int f = e - NA * NC, i = f / ND, l = f % ND;
                         for (int j = 0; j < NB; j++)
                             for (int k = 0; k < NC; k++) s = fma(V[((i * NB + j) * NC + k) * ND + l], dbc[j * NC + k], s);
-                        fixed_add(acc + (size_t)(cdd + l) * ld + ca + i, s, t.scaleK);
+                        fixed_add(acc + (size_t)(cdd + l) * ld + ca + i, s, scaleK);
                     } else if (e < NA * NC + NA * ND + NB * NC) {   // K(j,k) += sum_il V D(i,l)
                         const int f = e - NA * NC - NA * ND, j = f / NC, k = f % NC;
                         for (int i = 0; i < NA; i++)
                             for (int l = 0; l < ND; l++) s = fma(V[((i * NB + j) * NC + k) * ND + l], dad[i * ND + l], s);
-                        fixed_add(acc + (size_t)(cc + k) * ld + cb + j, s, t.scaleK);
+                        fixed_add(acc + (size_t)(cc + k) * ld + cb + j, s, scaleK);
                     } else {                                  // K(j,l) += sum_ik V D(i,k)
                         const int f = e - NA * NC - NA * ND - NB * NC, j = f / ND, l = f % ND;
                         for (int i = 0; i < NA; i++)
                             for (int k = 0; k < NC; k++) s = fma(V[((i * NB + j) * NC + k) * ND + l], dac[i * NC + k], s);
-                        fixed_add(acc + (size_t)(cdd + l) * ld + cb + j, s, t.scaleK);
+                        fixed_add(acc + (size_t)(cdd + l) * ld + cb + j, s, scaleK);
                     }
                 }
             }

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
     constexpr int TABLEN = tpq_table_len(NROOTS);
     constexpr int MAXBP = TPQ_WBP;
     extern __shared__ double smem[];
+    const double scaleJ = __ldg(t.scales), scaleK = __ldg(t.scales + 1);
     double* tab = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* sbra = smem + TABLEN + warp * (TPQ_NBRA * MAXBP);   // this warp's [TPQ_NBRA][MAXBP]
@@ -197,6 +198,26 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
         }
         double wgt = (sa == sb ? 1.0 : 2.0) * (sc == sd ? 1.0 : 2.0);
         wgt *= (t.same_class && ib == ik) ? 1.0 : 2.0;
+#ifdef CF_PREFETCH_D
+        if (active) {   // lines of the D elements read by the digestion -> L1 while the integrals are computed
+            const int pca = t.bra.cao_a[ib], pcb = t.bra.cao_b[ib], pcc = t.ket.cao_a[ik], pcd = t.ket.cao_b[ik];
+            const size_t pld = (size_t)t.ncart;
+#pragma unroll
+            for (int l = 0; l < ND; l++) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(t.Dtot + (pcd + l) * pld + pcc));
+                for (int x = 0; x < t.nk; x++) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(t.Dk[x] + (pcd + l) * pld + pca));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(t.Dk[x] + (pcd + l) * pld + pcb));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NC; k++)
+                for (int x = 0; x < t.nk; x++) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(t.Dk[x] + (pcc + k) * pld + pca));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(t.Dk[x] + (pcc + k) * pld + pcb));
+                }
+        }
+#endif
 
         double gout[NOUT];
 #pragma unroll
@@ -279,10 +300,10 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
                     s = fma(gout[ij * NCD + kl], dcd[kl], s);
                     jcd[kl] = fma(gout[ij * NCD + kl], dab, jcd[kl]);
                 }
-                fixed_add(t.accJ + off, s, t.scaleJ);
+                fixed_add(t.accJ + off, s, scaleJ);
             }
 #pragma unroll
-            for (int kl = 0; kl < NCD; kl++) fixed_add(t.accJ + (cd0 + kl % ND) * ld + cc0 + kl / ND, jcd[kl], t.scaleJ);
+            for (int kl = 0; kl < NCD; kl++) fixed_add(t.accJ + (cd0 + kl % ND) * ld + cc0 + kl / ND, jcd[kl], scaleJ);
         }
         for (int x = 0; x < t.nk; x++) {
             const double* __restrict__ D = t.Dk[x];
@@ -300,7 +321,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
                         for (int j = 0; j < NB; j++)
 #pragma unroll
                             for (int l = 0; l < ND; l++) s = fma(gout[((i * NB + j) * NC + k) * ND + l], d[j * ND + l], s);
-                        fixed_add(acc + (cc0 + k) * ld + ca + i, s, t.scaleK);
+                        fixed_add(acc + (cc0 + k) * ld + ca + i, s, scaleK);
                     }
             }
             {   // K(a,d) += sum_bc V D(b,c)
@@ -316,7 +337,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
                         for (int j = 0; j < NB; j++)
 #pragma unroll
                             for (int k = 0; k < NC; k++) s = fma(gout[((i * NB + j) * NC + k) * ND + l], d[j * NC + k], s);
-                        fixed_add(acc + (cd0 + l) * ld + ca + i, s, t.scaleK);
+                        fixed_add(acc + (cd0 + l) * ld + ca + i, s, scaleK);
                     }
             }
             {   // K(b,c) += sum_ad V D(a,d)
@@ -332,7 +353,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
                         for (int i = 0; i < NA; i++)
 #pragma unroll
                             for (int l = 0; l < ND; l++) s = fma(gout[((i * NB + j) * NC + k) * ND + l], d[i * ND + l], s);
-                        fixed_add(acc + (cc0 + k) * ld + cb + j, s, t.scaleK);
+                        fixed_add(acc + (cc0 + k) * ld + cb + j, s, scaleK);
                     }
             }
             {   // K(b,d) += sum_ac V D(a,c)
@@ -348,7 +369,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
                         for (int i = 0; i < NA; i++)
 #pragma unroll
                             for (int k = 0; k < NC; k++) s = fma(gout[((i * NB + j) * NC + k) * ND + l], d[i * NC + k], s);
-                        fixed_add(acc + (cd0 + l) * ld + cb + j, s, t.scaleK);
+                        fixed_add(acc + (cd0 + l) * ld + cb + j, s, scaleK);
                     }
             }
         }
@@ -466,6 +487,7 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
     constexpr int NQ = tpqs_nq(GS), NT = GS * NQ, VC = tpqs_vc(GS);
     static_assert(NA % GS == 0, "slices must divide the components of shell a");
     extern __shared__ double smem[];
+    const double scaleJ = __ldg(t.scales), scaleK = __ldg(t.scales + 1);
     double* tab = smem;
     double* sbra = smem + TABLEN;                   // [TPQ_NBRA][TPQ_MAXBP]
     double* part = sbra + TPQ_NBRA * TPQ_MAXBP;     // [VC][GS][NQ]
@@ -626,10 +648,10 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                         sum = fma(gout[(m * NB + j) * NCD + kl], dcd[kl], sum);
                         jcd[kl] = fma(gout[(m * NB + j) * NCD + kl], dab, jcd[kl]);
                     }
-                    if (active) fixed_add(t.accJ + off, sum, t.scaleJ);
+                    if (active) fixed_add(t.accJ + off, sum, scaleJ);
                 }
             reduce_add(std::integral_constant<int, NCD>{}, jcd,
-                       [&](int kl) { return (size_t)(cd0 + kl % ND) * ld + cc0 + kl / ND; }, t.accJ, t.scaleJ);
+                       [&](int kl) { return (size_t)(cd0 + kl % ND) * ld + cc0 + kl / ND; }, t.accJ, scaleJ);
         }
         for (int x = 0; x < t.nk; x++) {
             const double* __restrict__ D = t.Dk[x];
@@ -648,7 +670,7 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                             for (int j = 0; j < NB; j++)
 #pragma unroll
                                 for (int l = 0; l < ND; l++) sum = fma(gout[((m * NB + j) * NC + k) * ND + l], d[j * ND + l], sum);
-                            fixed_add(acc + (cc0 + k) * ld + ca + ia0 + m, sum, t.scaleK);
+                            fixed_add(acc + (cc0 + k) * ld + ca + ia0 + m, sum, scaleK);
                         }
                 }
                 {   // K(a,d) += sum_bc V D(b,c)   (complete)
@@ -664,7 +686,7 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                             for (int j = 0; j < NB; j++)
 #pragma unroll
                                 for (int k = 0; k < NC; k++) sum = fma(gout[((m * NB + j) * NC + k) * ND + l], d[j * NC + k], sum);
-                            fixed_add(acc + (cd0 + l) * ld + ca + ia0 + m, sum, t.scaleK);
+                            fixed_add(acc + (cd0 + l) * ld + ca + ia0 + m, sum, scaleK);
                         }
                 }
             }
@@ -695,7 +717,7 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                            if (e < NB * NC) return (size_t)(cc0 + e % NC) * ld + cb + e / NC;
                            const int f = e - NB * NC;
                            return (size_t)(cd0 + f % ND) * ld + cb + f / ND;
-                       }, acc, t.scaleK);
+                       }, acc, scaleK);
         }
     }
 }

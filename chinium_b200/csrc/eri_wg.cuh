@@ -21,6 +21,9 @@
 
 #define WG_WARPS 4
 
+// bring the 128-byte line of a global address into L1 (the digestion reads it ~10^4 cycles later)
+__device__ __forceinline__ void cf_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int B, int E, class F>
 __device__ __forceinline__ void wg_static_for(F&& f) {
     if constexpr (B < E) { f(std::integral_constant<int, B>{}); wg_static_for<B + 1, E>(f); }
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
     constexpr int NROOTS = C::NROOTS, LAB = C::LAB, GS = C::GS, QW = C::QW, NQ = C::NQ, LABP = C::LABP, TSZ = C::TSZ;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double smem[];
+    const double scaleJ = __ldg(t.scales), scaleK = __ldg(t.scales + 1);
     double* tab = smem;
     double* sbra = smem + C::TABLEN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -217,6 +221,21 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
         ca = t.bra.cao_a[ib]; cb = t.bra.cao_b[ib];
         if (active) { cc0 = t.ket.cao_a[ik]; cd0 = t.ket.cao_b[ik]; }
         const size_t ld = (size_t)t.ncart;
+#ifdef CF_PREFETCH_D
+        if (active) {   // D elements of the digestion: one line per (column, a|b row run); the L2 round trip overlaps the integral work
+#pragma unroll
+            for (int m = 0; m < MK; m++) {
+                if (!fok[m]) continue;
+                cf_prefetch_l1(t.Dtot + (cd0 + fid[m]) * ld + cc0 + fic[m]);
+                for (int x = 0; x < t.nk; x++) {
+                    cf_prefetch_l1(t.Dk[x] + (cd0 + fid[m]) * ld + ca);
+                    cf_prefetch_l1(t.Dk[x] + (cd0 + fid[m]) * ld + cb);
+                    cf_prefetch_l1(t.Dk[x] + (cc0 + fic[m]) * ld + ca);
+                    cf_prefetch_l1(t.Dk[x] + (cc0 + fic[m]) * ld + cb);
+                }
+            }
+        }
+#endif
 
         wg_static_for<0, HS>([&](auto hp_tag) {
         constexpr int IA0 = decltype(hp_tag)::value * NAP;     // first component of shell a of this pass
@@ -243,14 +262,30 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
                 sbra[8 * TPQ_MAXBP + threadIdx.x] = pz - Az;
             }
             __syncthreads();
+#ifdef CF_PREFETCH_KET
+            double n_qe = 1.0, n_hq = 0.5, n_c = 0.0, n_Qx = 0.0, n_Qy = 0.0, n_Qz = 0.0;   // primitive icd+1, loaded one iteration ahead
+            if (active && npcd > 0) {
+                n_qe = t.ket.p[pcd0]; n_hq = t.ket.hp[pcd0]; n_c = t.ket.c[pcd0];
+                n_Qx = t.ket.Px[pcd0]; n_Qy = t.ket.Py[pcd0]; n_Qz = t.ket.Pz[pcd0];
+            }
+#endif
             for (int icd = 0; icd < npcd_w; icd++) {
                 const bool vk = active && icd < npcd;
                 double qe = 1.0, hq = 0.5, ccd = 0.0, Qx = 0.0, Qy = 0.0, Qz = 0.0;
+#ifdef CF_PREFETCH_KET
+                if (vk) { qe = n_qe; hq = n_hq; ccd = n_c * wgt; Qx = n_Qx; Qy = n_Qy; Qz = n_Qz; }
+                if (active && icd + 1 < npcd) {
+                    const int scd = pcd0 + (icd + 1) * CF_PSTRIDE;
+                    n_qe = t.ket.p[scd]; n_hq = t.ket.hp[scd]; n_c = t.ket.c[scd];
+                    n_Qx = t.ket.Px[scd]; n_Qy = t.ket.Py[scd]; n_Qz = t.ket.Pz[scd];
+                }
+#else
                 if (vk) {
                     const int scd = pcd0 + icd * CF_PSTRIDE;
                     qe = t.ket.p[scd]; hq = t.ket.hp[scd]; ccd = t.ket.c[scd] * wgt;
                     Qx = t.ket.Px[scd]; Qy = t.ket.Py[scd]; Qz = t.ket.Pz[scd];
                 }
+#endif
                 const double QCx = Qx - Cx, QCy = Qy - Cy, QCz = Qz - Cz;
                 for (int iab = 0; iab < nb; iab++) {
                     const double cc = sbra[5 * TPQ_MAXBP + iab] * ccd;
@@ -332,7 +367,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
             }
 #pragma unroll
             for (int m = 0; m < MK; m++)
-                if (active && fok[m]) fixed_add(t.accJ + (cd0 + fid[m]) * ld + cc0 + fic[m], jcd[m], t.scaleJ);
+                if (active && fok[m]) fixed_add(t.accJ + (cd0 + fid[m]) * ld + cc0 + fic[m], jcd[m], scaleJ);
             __syncwarp();
             // J(a,b) is common to every quartet of the item: sum over ALL active quartets of the warp (fixed order) and
             // issue one add per element and warp; lanes map to consecutive rows i, i.e. consecutive addresses
@@ -348,7 +383,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
 #pragma unroll
                             for (int g2 = 0; g2 < GS; g2++) s += wq[(size_t)q2 * C::SCR + e * GS + g2];
                         }
-                    if (amask) fixed_add(t.accJ + (cb + j) * ld + ca + IA0 + i, s, t.scaleJ);
+                    if (amask) fixed_add(t.accJ + (cb + j) * ld + ca + IA0 + i, s, scaleJ);
                 }
             }
             __syncwarp();
@@ -388,7 +423,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
 #pragma unroll
                     for (int l = 0; l < ND; l++) s += myq[(r * NC + k) * ND + l];
                     const int row = r < NAP ? ca + IA0 + r : cb + (r - NAP);
-                    fixed_add(accK + (cc0 + k) * ld + row, s, t.scaleK);
+                    fixed_add(accK + (cc0 + k) * ld + row, s, scaleK);
                 }
             __syncwarp();
             // half 2: K(a,d) += sum_bc V D(b,c) ; K(b,d) += sum_ac V D(a,c)   -> slots [.., id, ic], summed over ic
@@ -423,7 +458,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
 #pragma unroll
                     for (int k = 0; k < NC; k++) s += myq[(r * ND + l) * NC + k];
                     const int row = r < NAP ? ca + IA0 + r : cb + (r - NAP);
-                    fixed_add(accK + (cd0 + l) * ld + row, s, t.scaleK);
+                    fixed_add(accK + (cd0 + l) * ld + row, s, scaleK);
                 }
             __syncwarp();
         }

@@ -71,6 +71,7 @@ class DistributedInt4C2E:
             if k == 0 or present[k - 1]:
                 self._pin_out[k].copy_(self._out[k], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        self.eng.sync_stats()            # timings + the deferred range check (raises on non-finite densities)
         for k in range(4):
             if k == 0 or present[k - 1]:
                 res.append(np.asfortranarray(self._pin_out[k].numpy().T.copy()))

@@ -260,7 +260,7 @@ class Int4C2E:
                      group=int(r[5])) for r in rows[:n.value]]
 
     def sync_stats(self):
-        self._lib.cf_sync_stats(self._h)
+        self._check(self._lib.cf_sync_stats(self._h))   # also the deferred fixed-point range check of that build
         return self.stats
 
 

@@ -133,7 +133,9 @@ int cf_finalize_device(cf_handle* h, int nbf, const int64_t* acc, double exx,
  * Ds/Gs are nmat consecutive nbf x nbf col-major matrices. */
 int cf_build_g_multi(cf_handle* h, int nbf, int nmat, const double* Ds, double exx, double* Gs);
 
-/* After the caller has synchronised the stream of a *_device call: refresh ms_device_last / ms_eri_last. */
+/* After the caller has synchronised the stream of a *_device call: refresh ms_device_last / ms_eri_last and run the
+ * fixed-point range check of that build (the *_device calls never synchronise, so CF_ERR_RANGE for a non-finite or
+ * astronomically large density is reported here; cf_build_jk reports it itself). */
 int cf_sync_stats(cf_handle* h);
 /* Developer/benchmark aid: run every (bra class, ket class) kernel alone and time it with CUDA events.
  * DEVICE density pointers. rows: 6 doubles each = bra class, ket class, quartets, ms, F_alg, threads per quartet. */
