@@ -140,6 +140,13 @@ __device__ __forceinline__ void tpq_roots(const double* __restrict__ tab, double
     }
 }
 
+// sum over the 32 lanes in a FIXED butterfly order (deterministic for a given work item); every lane gets the total
+__device__ __forceinline__ double warp_sum_fixed(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 #ifndef TPQ_MINB
 #define TPQ_MINB 2
 #endif
@@ -281,15 +288,16 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
                 }
             }
         }
-        if (!active) continue;
-
         // ---- digestion: six blocks, all in registers ------------------------------------------------
-        const int ca = t.bra.cao_a[ib], cb = t.bra.cao_b[ib], cc0 = t.ket.cao_a[ik], cd0 = t.ket.cao_b[ik];
+        // (inactive lanes hold gout == 0 and take part in the warp-wide J(a,b) sums only)
+        const int ca = t.bra.cao_a[ib], cb = t.bra.cao_b[ib];
+        int cc0 = 0, cd0 = 0;
+        if (active) { cc0 = t.ket.cao_a[ik]; cd0 = t.ket.cao_b[ik]; }
         const size_t ld = (size_t)t.ncart;
         {   // J(a,b) += sum_cd V Dtot(c,d) ; J(c,d) += sum_ab V Dtot(a,b)
             double dcd[NCD], jcd[NCD];
 #pragma unroll
-            for (int kl = 0; kl < NCD; kl++) { dcd[kl] = t.Dtot[(cd0 + kl % ND) * ld + cc0 + kl / ND]; jcd[kl] = 0.0; }
+            for (int kl = 0; kl < NCD; kl++) { dcd[kl] = active ? t.Dtot[(cd0 + kl % ND) * ld + cc0 + kl / ND] : 0.0; jcd[kl] = 0.0; }
 #pragma unroll
             for (int ij = 0; ij < NAB; ij++) {
                 const size_t off = (cb + ij % NB) * ld + ca + ij / NB;
@@ -300,11 +308,16 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
                     s = fma(gout[ij * NCD + kl], dcd[kl], s);
                     jcd[kl] = fma(gout[ij * NCD + kl], dab, jcd[kl]);
                 }
-                fixed_add(t.accJ + off, s, scaleJ);
+                // the bra pair is common to the warp's 32 quartets: one add per element and warp instead of 32
+                s = warp_sum_fixed(s);
+                if (lane == 0) fixed_add(t.accJ + off, s, scaleJ);
             }
+            if (active) {
 #pragma unroll
-            for (int kl = 0; kl < NCD; kl++) fixed_add(t.accJ + (cd0 + kl % ND) * ld + cc0 + kl / ND, jcd[kl], scaleJ);
+                for (int kl = 0; kl < NCD; kl++) fixed_add(t.accJ + (cd0 + kl % ND) * ld + cc0 + kl / ND, jcd[kl], scaleJ);
+            }
         }
+        if (!active) continue;
         for (int x = 0; x < t.nk; x++) {
             const double* __restrict__ D = t.Dk[x];
             long long* acc = t.accK[x];
@@ -608,7 +621,8 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
 
         // ---- digestion ----------------------------------------------------------------------------
         int ca = 0, cb = 0, cc0 = 0, cd0 = 0;
-        if (active) { ca = t.bra.cao_a[ib]; cb = t.bra.cao_b[ib]; cc0 = t.ket.cao_a[ik]; cd0 = t.ket.cao_b[ik]; }
+        ca = t.bra.cao_a[ib]; cb = t.bra.cao_b[ib];          // bra pair: valid for every lane (warp-wide J(a,b) sums)
+        if (active) { cc0 = t.ket.cao_a[ik]; cd0 = t.ket.cao_b[ik]; }
         const size_t ld = (size_t)t.ncart;
         const int ia0 = s * MA;
         // cross-slice sum of NV partial values through shared memory, chunk by chunk, then one fixed-point add each
@@ -648,7 +662,9 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                         sum = fma(gout[(m * NB + j) * NCD + kl], dcd[kl], sum);
                         jcd[kl] = fma(gout[(m * NB + j) * NCD + kl], dab, jcd[kl]);
                     }
-                    if (active) fixed_add(t.accJ + off, sum, scaleJ);
+                    // the bra pair and the slice are warp-uniform: one add per element and warp
+                    sum = warp_sum_fixed(sum);
+                    if ((threadIdx.x & 31) == 0) fixed_add(t.accJ + off, sum, scaleJ);
                 }
             reduce_add(std::integral_constant<int, NCD>{}, jcd,
                        [&](int kl) { return (size_t)(cd0 + kl % ND) * ld + cc0 + kl / ND; }, t.accJ, scaleJ);
