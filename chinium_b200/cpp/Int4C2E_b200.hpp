@@ -157,6 +157,26 @@ class Int4C2E_T {
         return Gs;
     }
 
+    // nuclear gradient (Int4C2E.cpp:747-763): grad[3*atom + xyz] = sum D1 o d/dR (J[2 D2] - EXX K[D2]); the 3*natoms
+    // intermediate matrices of getRepulsion1 (:312-408) are contracted on the fly and never formed
+    std::vector<double> ContractGrads(Matrix D1, Matrix D2, int output) {
+        ensure(0);
+        const int n = cf_nbf(h_.get());
+        if (D1.rows() != n || D1.cols() != n || D2.rows() != n || D2.cols() != n) throw std::runtime_error("ContractGrads: matrix is not nbf x nbf");
+        auto t0 = std::chrono::steady_clock::now();
+        if (output > 0) std::printf("Contracting 4c-2e repulsion integral nuclear gradient with 1 matrix from the left and 1 matrix from the right ... ");
+        int natom = 0;
+        for (int a : basis_->shell2atom) natom = a + 1 > natom ? a + 1 : natom;
+        std::vector<double> g(3 * (size_t)natom, 0.0);
+        check(cf_contract_grads(h_.get(), n, D1.data(), D2.data(), EXX, natom, g.data()));
+        if (output > 0) std::printf("Done in %f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        return g;
+    }
+
+    // extension for direct SCF (no counterpart in the stored-ERI reference): density-weighted screening for incremental
+    // builds G[D_n - D_(n-1)]; 0 switches it off (see cf_set_density_threshold)
+    void setDensityThreshold(double dthr) { ensure(0); check(cf_set_density_threshold(h_.get(), dthr)); }
+
     cf_handle* handle() { ensure(0); return h_.get(); }
 
   private:

@@ -40,6 +40,10 @@ struct PairClassDev {
     const double* c;        // ca*cb*exp(-ab/p |AB|^2) * sqrt(2) pi^(5/4) / p
 };
 
+// the evaluated-quartet counter is spread over CF_NQ_SLOTS words (same-address atomics serialise in L2)
+#define CF_NQ_SLOTS 1024
+__device__ __forceinline__ int cf_nq_slot() { return (int)((blockIdx.x * 8u + (threadIdx.x >> 5)) & (CF_NQ_SLOTS - 1)); }
+
 struct RysTablesDev {
     const double* table;
     const double* asym;
@@ -71,4 +75,17 @@ struct QuartetTask {
     // Schwarz bounds (only ket runs that can pass Q_ab * Q_cd > thr are listed; triangular limit folded in).
     const int4* items;
     long long nitem;
+    // bra-loop kernels (eri_tpqa.cuh): bra pairs (positions in the bra class arrays) grouped by shell a, Schwarz bound
+    // descending inside a group; item = (x: first entry of `border`, y: first ket pair of an aligned block of 32,
+    // z: ket pairs in the block, w: bra pairs in the chunk)
+    int braloop;            // thread-per-quartet classes: 1 = bra-loop kernel + chunk items (low contraction), 0 = one bra pair per item
+    const int* border;
+    // bra-role copy in `border` order: record e = (x: position in the class arrays, y: shell b | primitive count << 16,
+    // z: first Cartesian AO of b, w: offset of its CONTIGUOUS primitives) and (Q, ABx, ABy, ABz); primitive value v of
+    // primitive k lives at bprim[v * bprim_stride + w + k], v = p, 1/(2p), Px, Py, Pz, c
+    const int4* brec_i;
+    const double* brec_d;
+    const double* bprim;
+    long long bprim_stride;
+    unsigned long long* nq_done;   // [CF_NQ_SLOTS] counters of the shell quartets actually evaluated by this build (may be null)
 };

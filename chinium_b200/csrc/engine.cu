@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -24,7 +25,12 @@
 #include "cf_common.cuh"
 #include "eri_generic.cuh"     // rys_tmax/rys_off (host constexpr) -- no kernels instantiated here
 #include "eri_tpq.cuh"         // TPQ_THREADS
+#include "eri_grad.cuh"        // GradTask (kernels are instantiated in eri_inst.cu)
 #include "rys_tables_data.h"
+
+#ifndef CF_BRALOOP_MAXK
+#define CF_BRALOOP_MAXK 8.0    // mean primitive quartets per shell quartet below which the bra-loop kernel is used
+#endif
 
 #define CUDA_TRY(x)                                                                             \
     do {                                                                                        \
@@ -39,6 +45,11 @@
 #define DECL_BRA(n) cudaError_t cf_launch_bra##n(int, const QuartetTask&, int, int, cudaStream_t, int*, size_t*, int*);
 DECL_BRA(0) DECL_BRA(1) DECL_BRA(2) DECL_BRA(3) DECL_BRA(4) DECL_BRA(5) DECL_BRA(6) DECL_BRA(7) DECL_BRA(8) DECL_BRA(9)
 typedef cudaError_t (*bra_launch_fn)(int, const QuartetTask&, int, int, cudaStream_t, int*, size_t*, int*);
+#define DECL_GRAD(n) cudaError_t cf_launch_grad_bra##n(int, const GradTask&, int, cudaStream_t, int*, size_t*);
+DECL_GRAD(0) DECL_GRAD(1) DECL_GRAD(2) DECL_GRAD(3) DECL_GRAD(4) DECL_GRAD(5) DECL_GRAD(6) DECL_GRAD(7) DECL_GRAD(8) DECL_GRAD(9)
+typedef cudaError_t (*grad_launch_fn)(int, const GradTask&, int, cudaStream_t, int*, size_t*);
+static grad_launch_fn g_grad_launch[CF_NCLS] = {cf_launch_grad_bra0, cf_launch_grad_bra1, cf_launch_grad_bra2, cf_launch_grad_bra3, cf_launch_grad_bra4,
+                                                cf_launch_grad_bra5, cf_launch_grad_bra6, cf_launch_grad_bra7, cf_launch_grad_bra8, cf_launch_grad_bra9};
 static bra_launch_fn g_bra_launch[CF_NCLS] = {cf_launch_bra0, cf_launch_bra1, cf_launch_bra2, cf_launch_bra3, cf_launch_bra4,
                                               cf_launch_bra5, cf_launch_bra6, cf_launch_bra7, cf_launch_bra8, cf_launch_bra9};
 
@@ -66,11 +77,19 @@ struct PairClassHost {
     int la = 0, lb = 0;
     // canonical host storage: pairs in creation order, primitives contiguous per pair (prim_off / nprim)
     std::vector<int> sa, sb, cao_a, cao_b, prim_off, nprim, nprim_full;
-    std::vector<double> A, AB, Q, Qpure, p, P, c;
+    std::vector<double> A, AB, Q, Qpure, p, P, c, aexp /* exponent of shell a per primitive pair (derivatives) */;
     std::vector<int> order;          // device position -> canonical pair index
     std::vector<int> seg;            // device positions where the primitive count changes (+ npair): Q descends inside a segment
     DevBuf<int> d_sa, d_sb, d_cao_a, d_cao_b, d_pbase, d_nprim, d_seg;
-    DevBuf<double> d_A, d_AB, d_Q, d_Qcart, d_p, d_hp, d_Px, d_Py, d_Pz, d_c;
+    DevBuf<double> d_A, d_AB, d_Q, d_Qcart, d_p, d_hp, d_Px, d_Py, d_Pz, d_c, d_aexp;
+    // bra role of the bra-loop kernels (eri_tpqa.cuh): device positions grouped by shell a (Q descending inside a
+    // group; `group` holds the group boundaries in `border`); ket role: max Q of every aligned block of 32 positions
+    int nblk = 0;
+    std::vector<int> border, group;
+    DevBuf<int> d_border;
+    DevBuf<int4> d_brec_i;
+    DevBuf<double> d_blkQ, d_brec_d, d_bprim;
+    long long bprim_stride = 0;
     int npair() const { return (int)sa.size(); }
     PairClassDev dev() const {
         PairClassDev d;
@@ -94,14 +113,14 @@ struct PairClassHost {
             nslot += (size_t)mx * CF_PSTRIDE;
         }
         if (nslot > 0x7fffffffull) return cudaErrorInvalidValue;
-        std::vector<double> o_p(nslot, 1.0), o_hp(nslot, 0.5), o_Px(nslot, 0.0), o_Py(nslot, 0.0), o_Pz(nslot, 0.0), o_c(nslot, 0.0);
+        std::vector<double> o_p(nslot, 1.0), o_hp(nslot, 0.5), o_Px(nslot, 0.0), o_Py(nslot, 0.0), o_Pz(nslot, 0.0), o_c(nslot, 0.0), o_ae(nslot, 0.5);
         for (int i = 0; i < np; i++) {
             const int s = order[i];
             o_sa[i] = sa[s]; o_sb[i] = sb[s]; o_ca[i] = cao_a[s]; o_cb[i] = cao_b[s]; o_np[i] = nprim[s]; o_Q[i] = Qpure[s];
             for (int x = 0; x < 3; x++) { o_A[3 * (size_t)i + x] = A[3 * (size_t)s + x]; o_AB[3 * (size_t)i + x] = AB[3 * (size_t)s + x]; }
             for (int k = 0; k < nprim[s]; k++) {
                 const size_t slot = (size_t)o_pbase[i] + (size_t)k * CF_PSTRIDE, src = (size_t)prim_off[s] + k;
-                o_p[slot] = p[src]; o_hp[slot] = 0.5 / p[src]; o_c[slot] = c[src];
+                o_p[slot] = p[src]; o_hp[slot] = 0.5 / p[src]; o_c[slot] = c[src]; o_ae[slot] = aexp[src];
                 o_Px[slot] = P[3 * src]; o_Py[slot] = P[3 * src + 1]; o_Pz[slot] = P[3 * src + 2];
             }
         }
@@ -120,16 +139,83 @@ struct PairClassHost {
         if ((e = d_Px.upload(o_Px)) != cudaSuccess) return e;
         if ((e = d_Py.upload(o_Py)) != cudaSuccess) return e;
         if ((e = d_Pz.upload(o_Pz)) != cudaSuccess) return e;
+        if ((e = d_aexp.upload(o_ae)) != cudaSuccess) return e;
         seg.clear();
         for (int i = 0; i < np; i++) if (i == 0 || o_np[i] != o_np[i - 1]) seg.push_back(i);
         seg.push_back(np);
         if ((e = d_seg.upload(seg)) != cudaSuccess) return e;
         return d_c.upload(o_c);
     }
+    double qpos(int pos) const { return Qpure[order[pos]]; }
+    // needs `order` (device position -> canonical pair) and Qpure
+    cudaError_t build_roles() {
+        const int np = npair();
+        nblk = (np + 31) / 32;
+        border.resize(np); group.clear();
+        if (np == 0) return cudaSuccess;
+        std::iota(border.begin(), border.end(), 0);
+        std::stable_sort(border.begin(), border.end(), [&](int x, int y) {
+            const int ax = sa[order[x]], ay = sa[order[y]];
+            if (ax != ay) return ax < ay;
+            return qpos(x) > qpos(y);
+        });
+        for (int i = 0; i < np; i++) if (i == 0 || sa[order[border[i]]] != sa[order[border[i - 1]]]) group.push_back(i);
+        group.push_back(np);
+        std::vector<double> bq(nblk, 0.0);
+        for (int i = 0; i < np; i++) bq[i / 32] = std::max(bq[i / 32], qpos(i));
+        // bra-role copy in border order: records + contiguous primitives
+        std::vector<int4> ri(np);
+        std::vector<double> rd(4 * (size_t)np);
+        size_t tot = 0;
+        for (int e = 0; e < np; e++) tot += nprim[order[border[e]]];
+        bprim_stride = (long long)tot;
+        std::vector<double> bp(6 * tot);
+        size_t off = 0;
+        for (int e = 0; e < np; e++) {
+            const int s = order[border[e]];
+            if (nprim[s] >= 32768 || off > 0x7fffffffull) return cudaErrorInvalidValue;
+            ri[e] = make_int4(border[e], sb[s] | (nprim[s] << 16), cao_b[s], (int)off);
+            rd[4 * (size_t)e] = Qpure[s];
+            for (int x = 0; x < 3; x++) rd[4 * (size_t)e + 1 + x] = AB[3 * (size_t)s + x];
+            for (int k = 0; k < nprim[s]; k++) {
+                const size_t src = (size_t)prim_off[s] + k;
+                bp[off + k] = p[src]; bp[tot + off + k] = 0.5 / p[src];
+                bp[2 * tot + off + k] = P[3 * src]; bp[3 * tot + off + k] = P[3 * src + 1]; bp[4 * tot + off + k] = P[3 * src + 2];
+                bp[5 * tot + off + k] = c[src];
+            }
+            off += nprim[s];
+        }
+        cudaError_t e;
+        if ((e = d_border.upload(border)) != cudaSuccess) return e;
+        if ((e = d_brec_i.upload(ri)) != cudaSuccess) return e;
+        if ((e = d_brec_d.upload(rd)) != cudaSuccess) return e;
+        if ((e = d_bprim.upload(bp)) != cudaSuccess) return e;
+        return d_blkQ.upload(bq);
+    }
+    // chunks of consecutive entries of `border` inside one a-group: at most lch pairs and (after the first pair) at most
+    // pcap primitive pairs, so that the cost of a work item is bounded; heaviest chunks first (static schedule, short tail)
+    void make_chunks(int lch, double pcap, std::vector<int>& cstart, std::vector<int>& ccnt, std::vector<int>& cmax, std::vector<double>& cq) const {
+        struct Ch { int start, cnt, maxpos; double q, cost; };
+        std::vector<Ch> ch;
+        for (size_t g = 0; g + 1 < group.size(); g++)
+            for (int c0 = group[g]; c0 < group[g + 1];) {
+                int n = 0, mx = 0; double cost = 0;
+                while (c0 + n < group[g + 1] && n < lch) {
+                    const double np1 = nprim[order[border[c0 + n]]];
+                    if (n > 0 && cost + np1 > pcap) break;
+                    cost += np1; mx = std::max(mx, border[c0 + n]); n++;
+                }
+                ch.push_back({c0, n, mx, qpos(border[c0]), cost});
+                c0 += n;
+            }
+        std::stable_sort(ch.begin(), ch.end(), [](const Ch& x, const Ch& y) { return x.cost > y.cost; });
+        for (const Ch& c : ch) { cstart.push_back(c.start); ccnt.push_back(c.cnt); cmax.push_back(c.maxpos); cq.push_back(c.q); }
+    }
     void release() {
+        d_border.release(); d_blkQ.release(); d_brec_i.release(); d_brec_d.release(); d_bprim.release();
         d_sa.release(); d_sb.release(); d_cao_a.release(); d_cao_b.release(); d_pbase.release(); d_nprim.release(); d_seg.release();
         d_A.release(); d_AB.release(); d_Q.release(); d_Qcart.release(); d_p.release(); d_hp.release(); d_Px.release(); d_Py.release();
-        d_Pz.release(); d_c.release();
+        d_Pz.release(); d_c.release(); d_aexp.release();
     }
 };
 
@@ -142,6 +228,7 @@ struct ClassPairTask {
     int kind = 0;                    // 0 generic (CTA per quartet), 1 thread per quartet, 2 sliced thread per quartet
     int nq_item = 0;                 // kinds 1,2,3: ket pairs per work item
     int swap = 0;                    // kind 3: the LOWER class is handed to the kernel as the CTA-uniform pair
+    int braloop = 0;                 // kind 1: bra-loop kernel (eri_tpqa.cuh) with chunk items
     int G = 32;
     size_t smem[4] = {0, 0, 0, 0};   // by nk
     double flops_eri = 0;            // F_alg without the digestion term
@@ -154,6 +241,9 @@ struct cf_handle {
     int nshell = 0, nbf = 0, ncart = 0;
     std::vector<int> type, l, nprim, prim_off, bf_off, cao_off, nfun;
     std::vector<double> exps, coefs, xyz;
+    std::vector<int> shell2atom;           // empty when the caller gave none (gradients then refuse)
+    DevBuf<int> d_shell2atom;
+    DevBuf<double> d_gpart, d_grad;
     // per-shell transformation (function x cartesian), pooled by type
     std::vector<double> ctrans;            // pool
     std::vector<int> ct_off;               // [nshell] offset into pool
@@ -164,10 +254,13 @@ struct cf_handle {
     DevBuf<double> d_rys_table, d_rys_asym, d_boys;
     // per-build work space
     DevBuf<double> d_Dpure[3], d_Dcart[4] /* 0: Dtot, 1..3: Dk */, d_out[4] /* pure J,Kd,Ka,Kb */, d_partial, d_scales, d_diag,
-        d_QS /* [nshell^2] Cartesian Schwarz bound per shell pair */, d_B /* [4][nshell^2] block 1-norms of |D_cart| */, d_rwork;
+        d_QS /* [nshell^2] Cartesian Schwarz bound per shell pair */, d_B /* [4][nshell^2] block 1-norms of |D_cart| */, d_Bmax /* same, max-norms */, d_rwork;
     DevBuf<long long> d_acc;
+    DevBuf<unsigned long long> d_nq;         // shell quartets evaluated by the last build (device counter)
+    unsigned long long nq_host[CF_NQ_SLOTS] = {0};
     double qmax_cart = 0;
-    double scales_host[4] = {1, 1, 0, 0};   // copy of d_scales of the last synchronised build
+    double scales_host[8] = {1, 1, 0, 0, 0, 0, 0, 0};   // copy of d_scales of the last synchronised build
+    double density_threshold = 0.0;          // > 0: density-weighted screening (cf_set_density_threshold)
     cudaEvent_t ev[4];
     cudaStream_t side[3];
     cudaEvent_t ev_fork, ev_join[3];
@@ -189,10 +282,10 @@ __global__ void pure_to_cart_kernel(int nshell, int nbf, int ncart, const double
                                     const double* __restrict__ Db, double fd, double fa, double fb,
                                     const double* __restrict__ ctrans, const int* __restrict__ ct_off, const int* __restrict__ bf_off,
                                     const int* __restrict__ cao_off, const int* __restrict__ nfun, const int* __restrict__ ncsh,
-                                    double* __restrict__ out, double* __restrict__ bnorm) {
+                                    double* __restrict__ out, double* __restrict__ bnorm, double* __restrict__ bmax) {
     const int sa = blockIdx.x, sb = blockIdx.y;
-    __shared__ double sh[64];
-    double asum = 0.0;
+    __shared__ double sh[64], shm[64];
+    double asum = 0.0, amax = 0.0;
     const int na = nfun[sa], nb = nfun[sb], nca = ncsh[sa], ncb = ncsh[sb];
     const double* Ca = ctrans + ct_off[sa];
     const double* Cb = ctrans + ct_off[sb];
@@ -213,15 +306,17 @@ __global__ void pure_to_cart_kernel(int nshell, int nbf, int ncart, const double
         }
         out[(size_t)(cao_off[sb] + y) * ncart + cao_off[sa] + x] = s;
         asum += fabs(s);
+        amax = fmax(amax, fabs(s));
     }
     // entrywise 1-norm of the Cartesian shell block (fixed-order tree: deterministic), used by the fixed-point scale bound
-    sh[threadIdx.x] = asum;
+    sh[threadIdx.x] = asum; shm[threadIdx.x] = amax;
     __syncthreads();
     for (int w = 32; w > 0; w >>= 1) {
-        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        if (threadIdx.x < w) { sh[threadIdx.x] += sh[threadIdx.x + w]; shm[threadIdx.x] = fmax(shm[threadIdx.x], shm[threadIdx.x + w]); }
         __syncthreads();
     }
-    if (threadIdx.x == 0) bnorm[(size_t)sb * nshell + sa] = sh[0];
+    // max-norm of the block: density-weighted screening (effective threshold of the build, scales_kernel)
+    if (threadIdx.x == 0) { bnorm[(size_t)sb * nshell + sa] = sh[0]; bmax[(size_t)sb * nshell + sa] = shm[0]; }
 }
 
 // out_pure(block) = factor * C_a [ (acc + acc^T) / scale ] C_b^T ; integer sum first (exact), one conversion.
@@ -262,8 +357,8 @@ __global__ void finalize_kernel(int nbf, int ncart, const long long* __restrict_
 //   block x (K):  max_a sum_b QS[a,b] r_b, r_b = sum_d Bx[b,d]     |rawK_ik|  <= 8 QS_max * that
 // All reductions run in a FIXED order (strided per thread, then a shared-memory tree): every rank derives bit-identical
 // scales from the same density.
-__global__ void bounds_kernel(int ns, const double* __restrict__ QS, const double* __restrict__ B, double* __restrict__ r_work,
-                              double* __restrict__ bounds) {
+__global__ void bounds_kernel(int ns, const double* __restrict__ QS, const double* __restrict__ B, const double* __restrict__ Bmax,
+                              double* __restrict__ r_work, double* __restrict__ bounds) {
     __shared__ double sh[1024];
     const int x = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const double* Bx = B + (size_t)x * ns * ns;
@@ -291,9 +386,23 @@ __global__ void bounds_kernel(int ns, const double* __restrict__ QS, const doubl
         __syncthreads();
     }
     if (tid == 0) bounds[x] = sh[0];
+    __syncthreads();
+    // largest |D_cart| element of density x (0: total density): bounds[4 + x]
+    const double* Mx = Bmax + (size_t)x * ns * ns;
+    double m = 0.0;
+    for (size_t i = tid; i < (size_t)ns * ns; i += nt) m = fmax(m, Mx[i]);
+    sh[tid] = m;
+    __syncthreads();
+    for (int w = nt / 2; w > 0; w >>= 1) {
+        if (tid < w) sh[tid] = fmax(sh[tid], sh[tid + w]);
+        __syncthreads();
+    }
+    if (tid == 0) bounds[4 + x] = sh[0];
 }
-// scales[0] = J scale, scales[1] = K scale (powers of two), scales[2..3] = the bounds themselves
-__global__ void scales_kernel(const double* __restrict__ bounds, int nk, double qmax, double* __restrict__ scales) {
+// scales[0] = J scale, scales[1] = K scale (powers of two), scales[2..3] = the bounds themselves,
+// scales[4] = effective Schwarz threshold of this build: a quartet is evaluated iff Q_ab Q_cd > thr (the reference's
+// test, Int4C2E.cpp:108-113) AND Q_ab Q_cd max|D| > dthr (density-weighted, off when dthr <= 0), scales[5] = max|D|
+__global__ void scales_kernel(const double* __restrict__ bounds, int nk, double qmax, double thr, double dthr, double* __restrict__ scales) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double nkmax = 0.0;
     for (int x = 0; x < nk; x++) nkmax = fmax(nkmax, bounds[1 + x]);
@@ -306,6 +415,12 @@ __global__ void scales_kernel(const double* __restrict__ bounds, int nk, double 
     scales[1] = ldexp(1.0, min(62 - ek, 512));
     scales[2] = bj;
     scales[3] = bk;
+    double dmax = bounds[4];
+    for (int x = 0; x < nk; x++) dmax = fmax(dmax, bounds[5 + x]);
+    double eff = thr > 0.0 ? thr : 0.0;
+    if (dthr > 0.0) eff = fmax(eff, dmax > 0.0 ? dthr / dmax : 1e300);
+    scales[4] = eff;
+    scales[5] = dmax;
 }
 
 // Schwarz bounds of one pair class from the stored Cartesian (ab|ab) blocks: one CTA per pair
@@ -392,6 +507,29 @@ __global__ void item_list_kernel(int nH, const double* __restrict__ QH, const do
     if (counts) counts[ih] = n;
 }
 
+// Work items of the bra-loop kernels (eri_tpqa.cuh): one thread per bra chunk walks the aligned ket blocks of 32.
+// An item survives iff the best quartet of (chunk, block) can pass the Schwarz test and, for triangular tasks, the
+// chunk reaches up to the block (canonical iff ket position <= bra position).  counts-only pass when items == nullptr.
+__global__ void item_list_a_kernel(int nchunk, const int* __restrict__ cstart, const int* __restrict__ ccnt,
+                                   const int* __restrict__ cmaxpos, const double* __restrict__ cq, int nblk, int npairK,
+                                   const double* __restrict__ blkQ, double thr, int same, long long* __restrict__ counts,
+                                   const long long* __restrict__ offs, int4* __restrict__ items) {
+    const int ic = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ic >= nchunk) return;
+    const double q = cq[ic];
+    const int start = cstart[ic], cnt = ccnt[ic], maxpos = cmaxpos[ic];
+    int4* out = items ? items + offs[ic] : nullptr;
+    long long n = 0;
+    for (int r = 0; r < nblk; r++) {
+        const int k0 = r * 32;
+        if (same && maxpos < k0) break;
+        if (thr > 0.0 && !(q * blkQ[r] > thr)) continue;
+        if (out) out[n] = make_int4(start, k0, min(32, npairK - k0), cnt);
+        n++;
+    }
+    if (counts) counts[ic] = n;
+}
+
 // register-resident DFMA loop: the FP64 roofline denominator measured on the device itself
 __global__ void dfma_peak_kernel(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -463,6 +601,8 @@ static int launch_task(cf_handle* h, ClassPairTask* t, QuartetTask& qt, int stor
     if (t->swap && !store) { qt.bra = K.dev(); qt.ket = B.dev(); }
     qt.qoff = t->d_qoff.p; qt.nquartet = t->nquartet;
     qt.items = t->d_items.p; qt.nitem = t->nitem;
+    qt.braloop = t->braloop;
+    qt.border = B.d_border.p; qt.brec_i = B.d_brec_i.p; qt.brec_d = B.d_brec_d.p; qt.bprim = B.d_bprim.p; qt.bprim_stride = B.bprim_stride;
     qt.same_class = (t->bra == t->ket);
     qt.thr = h->opt.threshold > 0 ? h->opt.threshold : 0.0;
     const long long nq = qt.nquartet;
@@ -559,19 +699,21 @@ extern "C" void cf_destroy(cf_handle* h) {
     for (auto& b : h->d_Dpure) b.release();
     for (auto& b : h->d_Dcart) b.release();
     for (auto& b : h->d_out) b.release();
-    h->d_partial.release(); h->d_scales.release(); h->d_diag.release(); h->d_acc.release();
-    h->d_QS.release(); h->d_B.release(); h->d_rwork.release();
+    h->d_partial.release(); h->d_scales.release(); h->d_diag.release(); h->d_acc.release(); h->d_nq.release();
+    h->d_QS.release(); h->d_B.release(); h->d_Bmax.release(); h->d_rwork.release();
+    h->d_shell2atom.release(); h->d_gpart.release(); h->d_grad.release();
     for (auto& e : h->ev) cudaEventDestroy(e);
     for (int i = 0; i < 3; i++) { cudaStreamDestroy(h->side[i]); cudaEventDestroy(h->ev_join[i]); }
     cudaEventDestroy(h->ev_fork);
     delete h;
 }
 
-static void fill_rys(QuartetTask& qt, const cf_handle* h) {
-    qt.rys.table = h->d_rys_table.p;
-    qt.rys.asym = h->d_rys_asym.p;
-    qt.rys.boys = h->d_boys.p;
+static void fill_rys_tables(RysTablesDev& r, const cf_handle* h) {
+    r.table = h->d_rys_table.p;
+    r.asym = h->d_rys_asym.p;
+    r.boys = h->d_boys.p;
 }
+static void fill_rys(QuartetTask& qt, const cf_handle* h) { fill_rys_tables(qt.rys, h); }
 
 extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     if (!basis || basis->nshell <= 0 || !basis->type || !basis->nprim || !basis->prim_offset || !basis->exps ||
@@ -603,6 +745,7 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     h->nprim.assign(basis->nprim, basis->nprim + ns);
     h->prim_off.assign(basis->prim_offset, basis->prim_offset + ns);
     h->xyz.assign(basis->center_xyz, basis->center_xyz + 3 * ns);
+    if (basis->shell2atom) h->shell2atom.assign(basis->shell2atom, basis->shell2atom + ns);
     int nptot = 0;
     for (int s = 0; s < ns; s++) nptot = std::max(nptot, h->prim_off[s] + h->nprim[s]);
     h->exps.assign(basis->exps, basis->exps + nptot);
@@ -667,6 +810,7 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
                     c.p.push_back(p);
                     for (int x = 0; x < 3; x++) c.P.push_back((ea * A[x] + eb * B[x]) / p);
                     c.c.push_back(cc);
+                    c.aexp.push_back(ea);
                     kept++;
                 }
             if (kept == 0) continue;
@@ -728,6 +872,7 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
         });
         for (double q : c.Q) h->qmax_cart = std::max(h->qmax_cart, q);
         if (c.upload() != cudaSuccess) return fail("pair re-upload failed");
+        if (c.build_roles() != cudaSuccess) return fail("bra/ket role upload failed");
     }
     {   // dense Cartesian Schwarz matrix over shell pairs (0 for pairs dropped by the primitive cutoff)
         std::vector<double> QS((size_t)ns * ns, 0.0);
@@ -736,7 +881,7 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
                 QS[(size_t)c.sa[i] * ns + c.sb[i]] = c.Q[i];
                 QS[(size_t)c.sb[i] * ns + c.sa[i]] = c.Q[i];
             }
-        if (h->d_QS.upload(QS) != cudaSuccess || h->d_B.alloc(4 * (size_t)ns * ns) != cudaSuccess || h->d_rwork.alloc(4 * (size_t)ns) != cudaSuccess)
+        if (h->d_QS.upload(QS) != cudaSuccess || h->d_B.alloc(4 * (size_t)ns * ns) != cudaSuccess || h->d_Bmax.alloc(4 * (size_t)ns * ns) != cudaSuccess || h->d_rwork.alloc(4 * (size_t)ns) != cudaSuccess)
             return fail("cudaMalloc failed (Schwarz matrix)");
     }
 
@@ -803,7 +948,43 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
             QuartetTask dummy{};
             for (int k = 0; k < 4; k++) { dummy.nk = k; g_bra_launch[cb](ck, dummy, 0, 0, 0, &t->G, &t->smem[k], &t->kind); }
             t->nq_item = t->kind >> 4; t->swap = (t->kind >> 3) & 1; t->kind &= 7;
-            if (t->kind >= 1) {   // work items: (CTA-uniform pair, run of <= nq_item spread pairs); swap: roles exchanged
+            // thread-per-quartet classes: tasks with few primitive quartets per shell quartet are bound by the digestion
+            // (atomics, latency) -> bra-loop kernel; deeply contracted ones are FP64-bound -> one bra pair per item
+            t->braloop = (t->kind == 1 && primq < CF_BRALOOP_MAXK * nq) ? 1 : 0;
+            if (const char* e = getenv("CF_BRALOOP")) t->braloop = (t->kind == 1 && atoi(e) != 0) ? 1 : 0;   // developer override (A/B)
+            if (t->braloop) {   // bra-loop kernels: (bra chunk of one a-group) x (aligned block of 32 kets)
+                // chunk length: long chunks amortise the J(c,d)/K(a,.) flushes, but the static schedule wants >= ~32 items
+                // per resident warp and no item heavier than ~1/16 of a warp's share (cost ~ bra primitives x ket primitives)
+                const double nbatch = (double)nb * K.nblk * (same ? 0.5 : 1.0);
+                const int lch = (int)std::max(1.0, std::min(64.0, std::floor(nbatch / (148.0 * 8 * 32))));
+                double sumB = 0, sumK = 0; int maxK = 1;
+                for (int i = 0; i < nb; i++) sumB += B.nprim[i];
+                for (int i = 0; i < nk; i++) { sumK += K.nprim[i]; maxK = std::max(maxK, K.nprim[i]); }
+                const double pcap = std::max(1.0, sumB * sumK * (same ? 0.5 : 1.0) / (148.0 * 8 * 16 * 32 * maxK));
+                std::vector<int> cstart, ccnt, cmax; std::vector<double> cq;
+                B.make_chunks(lch, pcap, cstart, ccnt, cmax, cq);
+                const int nH = (int)cstart.size();
+                DevBuf<int> d_cs, d_cc, d_cm; DevBuf<double> d_cq;
+                DevBuf<long long> d_cnt, d_off;
+                if (d_cs.upload(cstart) != cudaSuccess || d_cc.upload(ccnt) != cudaSuccess || d_cm.upload(cmax) != cudaSuccess || d_cq.upload(cq) != cudaSuccess ||
+                    d_cnt.alloc(nH) != cudaSuccess || d_off.alloc(nH) != cudaSuccess) { delete t; return fail("cudaMalloc failed (item counts)"); }
+                const int tb = 128, gb = (nH + tb - 1) / tb;
+                item_list_a_kernel<<<gb, tb>>>(nH, d_cs.p, d_cc.p, d_cm.p, d_cq.p, K.nblk, nk, K.d_blkQ.p,
+                                               thr, same ? 1 : 0, d_cnt.p, nullptr, nullptr);
+                std::vector<long long> cnt(nH), off(nH);
+                if (cudaMemcpy(cnt.data(), d_cnt.p, sizeof(long long) * nH, cudaMemcpyDeviceToHost) != cudaSuccess) { delete t; return fail("item count kernel failed"); }
+                long long tot = 0;
+                for (int i = 0; i < nH; i++) { off[i] = tot; tot += cnt[i]; }
+                t->nitem = tot;
+                if (tot > 0) {
+                    if (cudaMemcpy(d_off.p, off.data(), sizeof(long long) * nH, cudaMemcpyHostToDevice) != cudaSuccess ||
+                        t->d_items.alloc((size_t)tot) != cudaSuccess) { delete t; return fail("cudaMalloc failed (work items)"); }
+                    item_list_a_kernel<<<gb, tb>>>(nH, d_cs.p, d_cc.p, d_cm.p, d_cq.p, K.nblk, nk, K.d_blkQ.p,
+                                                   thr, same ? 1 : 0, nullptr, d_off.p, t->d_items.p);
+                    if (cudaDeviceSynchronize() != cudaSuccess) { delete t; return fail("item list kernel failed"); }
+                }
+                d_cnt.release(); d_off.release(); d_cs.release(); d_cc.release(); d_cm.release(); d_cq.release();
+            } else if (t->kind >= 1) {   // work items: (CTA-uniform pair, run of <= nq_item spread pairs); swap: roles exchanged
                 const PairClassHost& Hc = t->swap ? K : B;
                 const PairClassHost& Sc = t->swap ? B : K;
                 const int nH = Hc.npair(), nseg = (int)Sc.seg.size() - 1;
@@ -847,7 +1028,7 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     for (auto& b : h->d_Dpure) ok = ok && b.alloc(n2p) == cudaSuccess;
     for (auto& b : h->d_Dcart) ok = ok && b.alloc(n2c) == cudaSuccess;
     for (auto& b : h->d_out) ok = ok && b.alloc(n2p) == cudaSuccess;
-    ok = ok && h->d_acc.alloc(4 * n2c) == cudaSuccess && h->d_partial.alloc(4 * 256) == cudaSuccess && h->d_scales.alloc(4) == cudaSuccess;
+    ok = ok && h->d_acc.alloc(4 * n2c) == cudaSuccess && h->d_partial.alloc(4 * 256) == cudaSuccess && h->d_scales.alloc(8) == cudaSuccess && h->d_nq.alloc(CF_NQ_SLOTS) == cudaSuccess;
     if (!ok) return fail("cudaMalloc failed (work space)");
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(std::string("setup kernels failed: ") + cudaGetErrorString(cudaGetLastError()));
     if (h->opt.verbose > 0) {
@@ -859,6 +1040,12 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
 }
 
 extern "C" int cf_nbf(const cf_handle* h) { return h ? h->nbf : -1; }
+
+extern "C" int cf_set_density_threshold(cf_handle* h, double dthr) {
+    if (!h) return CF_ERR_BAD_ARGUMENT;
+    h->density_threshold = dthr > 0.0 ? dthr : 0.0;
+    return CF_OK;
+}
 
 extern "C" int cf_get_stats(const cf_handle* h, cf_stats* out) {
     if (!h || !out) return CF_ERR_BAD_ARGUMENT;
@@ -908,18 +1095,19 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
     // total density 2Dd + Da + Db (Int4C2E.cpp:612-615) and the exchange densities, in the Cartesian working basis
     const size_t ns2 = (size_t)ns * ns;
     pure_to_cart_kernel<<<grid2, 64, 0, s>>>(ns, nbf, ncart, Dd, Da, Db, 2.0, 1.0, 1.0, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
-                                             h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[0].p, h->d_B.p);
+                                             h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[0].p, h->d_B.p, h->d_Bmax.p);
     h->stats.n_launches_last++;
     for (int x = 0; x < nk; x++) {
         pure_to_cart_kernel<<<grid2, 64, 0, s>>>(ns, nbf, ncart, dk[x], nullptr, nullptr, 1.0, 0.0, 0.0, h->d_ctrans.p, h->d_ct_off.p,
                                                  h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[1 + x].p,
-                                                 h->d_B.p + (size_t)(1 + x) * ns2);
+                                                 h->d_B.p + (size_t)(1 + x) * ns2, h->d_Bmax.p + (size_t)(1 + x) * ns2);
         h->stats.n_launches_last++;
     }
-    bounds_kernel<<<1 + nk, 1024, 0, s>>>(ns, h->d_QS.p, h->d_B.p, h->d_rwork.p, h->d_partial.p);
-    scales_kernel<<<1, 32, 0, s>>>(h->d_partial.p, nk, h->qmax_cart, h->d_scales.p);
+    bounds_kernel<<<1 + nk, 1024, 0, s>>>(ns, h->d_QS.p, h->d_B.p, h->d_Bmax.p, h->d_rwork.p, h->d_partial.p);
+    scales_kernel<<<1, 32, 0, s>>>(h->d_partial.p, nk, h->qmax_cart, h->opt.threshold, h->density_threshold, h->d_scales.p);
     h->stats.n_launches_last += 2;
     CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * (1 + nk) * n2c, s));
+    CUDA_TRY(cudaMemsetAsync(h->d_nq.p, 0, sizeof(unsigned long long) * CF_NQ_SLOTS, s));
     // the scales stay on the device (kernels read them through QuartetTask::scales): no host synchronisation inside the
     // build; the range check happens after the caller's synchronisation (check_scales)
     CUDA_TRY(cudaEventRecord(h->ev[1], s));
@@ -934,7 +1122,7 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
         qt.Dtot = h->d_Dcart[0].p;
         for (int x = 0; x < nk; x++) { qt.Dk[x] = h->d_Dcart[1 + x].p; qt.accK[x] = (long long*)acc + (size_t)(1 + x) * n2c; }
         qt.accJ = (long long*)acc;
-        qt.scales = h->d_scales.p;
+        qt.scales = h->d_scales.p; qt.nq_done = h->d_nq.p;
         qt.store = nullptr; qt.diag = 0; qt.prim_cut = 1e-22;
         fill_rys(qt, h);
         cudaStream_t ts = (it % 4 == 0) ? s : h->side[it % 4 - 1];
@@ -997,6 +1185,8 @@ static int check_scales(cf_handle* h) {
     const double* sc = h->scales_host;
     h->stats.fixedpoint_scale_log2[0] = std::log2(sc[0]);
     h->stats.fixedpoint_scale_log2[1] = std::log2(sc[1]);
+    h->stats.threshold_effective_last = sc[4];
+    { unsigned long long tot = 0; for (int i = 0; i < CF_NQ_SLOTS; i++) tot += h->nq_host[i]; h->stats.quartets_evaluated_last = (int64_t)tot; }
     if (!(sc[0] > 0x1p-900) || !(sc[1] > 0x1p-900) || !std::isfinite(sc[2]) || !std::isfinite(sc[3])) {
         set_error(h, "fixed-point accumulator range exceeded: density contains non-finite or astronomically large entries");
         return CF_ERR_RANGE;
@@ -1017,6 +1207,7 @@ extern "C" int cf_sync_stats(cf_handle* h) {   // after a *_device call has been
     cudaSetDevice(h->device);
     fetch_times(h);
     CUDA_TRY(cudaMemcpy(h->scales_host, h->d_scales.p, sizeof(h->scales_host), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(h->nq_host, h->d_nq.p, sizeof(h->nq_host), cudaMemcpyDeviceToHost));
     return check_scales(h);
 }
 
@@ -1042,6 +1233,7 @@ extern "C" int cf_build_jk(cf_handle* h, int nbf, const double* Dd, const double
     for (int k = 0; k < 3; k++)
         if (src[k]) CUDA_TRY(cudaMemcpyAsync(outs[k], h->d_out[1 + k].p, bytes, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaMemcpyAsync(h->scales_host, h->d_scales.p, sizeof(h->scales_host), cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpyAsync(h->nq_host, h->d_nq.p, sizeof(h->nq_host), cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaStreamSynchronize(0));
     CUDA_TRY(cudaGetLastError());
     fetch_times(h);
@@ -1089,6 +1281,73 @@ extern "C" int cf_profile_tasks(cf_handle* h, int nbf, const double* Dd_dev, con
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *nrows = n;
+    return CF_OK;
+}
+
+// fixed-order sum of the per-CTA rows of the gradient kernels
+__global__ void grad_reduce_kernel(const double* __restrict__ gpart, int nrow, int ngrad, double* __restrict__ grad) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ngrad) return;
+    double s = 0.0;
+    for (int r = 0; r < nrow; r++) s += gpart[(size_t)r * ngrad + j];
+    grad[j] = s;
+}
+
+// Int4C2E::ContractGrads(D1, D2, output) (Int4C2E.cpp:747-763) on top of getRepulsion1 (:312-408); this partition's share
+extern "C" int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const double* D2, double exx, int natom, double* grad) {
+    if (!h || !D1 || !D2 || !grad || natom <= 0) return CF_ERR_BAD_ARGUMENT;
+    if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
+    if (h->shell2atom.empty()) { set_error(h, "cf_contract_grads needs cf_basis.shell2atom"); return CF_ERR_BAD_ARGUMENT; }
+    for (int a : h->shell2atom) if (a < 0 || a >= natom) { set_error(h, "shell2atom entry outside [0, natom)"); return CF_ERR_BAD_ARGUMENT; }
+    cudaSetDevice(h->device);
+    const int ns = h->nshell, ncart = h->ncart, ngrad = 3 * natom;
+    const size_t bytes = sizeof(double) * (size_t)nbf * nbf, ns2 = (size_t)ns * ns;
+    const int max_grid = 148 * 8;
+    if (h->d_shell2atom.n == 0 && h->d_shell2atom.upload(h->shell2atom) != cudaSuccess) { set_error(h, "cudaMalloc failed (shell2atom)"); return CF_ERR_CUDA; }
+    if (h->d_gpart.n < (size_t)max_grid * ngrad && h->d_gpart.alloc((size_t)max_grid * ngrad) != cudaSuccess) { set_error(h, "cudaMalloc failed (gradient rows)"); return CF_ERR_CUDA; }
+    if (h->d_grad.n < (size_t)ngrad && h->d_grad.alloc(ngrad) != cudaSuccess) { set_error(h, "cudaMalloc failed (gradient)"); return CF_ERR_CUDA; }
+    CUDA_TRY(cudaMemcpyAsync(h->d_Dpure[0].p, D1, bytes, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(h->d_Dpure[1].p, D2, bytes, cudaMemcpyHostToDevice, 0));
+    dim3 grid2(ns, ns);
+    for (int k = 0; k < 2; k++)
+        pure_to_cart_kernel<<<grid2, 64>>>(ns, nbf, ncart, h->d_Dpure[k].p, nullptr, nullptr, 1.0, 0.0, 0.0, h->d_ctrans.p, h->d_ct_off.p,
+                                            h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[1 + k].p,
+                                            h->d_B.p + (size_t)k * ns2, h->d_Bmax.p + (size_t)k * ns2);
+    CUDA_TRY(cudaMemsetAsync(h->d_gpart.p, 0, sizeof(double) * (size_t)max_grid * ngrad, 0));
+    for (ClassPairTask* t : h->tasks) {
+        const PairClassHost& B = h->cls[t->bra];
+        const PairClassHost& K = h->cls[t->ket];
+        if (t->nquartet == 0) continue;
+        if (t->d_qoff.n == 0) {       // first gradient call: quartet offsets of the CTA-per-quartet enumeration
+            const int nb = B.npair(), nk = K.npair();
+            std::vector<long long> qoff(nb + 1, 0);
+            for (int i = 0; i < nb; i++) qoff[i + 1] = qoff[i] + (t->bra == t->ket ? i + 1 : nk);
+            if (t->d_qoff.upload(qoff) != cudaSuccess) { set_error(h, "qoff upload failed"); return CF_ERR_CUDA; }
+        }
+        GradTask gt{};
+        gt.bra = B.dev(); gt.ket = K.dev();
+        gt.bra_aexp = B.d_aexp.p; gt.ket_aexp = K.d_aexp.p;
+        gt.qoff = t->d_qoff.p; gt.nquartet = t->nquartet;
+        gt.rank = h->opt.rank; gt.world = h->opt.world_size;
+        gt.same_class = (t->bra == t->ket); gt.ncart = ncart;
+        gt.D1 = h->d_Dcart[1].p; gt.D2 = h->d_Dcart[2].p; gt.exx = exx;
+        gt.shell2atom = h->d_shell2atom.p; gt.gpart = h->d_gpart.p; gt.ngrad = ngrad;
+        gt.prim_cut = 1e-22; gt.thr = h->opt.threshold > 0 ? h->opt.threshold : 0.0;
+        fill_rys_tables(gt.rys, h);
+        long long chunk = t->nquartet / ((long long)max_grid * 4 * std::max(1, gt.world));
+        chunk = std::max(1LL, std::min(64LL, chunk));
+        gt.chunk = (int)chunk;
+        const long long nchunk_total = (t->nquartet + chunk - 1) / chunk;
+        const long long nchunk_local = (nchunk_total - gt.rank + gt.world - 1) / gt.world;
+        if (nchunk_local <= 0) continue;
+        const int grid = (int)std::min<long long>(nchunk_local, max_grid);
+        cudaError_t e = g_grad_launch[t->bra](t->ket, gt, grid, 0, nullptr, nullptr);
+        if (e != cudaSuccess) { set_error(h, std::string("gradient kernel launch failed: ") + cudaGetErrorString(e)); return CF_ERR_CUDA; }
+    }
+    grad_reduce_kernel<<<(ngrad + 127) / 128, 128>>>(h->d_gpart.p, max_grid, ngrad, h->d_grad.p);
+    CUDA_TRY(cudaMemcpyAsync(grad, h->d_grad.p, sizeof(double) * ngrad, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    CUDA_TRY(cudaGetLastError());
     return CF_OK;
 }
 

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
     // shared: rw[2*NROOTS] | g[NROOTS*3*GSZ] | V[NOUT] | D blocks
     extern __shared__ double smem[];
     const double scaleJ = STORE ? 1.0 : __ldg(t.scales), scaleK = STORE ? 1.0 : __ldg(t.scales + 1);
+    const double thr = STORE ? t.thr : __ldg(t.scales + 4);   // effective Schwarz threshold of this build (scales_kernel)
     double* rw = smem;
     double* g = rw + 2 * NROOTS;
     double* V = g + NROOTS * 3 * GSZ;
@@ -178,7 +179,8 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
             const double ABx = t.bra.AB[3 * ib], ABy = t.bra.AB[3 * ib + 1], ABz = t.bra.AB[3 * ib + 2];
             const double Cx = t.ket.A[3 * ik], Cy = t.ket.A[3 * ik + 1], Cz = t.ket.A[3 * ik + 2];
             const double CDx = t.ket.AB[3 * ik], CDy = t.ket.AB[3 * ik + 1], CDz = t.ket.AB[3 * ik + 2];
-            if (t.thr > 0.0 && !(t.bra.Q[ib] * t.ket.Q[ik] > t.thr)) continue;   // uniform across the CTA
+            if (thr > 0.0 && !(t.bra.Q[ib] * t.ket.Q[ik] > thr)) continue;   // uniform across the CTA
+            if (!STORE && lane == 0 && t.nq_done) atomicAdd(t.nq_done + cf_nq_slot(), 1ull);
             const int pab0 = t.bra.pbase[ib], npab = t.bra.nprim[ib];
             const int pcd0 = t.ket.pbase[ik], npcd = t.ket.nprim[ik];
             double wgt = (sa == sb ? 1.0 : 2.0) * (sc == sd ? 1.0 : 2.0);

@@ -1,0 +1,201 @@
+// eri_grad.cuh -- first-derivative ERIs contracted on the fly into the nuclear gradient.
+//
+// Replaces getRepulsion1 + Int4C2E::ContractGrads(D1, D2) (src/Integral/Int4C2E.cpp:312-408, :747-763):
+//     grad[A,x] = sum_ij D1_ij * d/dA_x ( J[2 D2] - exx K[D2] )_ij          (densities fixed)
+//               = sum over canonical shell quartets  sum_abcd  d(ab|cd)/dA_x * Gamma_abcd ,
+//     Gamma_abcd = wgt * [ D1_ab D2_cd + D1_cd D2_ab - exx/4 (D1_ac D2_bd + D1_bc D2_ad + D1_ad D2_bc + D1_bd D2_ac) ]
+// (the reference's 8-fold degeneracy weights, :377-383, folded into `wgt`; its 3*natom nbf x nbf matrices are never
+// formed -- the 12 derivative buffers libint2 hands it are contracted with Gamma while they are still in registers).
+// Rys quadrature: d/dA_x acts on the x-direction 2-D integral only,
+//     d/dA_x I_x(i,j,k,l) = 2 alpha_a I_x(i+1,j,k,l) - i I_x(i-1,j,k,l)
+// so one 2-D table with every index raised by one serves all centres; centre D follows from translational
+// invariance.  One CTA of G threads per shell quartet, same phases as eri_generic.cuh; each lane owns Cartesian
+// components, keeps Gamma for them in registers and accumulates 9 scalars.  Per-CTA partial gradients are written
+// without atomics to the CTA's own row and summed in a fixed order afterwards (deterministic for a fixed launch).
+#pragma once
+#include "cf_common.cuh"
+#include "eri_generic.cuh"
+
+struct GradTask {
+    PairClassDev bra, ket;
+    const double* bra_aexp;      // exponent of shell a of every bra primitive pair (slot layout of PairClassDev)
+    const double* ket_aexp;      // ... of shell c
+    const long long* qoff;       // [bra.npair+1] first quartet of each bra pair
+    long long nquartet;
+    int chunk, rank, world, same_class, ncart;
+    const double* D1;            // Cartesian working basis, symmetric
+    const double* D2;
+    double exx;                  // <= 0: Coulomb part only
+    const int* shell2atom;
+    double* gpart;               // [gridDim.x][ngrad] per-CTA partial gradients
+    int ngrad;                   // 3 * natom
+    RysTablesDev rys;
+    double prim_cut, thr;
+};
+
+template <int LA, int LB, int LC, int LD>
+constexpr size_t eri_grad_smem(int G) {
+    constexpr int NR = (LA + LB + LC + LD + 1) / 2 + 1;
+    constexpr int GSZ2 = (LA + 2) * (LB + 2) * (LC + 2) * (LD + 2);
+    constexpr int NOUT = cf_ncart(LA) * cf_ncart(LB) * cf_ncart(LC) * cf_ncart(LD);
+    return sizeof(double) * (size_t)(2 * NR + NR * 3 * GSZ2 + NOUT + (G / 32) * 9 + 16);
+}
+
+template <int LA, int LB, int LC, int LD, int G>
+__global__ void __launch_bounds__(G) eri_grad_generic(const GradTask t) {
+    constexpr int NA = cf_ncart(LA), NB = cf_ncart(LB), NC = cf_ncart(LC), ND = cf_ncart(LD);
+    constexpr int NOUT = NA * NB * NC * ND;
+    constexpr int NR = (LA + LB + LC + LD + 1) / 2 + 1;
+    constexpr int GSZ2 = (LA + 2) * (LB + 2) * (LC + 2) * (LD + 2);
+    constexpr int SA = (LB + 2) * (LC + 2) * (LD + 2), SB = (LC + 2) * (LD + 2), SC = (LD + 2);
+    extern __shared__ double smem[];
+    double* rw = smem;
+    double* g = rw + 2 * NR;
+    double* gam = g + NR * 3 * GSZ2;        // [NOUT] effective two-particle density of the quartet
+    double* red = gam + NOUT;               // [G/32][9]
+    const int lane = threadIdx.x;
+    const size_t ld = (size_t)t.ncart;
+    double* myrow = t.gpart + (size_t)blockIdx.x * t.ngrad;
+
+    const long long nchunk_total = (t.nquartet + t.chunk - 1) / t.chunk;
+    const long long nchunk_local = (nchunk_total - t.rank + t.world - 1) / t.world;
+    for (long long lc = blockIdx.x; lc < nchunk_local; lc += gridDim.x) {
+        const long long chunk = lc * t.world + t.rank;
+        long long q = chunk * t.chunk;
+        const long long q_end = min(q + (long long)t.chunk, t.nquartet);
+        int lo = 0, hi = t.bra.npair;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (t.qoff[mid] <= q) lo = mid; else hi = mid;
+        }
+        int ib = lo;
+        for (; q < q_end; q++) {
+            while (t.qoff[ib + 1] <= q) ib++;
+            const int ik = (int)(q - t.qoff[ib]);
+            if (t.thr > 0.0 && !(t.bra.Q[ib] * t.ket.Q[ik] > t.thr)) continue;   // uniform across the CTA (Int4C2E.cpp:108-113)
+            const int sa = t.bra.sa[ib], sb = t.bra.sb[ib], sc = t.ket.sa[ik], sd = t.ket.sb[ik];
+            const double Ax = t.bra.A[3 * ib], Ay = t.bra.A[3 * ib + 1], Az = t.bra.A[3 * ib + 2];
+            const double ABx = t.bra.AB[3 * ib], ABy = t.bra.AB[3 * ib + 1], ABz = t.bra.AB[3 * ib + 2];
+            const double Cx = t.ket.A[3 * ik], Cy = t.ket.A[3 * ik + 1], Cz = t.ket.A[3 * ik + 2];
+            const double CDx = t.ket.AB[3 * ik], CDy = t.ket.AB[3 * ik + 1], CDz = t.ket.AB[3 * ik + 2];
+            const int pab0 = t.bra.pbase[ib], npab = t.bra.nprim[ib];
+            const int pcd0 = t.ket.pbase[ik], npcd = t.ket.nprim[ik];
+            double wgt = (sa == sb ? 1.0 : 2.0) * (sc == sd ? 1.0 : 2.0);
+            wgt *= (t.same_class && ib == ik) ? 1.0 : 2.0;
+            const int ca = t.bra.cao_a[ib], cb = t.bra.cao_b[ib], cc = t.ket.cao_a[ik], cdd = t.ket.cao_b[ik];
+
+            // effective two-particle density of the quartet (component n is read back by the lane that wrote it)
+            for (int n = lane; n < NOUT; n += G) {
+                const int a = ca + n / (ND * NC * NB), b = cb + (n / (ND * NC)) % NB, c = cc + (n / ND) % NC, d = cdd + n % ND;
+                double v = t.D1[b * ld + a] * t.D2[d * ld + c] + t.D1[d * ld + c] * t.D2[b * ld + a];
+                if (t.exx > 0.0)
+                    v -= 0.25 * t.exx * (t.D1[c * ld + a] * t.D2[d * ld + b] + t.D1[c * ld + b] * t.D2[d * ld + a] +
+                                         t.D1[d * ld + a] * t.D2[c * ld + b] + t.D1[d * ld + b] * t.D2[c * ld + a]);
+                gam[n] = v * wgt;
+            }
+            double acc[9];
+#pragma unroll
+            for (int e = 0; e < 9; e++) acc[e] = 0.0;
+
+            for (int iab = 0; iab < npab; iab++) {
+                const int sab = pab0 + iab * CF_PSTRIDE;
+                const double p = t.bra.p[sab], cab = t.bra.c[sab];
+                const double Px = t.bra.Px[sab], Py = t.bra.Py[sab], Pz = t.bra.Pz[sab];
+                const double ta = 2.0 * t.bra_aexp[sab], tb = 2.0 * p - ta;        // 2 alpha_a, 2 alpha_b
+                for (int icd = 0; icd < npcd; icd++) {
+                    const int scd = pcd0 + icd * CF_PSTRIDE;
+                    const double ccd = t.ket.c[scd];
+                    if (fabs(cab * ccd) < t.prim_cut) continue;   // uniform across the CTA
+                    const double qe = t.ket.p[scd];
+                    const double Qx = t.ket.Px[scd], Qy = t.ket.Py[scd], Qz = t.ket.Pz[scd];
+                    const double tc = 2.0 * t.ket_aexp[scd];
+                    const double pq = p + qe;
+                    const double rho = p * qe / pq;
+                    const double PQx = Px - Qx, PQy = Py - Qy, PQz = Pz - Qz;
+                    const double T = rho * (PQx * PQx + PQy * PQy + PQz * PQz);
+                    __syncthreads();                               // previous tables consumed
+                    if (lane < 2 * NR) rw[lane] = rys_value<NR>(t.rys, T, lane);
+                    __syncthreads();
+                    for (int tk = lane; tk < 3 * NR; tk += G) {
+                        const int r = tk / 3, dim = tk - 3 * r;
+                        const double x = rw[r];
+                        const double rx_p = rho * x / p;
+                        const double rx_q = rho * x / qe;
+                        const double b00 = 0.5 * x / pq;
+                        const double b10 = (1.0 - rx_p) * (0.5 / p);
+                        const double b01 = (1.0 - rx_q) * (0.5 / qe);
+                        double PA, PQ, QC, ab, cd, w0;
+                        if (dim == 0) { PA = Px - Ax; PQ = PQx; QC = Qx - Cx; ab = ABx; cd = CDx; w0 = 1.0; }
+                        else if (dim == 1) { PA = Py - Ay; PQ = PQy; QC = Qy - Cy; ab = ABy; cd = CDy; w0 = 1.0; }
+                        else { PA = Pz - Az; PQ = PQz; QC = Qz - Cz; ab = ABz; cd = CDz; w0 = rw[NR + r] * cab * ccd * rsqrt(pq); }
+                        rys_2d<LA + 1, LB + 1, LC + 1, LD + 1>(w0, PA - rx_p * PQ, QC + rx_q * PQ, b10, b01, b00, ab, cd, g + (size_t)tk * GSZ2);
+                    }
+                    __syncthreads();
+                    for (int n = lane; n < NOUT; n += G) {
+                        int ea[3], eb[3], ec[3], ed[3];
+                        cart_comp(LA, n / (ND * NC * NB), ea[0], ea[1], ea[2]);
+                        cart_comp(LB, (n / (ND * NC)) % NB, eb[0], eb[1], eb[2]);
+                        cart_comp(LC, (n / ND) % NC, ec[0], ec[1], ec[2]);
+                        cart_comp(LD, n % ND, ed[0], ed[1], ed[2]);
+                        int id3[3];
+#pragma unroll
+                        for (int d = 0; d < 3; d++) id3[d] = ea[d] * SA + eb[d] * SB + ec[d] * SC + ed[d];
+                        double s[9];
+#pragma unroll
+                        for (int k = 0; k < 9; k++) s[k] = 0.0;
+                        for (int r = 0; r < NR; r++) {
+                            const double* gr = g + (size_t)(3 * r) * GSZ2;
+                            double f[3], dA[3], dB[3], dC[3];
+#pragma unroll
+                            for (int d = 0; d < 3; d++) {
+                                const double* gd = gr + d * GSZ2 + id3[d];
+                                f[d] = gd[0];
+                                dA[d] = ta * gd[SA] - (ea[d] ? ea[d] * gd[-SA] : 0.0);
+                                dB[d] = tb * gd[SB] - (eb[d] ? eb[d] * gd[-SB] : 0.0);
+                                dC[d] = tc * gd[SC] - (ec[d] ? ec[d] * gd[-SC] : 0.0);
+                            }
+                            const double fyz = f[1] * f[2], fxz = f[0] * f[2], fxy = f[0] * f[1];
+                            s[0] = fma(dA[0], fyz, s[0]); s[1] = fma(dA[1], fxz, s[1]); s[2] = fma(dA[2], fxy, s[2]);
+                            s[3] = fma(dB[0], fyz, s[3]); s[4] = fma(dB[1], fxz, s[4]); s[5] = fma(dB[2], fxy, s[5]);
+                            s[6] = fma(dC[0], fyz, s[6]); s[7] = fma(dC[1], fxz, s[7]); s[8] = fma(dC[2], fxy, s[8]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 9; k++) acc[k] = fma(gam[n], s[k], acc[k]);
+                    }
+                }
+            }
+
+            // ---- CTA-wide sums of the 9 scalars (fixed order), then this CTA's private row --------------------------
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                double v = acc[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                acc[k] = v;
+            }
+            __syncthreads();       // tables of the last primitive quartet consumed; `red` free
+            if ((lane & 31) == 0) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) red[(lane >> 5) * 9 + k] = acc[k];
+            }
+            __syncthreads();
+            if (lane == 0) {
+                double tot[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    double v = 0.0;
+                    for (int w = 0; w < G / 32; w++) v += red[w * 9 + k];
+                    tot[k] = v;
+                }
+                const int atA = t.shell2atom[sa], atB = t.shell2atom[sb], atC = t.shell2atom[sc], atD = t.shell2atom[sd];
+#pragma unroll
+                for (int x = 0; x < 3; x++) {
+                    myrow[3 * atA + x] += tot[x];
+                    myrow[3 * atB + x] += tot[3 + x];
+                    myrow[3 * atC + x] += tot[6 + x];
+                    myrow[3 * atD + x] -= tot[x] + tot[3 + x] + tot[6 + x];     // translational invariance
+                }
+            }
+        }
+    }
+}

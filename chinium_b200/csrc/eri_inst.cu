@@ -4,7 +4,9 @@
 #include <type_traits>
 #include "eri_generic.cuh"
 #include "eri_tpq.cuh"
+#include "eri_tpqa.cuh"
 #include "eri_wg.cuh"
+#include "eri_grad.cuh"
 
 // developer knob for A/B measurements of the warp-group configurations (see wg_cfg in eri_wg.cuh)
 static int cf_wg_variant() {
@@ -43,15 +45,25 @@ static cudaError_t launch_pair(const QuartetTask& t, int store, int grid, cudaSt
     constexpr int NROOTS = (LA + LB + LC + LD) / 2 + 1;
     cudaError_t e;
     if constexpr (tpq_ok(LA, LB, LC, LD)) {
-        if (!store) {   // thread-per-quartet family: grid counts work items (bra pair x 128 kets)
+        if (!store) {   // thread-per-quartet family (bra-loop kernel): grid counts warp-private work items
             constexpr size_t smem = tpq_smem(NROOTS);
             if (g_out) *g_out = TPQ_THREADS;
             if (smem_out) *smem_out = smem;
-            if (kind_out) *kind_out = 1 + 16 * 32;    // items of <= 32 kets, one per warp
+            if (kind_out) *kind_out = 1 + 16 * 32;    // items: bra chunk x aligned block of 32 kets, one per warp
             if (grid <= 0) return cudaSuccess;
-            auto k = eri_jk_tpq<LA, LB, LC, LD>;
-            if (smem > 48 * 1024) { e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
-            k<<<grid, TPQ_THREADS, smem, s>>>(t);
+            // bra-loop kernel; the register accumulators are sized by the number of exchange densities
+            auto go = [&](auto k) -> cudaError_t {
+                if (smem > 48 * 1024) { cudaError_t e2 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e2 != cudaSuccess) return e2; }
+                k<<<grid, TPQ_THREADS, smem, s>>>(t);
+                return cudaSuccess;
+            };
+            // low contraction (digestion/atomics-bound): bra-loop kernel; high contraction (FP64-bound): the leaner
+            // one-bra-pair-per-item kernel.  The engine decides per task (QuartetTask::braloop) and builds the matching items.
+            if (!t.braloop) e = go(eri_jk_tpq<LA, LB, LC, LD>);
+            else if (t.nk <= 1) e = go(eri_jk_tpqa<LA, LB, LC, LD, 1>);
+            else if (t.nk == 2) e = go(eri_jk_tpqa<LA, LB, LC, LD, 2>);
+            else e = go(eri_jk_tpqa<LA, LB, LC, LD, 3>);
+            if (e != cudaSuccess) return e;
             return cudaGetLastError();
         }
     }
@@ -137,4 +149,34 @@ struct Dispatch<BRA, -1> {
 // cf_launch_bra<N>(ket_class, task, store, grid, stream, &G, &smem, &kind)   kind: 0 generic (grid = CTAs over quartet chunks), 1 thread-per-quartet
 cudaError_t CF_CAT(cf_launch_bra, CF_BRA)(int ket, const QuartetTask& t, int store, int grid, cudaStream_t s, int* g, size_t* sm, int* kind) {
     return Dispatch<CF_BRA, CF_BRA>::go(ket, t, store, grid, s, g, sm, kind);
+}
+
+// ---- nuclear-gradient kernels (eri_grad.cuh): one generic kernel per class pair ------------------------------------
+template <int BRA, int KET>
+static cudaError_t launch_grad_pair(const GradTask& t, int grid, cudaStream_t s, int* g_out, size_t* smem_out) {
+    constexpr int LA = ClassL<BRA>::a, LB = ClassL<BRA>::b, LC = ClassL<KET>::a, LD = ClassL<KET>::b;
+    constexpr int NOUT = cf_ncart(LA) * cf_ncart(LB) * cf_ncart(LC) * cf_ncart(LD);
+    constexpr int G = group_size(NOUT) < 64 ? 64 : group_size(NOUT);
+    const size_t smem = eri_grad_smem<LA, LB, LC, LD>(G);
+    if (g_out) *g_out = G;
+    if (smem_out) *smem_out = smem;
+    if (grid <= 0) return cudaSuccess;
+    auto k = eri_grad_generic<LA, LB, LC, LD, G>;
+    if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+    k<<<grid, G, smem, s>>>(t);
+    return cudaGetLastError();
+}
+template <int BRA, int KET>
+struct GradDispatch {
+    static cudaError_t go(int ket, const GradTask& t, int grid, cudaStream_t s, int* g, size_t* sm) {
+        if (ket == KET) return launch_grad_pair<BRA, KET>(t, grid, s, g, sm);
+        return GradDispatch<BRA, KET - 1>::go(ket, t, grid, s, g, sm);
+    }
+};
+template <int BRA>
+struct GradDispatch<BRA, -1> {
+    static cudaError_t go(int, const GradTask&, int, cudaStream_t, int*, size_t*) { return cudaErrorInvalidValue; }
+};
+cudaError_t CF_CAT(cf_launch_grad_bra, CF_BRA)(int ket, const GradTask& t, int grid, cudaStream_t s, int* g, size_t* sm) {
+    return GradDispatch<CF_BRA, CF_BRA>::go(ket, t, grid, s, g, sm);
 }

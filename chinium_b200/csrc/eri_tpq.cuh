@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
     constexpr int MAXBP = TPQ_WBP;
     extern __shared__ double smem[];
     const double scaleJ = __ldg(t.scales), scaleK = __ldg(t.scales + 1);
+    const double thr = __ldg(t.scales + 4);   // effective Schwarz threshold of this build (scales_kernel)
     double* tab = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* sbra = smem + TABLEN + warp * (TPQ_NBRA * MAXBP);   // this warp's [TPQ_NBRA][MAXBP]
@@ -187,7 +188,12 @@ __global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const Quarte
         const int ib = it.x;
         const int ik = it.y + lane;
         bool active = lane < it.z;
-        if (active && t.thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > t.thr;
+        if (active && thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > thr;
+        {   // warp-uniform: skip items whose quartets are all screened out; count the evaluated ones
+            const unsigned amask = __ballot_sync(0xffffffffu, active);
+            if (!amask) continue;
+            if (lane == 0 && t.nq_done) atomicAdd(t.nq_done + cf_nq_slot(), (unsigned long long)__popc(amask));
+        }
 
         // bra pair: uniform across the warp
         const int sa = t.bra.sa[ib], sb = t.bra.sb[ib];
@@ -501,6 +507,7 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
     static_assert(NA % GS == 0, "slices must divide the components of shell a");
     extern __shared__ double smem[];
     const double scaleJ = __ldg(t.scales), scaleK = __ldg(t.scales + 1);
+    const double thr = __ldg(t.scales + 4);   // effective Schwarz threshold of this build (scales_kernel)
     double* tab = smem;
     double* sbra = smem + TABLEN;                   // [TPQ_NBRA][TPQ_MAXBP]
     double* part = sbra + TPQ_NBRA * TPQ_MAXBP;     // [VC][GS][NQ]
@@ -532,7 +539,11 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
         const int ib = it.x;
         const int ik = it.y + q;
         bool active = q < it.z;
-        if (active && t.thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > t.thr;
+        if (active && thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > thr;
+        if (s == 0 && t.nq_done) {   // count the evaluated quartets (slice 0 of every quartet lives in the first warps)
+            const unsigned amask = __ballot_sync(0xffffffffu, active);
+            if ((threadIdx.x & 31) == 0 && amask) atomicAdd(t.nq_done + cf_nq_slot(), (unsigned long long)__popc(amask));
+        }
 
         const int sa = t.bra.sa[ib], sb = t.bra.sb[ib];
         const double Ax = t.bra.A[3 * ib], Ay = t.bra.A[3 * ib + 1], Az = t.bra.A[3 * ib + 2];

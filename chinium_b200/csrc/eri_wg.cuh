@@ -22,7 +22,10 @@
 #define WG_WARPS 4
 
 // bring the 128-byte line of a global address into L1 (the digestion reads it ~10^4 cycles later)
+#ifndef CF_HAVE_PREFETCH_L1
+#define CF_HAVE_PREFETCH_L1
 __device__ __forceinline__ void cf_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
 
 template <int B, int E, class F>
 __device__ __forceinline__ void wg_static_for(F&& f) {
@@ -156,6 +159,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double smem[];
     const double scaleJ = __ldg(t.scales), scaleK = __ldg(t.scales + 1);
+    const double thr = __ldg(t.scales + 4);   // effective Schwarz threshold of this build (scales_kernel)
     double* tab = smem;
     double* sbra = smem + C::TABLEN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -198,7 +202,11 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
         const int ib = it.x;
         const int ik = it.y + warp * QW + qi;
         bool active = lane_ok && warp * QW + qi < it.z;
-        if (active && t.thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > t.thr;
+        if (active && thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > thr;
+        if (t.nq_done) {   // count the evaluated quartets
+            const unsigned amask = __ballot_sync(FULL, active && g == 0);
+            if (lane == 0 && amask) atomicAdd(t.nq_done + cf_nq_slot(), (unsigned long long)__popc(amask));
+        }
 
         const int sa = t.bra.sa[ib], sb = t.bra.sb[ib];
         const double Ax = t.bra.A[3 * ib], Ay = t.bra.A[3 * ib + 1], Az = t.bra.A[3 * ib + 2];

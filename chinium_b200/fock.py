@@ -5,6 +5,7 @@ Same method names, argument meaning and error behaviour as the reference:
     getRepulsionIndices(output); getThreadPointers(nthreads, output); CalculateIntegrals(order, output);
     ContractInts(Dd, Da, Db, nthreads, output) -> (J, Kd, Ka, Kb)     [None = the reference's 0x0 matrix]
     ContractInts([D...], nthreads, output) -> [G...]
+    ContractGrads(D1, D2, output) -> [3*natoms]
 Everything numerical happens in libchinium_fock.so on the GPU.
 """
 from __future__ import annotations
@@ -40,7 +41,8 @@ class CfStats(C.Structure):
                 ("canonical_quartets", C.c_int64), ("canonical_quartets_local", C.c_int64),
                 ("unique_integrals", C.c_int64), ("primitive_quartets", C.c_int64),
                 ("flops_alg_jk", C.c_double * 4), ("n_launches_last", C.c_int),
-                ("ms_device_last", C.c_double), ("ms_eri_last", C.c_double), ("fixedpoint_scale_log2", C.c_double * 2)]
+                ("ms_device_last", C.c_double), ("ms_eri_last", C.c_double), ("fixedpoint_scale_log2", C.c_double * 2),
+                ("threshold_effective_last", C.c_double), ("quartets_evaluated_last", C.c_int64)]
 
     def as_dict(self):
         d = {}
@@ -71,6 +73,7 @@ def load_library(path: str = LIB_PATH):
     L.cf_last_error.argtypes = [vp]
     L.cf_get_stats.argtypes = [vp, C.POINTER(CfStats)]
     L.cf_nbf.argtypes = [vp]
+    L.cf_set_density_threshold.argtypes = [vp, C.c_double]
     L.cf_get_repulsion_diag.argtypes = [vp, dp]
     L.cf_build_jk.argtypes = [vp, ip, dp, dp, dp, C.c_double, dp, dp, dp, dp]
     L.cf_build_jk_device.argtypes = [vp, ip, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp]
@@ -79,6 +82,7 @@ def load_library(path: str = LIB_PATH):
     L.cf_accumulate_device.argtypes = [vp, ip, vp, vp, vp, C.c_double, vp, vp]
     L.cf_finalize_device.argtypes = [vp, ip, vp, C.c_double, ip, ip, ip, vp, vp, vp, vp, vp]
     L.cf_build_g_multi.argtypes = [vp, ip, ip, dp, C.c_double, dp]
+    L.cf_contract_grads.argtypes = [vp, ip, dp, dp, C.c_double, ip, dp]
     L.cf_device_info.argtypes = [ip, C.c_char_p, ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]
     L.cf_measure_fp64_peak.argtypes = [ip, dp]
     L.cf_sync_stats.argtypes = [vp]
@@ -159,6 +163,11 @@ class Int4C2E:
         except Exception:
             pass
 
+    def setDensityThreshold(self, dthr: float):
+        """Density-weighted screening for incremental builds (extension; see cf_set_density_threshold). 0 = off."""
+        self._ensure()
+        self._check(self._lib.cf_set_density_threshold(self._h, float(dthr)))
+
     @property
     def stats(self) -> dict:
         self._ensure()
@@ -229,6 +238,21 @@ class Int4C2E:
         out = np.zeros_like(stack)
         self._check(self._lib.cf_build_g_multi(self._h, n, len(Ds), _dptr(stack), self.EXX, _dptr(out)))
         return [np.asfortranarray(out[k].T) for k in range(len(Ds))]
+
+    # ---- nuclear gradient (Int4C2E.cpp:747-763) ------------------------------------------------------
+    def ContractGrads(self, D1, D2, output=0):
+        """ContractGrads(D1, D2, output) -> [3*natoms]: sum_ij D1_ij d/dR (J[2 D2] - EXX K[D2])_ij, index 3*atom + xyz.
+        (The reference's other overloads return the 3*natoms intermediate matrices; they are not formed here.)
+        With world_size > 1 this is the partition's share: sum over the ranks."""
+        self._ensure()
+        n = self.nbf
+        D1, D2 = _fmat(D1, n), _fmat(D2, n)
+        if D1 is None or D2 is None:
+            raise FockEngineError("ContractGrads needs two nbf x nbf matrices")
+        natom = int(np.max(self.MWFN.shell2atom)) + 1
+        g = np.zeros(3 * natom)
+        self._check(self._lib.cf_contract_grads(self._h, n, _dptr(D1), _dptr(D2), self.EXX, natom, _dptr(g)))
+        return g
 
     # ---- device-resident / multi-GPU building blocks (plain pointers: e.g. torch tensors' data_ptr()) ---
     def acc_len(self, nk):

@@ -85,6 +85,8 @@ typedef struct cf_stats {
     double  ms_device_last;            /* CUDA-event time of the last build (all kernels)            */
     double  ms_eri_last;               /* ... of the ERI/digestion kernels only                      */
     double  fixedpoint_scale_log2[2];  /* log2 of the J and K accumulator scales of the last build   */
+    double  threshold_effective_last;  /* Schwarz threshold the last build applied: max(threshold, density_threshold / max|D|) */
+    int64_t quartets_evaluated_last;   /* shell quartets this partition actually evaluated in the last build            */
 } cf_stats;
 
 /* cf_create: pair build + Schwarz bounds + class sort + task lists, all on the device.
@@ -96,6 +98,13 @@ void cf_destroy(cf_handle* h);
 const char* cf_last_error(const cf_handle* h);
 int cf_get_stats(const cf_handle* h, cf_stats* out);
 int cf_nbf(const cf_handle* h);
+
+/* Density-weighted screening for direct SCF (the stored-ERI reference has no counterpart):
+ * with dthr > 0 a shell quartet is evaluated iff Q_ab Q_cd > threshold (the reference's test, Int4C2E.cpp:108-113)
+ * AND Q_ab Q_cd * max|D| > dthr, max|D| being the largest element of the densities of THAT call (derived on the
+ * device per build).  Meant for incremental builds G[D_n - D_(n-1)]: the neglected contributions are bounded by
+ * dthr per quartet.  dthr <= 0 switches it off (default).  Results stay bit-identical for any number of GPUs. */
+int cf_set_density_threshold(cf_handle* h, double dthr);
 
 /* Schwarz diagonal (ab|ab) for all basis-function pairs, nbf x nbf col-major
  * (the reference's Diag1212, Int4C2E.cpp:19-77). */
@@ -132,6 +141,14 @@ int cf_finalize_device(cf_handle* h, int nbf, const int64_t* acc, double exx,
  * GhfMultiple (Int4C2E.cpp:685-745): G_k = J[2 D_k] - exx * K[D_k].  HOST pointers,
  * Ds/Gs are nmat consecutive nbf x nbf col-major matrices. */
 int cf_build_g_multi(cf_handle* h, int nbf, int nmat, const double* Ds, double exx, double* Gs);
+
+/* Nuclear-gradient contraction; replaces Int4C2E::ContractGrads(D1, D2, output) (Int4C2E.cpp:747-763)
+ * on top of getRepulsion1 (:312-408):  grad[3*atom + xyz] = sum_ij D1_ij G^(atom,xyz)[D2]_ij,  G^(A,x) = d/dA_x of
+ * (J[2 D2] - exx K[D2]) at fixed D2, the derivative acting on the four centres of every ERI (libint2's 12 buffers,
+ * :377-389).  The reference's 3*natom intermediate matrices are not formed.  HOST pointers; D1, D2 symmetric nbf x nbf;
+ * needs cf_basis.shell2atom at cf_create.  Quartets are screened with the handle's Schwarz threshold like the reference's
+ * list.  A handle with world_size > 1 returns ITS PARTITION's share: sum the vectors over the ranks. */
+int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const double* D2, double exx, int natom, double* grad);
 
 /* After the caller has synchronised the stream of a *_device call: refresh ms_device_last / ms_eri_last and run the
  * fixed-point range check of that build (the *_device calls never synchronise, so CF_ERR_RANGE for a non-finite or

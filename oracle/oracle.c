@@ -753,6 +753,197 @@ void oracle_jk_block(const cf_basis* b, int nbf, const double* Dtot, const doubl
     free(part); free(s2bf);
 }
 
+/* ================================================================ first-derivative ERIs
+ * The reference asks libint2 for deriv_order = 1 (Int4C2E.cpp:339) and reads 12 buffers: d/dR of the integral for the
+ * centres of s1..s4 x (x,y,z) (:377-389).  Restated here from first principles: for a primitive Cartesian Gaussian
+ * d/dA_x [ (x-A)^l e^{-a r_A^2} ] = 2a (x-A)^{l+1} e^{..} - l (x-A)^{l-1} e^{..}, so a derivative block is the
+ * (l+1) block with primitive prefactors scaled by 2a minus l_x times the (l-1) block; the pure transformation of the
+ * ORIGINAL shell is applied afterwards (it is linear and independent of the centre). */
+static void make_pair_shift(const cf_basis* b, int sa, int sb, int da, int db, int ea, int eb, pairdata* pd) {
+    make_pair(b, sa, sb, pd);
+    free(pd->E);
+    int la = sh_l(b, sa) + da, lb = sh_l(b, sb) + db;
+    int na = b->nprim[sa], nb = b->nprim[sb];
+    const double* A = b->center_xyz + 3 * sa;
+    const double* B = b->center_xyz + 3 * sb;
+    pd->la = la; pd->lb = lb;
+    pd->E = (ecoef*)malloc(sizeof(ecoef) * 3 * pd->npp);
+    int n = 0;
+    for (int i = 0; i < na; i++)
+        for (int j = 0; j < nb; j++, n++) {
+            double a = b->exps[b->prim_offset[sa] + i], bb = b->exps[b->prim_offset[sb] + j];
+            if (ea) pd->K[n] *= 2.0 * a;
+            if (eb) pd->K[n] *= 2.0 * bb;
+            for (int x = 0; x < 3; x++) hermite_E(la, lb, pd->p[n], pd->P[3 * n + x] - A[x], pd->P[3 * n + x] - B[x], &pd->E[3 * n + x]);
+        }
+}
+
+/* buf12[(pos*3 + dir)][n1][n2][n3][n4]: d (s1 s2|s3 s4) / d R_pos,dir in the reference's function order */
+void oracle_eri_deriv_quartet(const cf_basis* b, int s1, int s2, int s3, int s4, double* buf12) {
+    int sh[4] = {s1, s2, s3, s4};
+    int l[4], nc[4], nf[4];
+    for (int i = 0; i < 4; i++) { l[i] = sh_l(b, sh[i]); nc[i] = NCART(l[i]); nf[i] = sh_nfun(b, sh[i]); }
+    size_t ncart = (size_t)nc[0] * nc[1] * nc[2] * nc[3], nfun = (size_t)nf[0] * nf[1] * nf[2] * nf[3];
+    pairdata ab0, cd0;
+    make_pair(b, s1, s2, &ab0); make_pair(b, s3, s4, &cd0);
+    double* dcart = (double*)malloc(sizeof(double) * ncart);
+    double* t1 = (double*)malloc(sizeof(double) * ncart);
+    double* t2 = (double*)malloc(sizeof(double) * ncart);
+    double C[(2 * LMAX + 1) * NCMAX];
+    for (int pos = 0; pos < 4; pos++) {
+        int lp = l[pos];
+        int ncp = NCART(lp + 1), ncm = lp > 0 ? NCART(lp - 1) : 0;
+        int nn[4] = {nc[0], nc[1], nc[2], nc[3]};
+        nn[pos] = ncp;
+        size_t nplus = (size_t)nn[0] * nn[1] * nn[2] * nn[3];
+        nn[pos] = ncm;
+        size_t nminus = (size_t)nn[0] * nn[1] * nn[2] * nn[3];
+        double* plus = (double*)malloc(sizeof(double) * nplus);
+        double* minus = ncm ? (double*)malloc(sizeof(double) * nminus) : NULL;
+        pairdata sp, sm;
+        int da = (pos == 0 || pos == 2) ? 1 : 0, db = 1 - da;
+        if (pos < 2) { make_pair_shift(b, s1, s2, da, db, da, db, &sp); eri_cart(&sp, &cd0, plus); }
+        else { make_pair_shift(b, s3, s4, da, db, da, db, &sp); eri_cart(&ab0, &sp, plus); }
+        free_pair(&sp);
+        if (ncm) {
+            if (pos < 2) { make_pair_shift(b, s1, s2, -da, -db, 0, 0, &sm); eri_cart(&sm, &cd0, minus); }
+            else { make_pair_shift(b, s3, s4, -da, -db, 0, 0, &sm); eri_cart(&ab0, &sm, minus); }
+            free_pair(&sm);
+        }
+        int comp[NCMAX][3];
+        cart_components(lp, comp);
+        /* strides of the 4-index Cartesian tensors around index `pos` */
+        size_t outer = 1, inner = 1;
+        for (int i = 0; i < pos; i++) outer *= nc[i];
+        for (int i = pos + 1; i < 4; i++) inner *= nc[i];
+        for (int dir = 0; dir < 3; dir++) {
+            for (size_t o = 0; o < outer; o++)
+                for (int c = 0; c < nc[pos]; c++) {
+                    int e[3] = {comp[c][0], comp[c][1], comp[c][2]};
+                    e[dir] += 1;
+                    int cp = cart_index(lp + 1, e[0], e[1]);
+                    int cm = -1;
+                    if (comp[c][dir] > 0) { e[dir] -= 2; cm = cart_index(lp - 1, e[0], e[1]); }
+                    for (size_t k = 0; k < inner; k++) {
+                        double v = plus[(o * ncp + cp) * inner + k];
+                        if (cm >= 0) v -= comp[c][dir] * minus[(o * ncm + cm) * inner + k];
+                        dcart[(o * nc[pos] + c) * inner + k] = v;
+                    }
+                }
+            int n[4] = {nc[0], nc[1], nc[2], nc[3]};
+            memcpy(t1, dcart, sizeof(double) * ncart);
+            double* src = t1; double* dst = t2;
+            for (int i = 0; i < 4; i++) {
+                int nnew = shell_transform(b->type[sh[i]], C);
+                transform_index(src, dst, n, i, C, nnew);
+                n[i] = nnew;
+                double* tmp = src; src = dst; dst = tmp;
+            }
+            memcpy(buf12 + (size_t)(pos * 3 + dir) * nfun, src, sizeof(double) * nfun);
+        }
+        free(plus); if (minus) free(minus);
+    }
+    free(dcart); free(t1); free(t2);
+    free_pair(&ab0); free_pair(&cd0);
+}
+
+/* getRepulsion1 (Int4C2E.cpp:312-408) restated: loop nest of the reference's quartet list (:83-93), function-level
+ * uniqueness predicate and abcd_deg (:377-383), the six scatter updates per atom and direction (:388-397), then
+ * gs = 1/2 (rawj + rawj^T) - 1/2 kscale * 1/4 (rawk + rawk^T) (:403-405).  G: [3*natom][nbf*nbf] col-major. */
+void ref_getRepulsion1(const cf_basis* b, int natom, const double* D, double kscale, double* G, int nthreads) {
+    int nbf = oracle_nbf(b), ns = b->nshell;
+    int* s2bf = (int*)malloc(sizeof(int) * ns);
+    shell2bf(b, s2bf);
+    size_t n2 = (size_t)nbf * nbf, nmat = (size_t)3 * natom;
+    if (nthreads < 1) nthreads = 1;
+    double* raw = (double*)calloc(2 * nmat * n2 * nthreads, sizeof(double));   /* per thread: rawjs | rawks */
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
+    for (int s1 = ns - 1; s1 >= 0; s1--) {
+#ifdef _OPENMP
+        int ith = omp_get_thread_num();
+#else
+        int ith = 0;
+#endif
+        double* rawj = raw + (size_t)ith * 2 * nmat * n2;
+        double* rawk = rawj + nmat * n2;
+        double* buf = (double*)malloc(sizeof(double) * 12 * (size_t)(2 * LMAX + 1) * (2 * LMAX + 1) * (2 * LMAX + 1) * (2 * LMAX + 1));
+        short bf1_first = s2bf[s1], n1 = sh_nfun(b, s1);
+        for (short s2 = 0; s2 <= s1; s2++) {
+            short bf2_first = s2bf[s2], n2f = sh_nfun(b, s2);
+            for (short s3 = 0; s3 <= s1; s3++) {
+                short bf3_first = s2bf[s3], n3 = sh_nfun(b, s3);
+                for (short s4 = 0; s4 <= (s2 > s3 ? s2 : s3); s4++) {
+                    short bf4_first = s2bf[s4], n4 = sh_nfun(b, s4);
+                    size_t nfun = (size_t)n1 * n2f * n3 * n4;
+                    oracle_eri_deriv_quartet(b, s1, s2, s3, s4, buf);
+                    const int atomlist[4] = {b->shell2atom[s1], b->shell2atom[s2], b->shell2atom[s3], b->shell2atom[s4]};
+                    int f1234 = 0;
+                    for (short f1 = 0; f1 != n1; f1++) {
+                        const short bf1 = bf1_first + f1;
+                        for (short f2 = 0; f2 != n2f; f2++) {
+                            const short bf2 = bf2_first + f2;
+                            const double ab_deg = (bf1 == bf2) ? 1 : 2;
+                            for (short f3 = 0; f3 != n3; f3++) {
+                                const short bf3 = bf3_first + f3;
+                                for (short f4 = 0; f4 != n4; f4++, f1234++) {
+                                    const short bf4 = bf4_first + f4;
+                                    if (bf2 <= bf1 && bf3 <= bf1 && bf4 <= ((bf1 == bf3) ? bf2 : bf3)) {
+                                        const double cd_deg = (bf3 == bf4) ? 1 : 2;
+                                        const double ab_cd_deg = (bf1 == bf3) ? (bf2 == bf4 ? 1 : 2) : 2;
+                                        const double abcd_deg = ab_deg * cd_deg * ab_cd_deg;
+                                        for (int p = 0, pt = 0; p < 4; p++) {
+                                            const int atom = atomlist[p];
+                                            for (int t = 0; t < 3; t++, pt++) {
+                                                const double tmp = abcd_deg * buf[(size_t)pt * nfun + f1234];
+                                                double* rj = rawj + (size_t)(atom * 3 + t) * n2;
+                                                double* rk = rawk + (size_t)(atom * 3 + t) * n2;
+                                                M(rj, bf1, bf2) += tmp * M(D, bf3, bf4);
+                                                M(rj, bf3, bf4) += tmp * M(D, bf1, bf2);
+                                                if (kscale > 0) {
+                                                    M(rk, bf1, bf3) += tmp * M(D, bf2, bf4);
+                                                    M(rk, bf2, bf4) += tmp * M(D, bf1, bf3);
+                                                    M(rk, bf1, bf4) += tmp * M(D, bf2, bf3);
+                                                    M(rk, bf2, bf3) += tmp * M(D, bf1, bf4);
+                                                }
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        free(buf);
+    }
+    for (int t = 1; t < nthreads; t++)
+        for (size_t i = 0; i < 2 * nmat * n2; i++) raw[i] += raw[(size_t)t * 2 * nmat * n2 + i];
+    for (size_t m = 0; m < nmat; m++) {
+        const double* rj = raw + m * n2;
+        const double* rk = raw + (nmat + m) * n2;
+        double* g = G + m * n2;
+        for (int i = 0; i < nbf; i++)
+            for (int j = 0; j < nbf; j++)
+                M(g, i, j) = 0.5 * (M(rj, i, j) + M(rj, j, i)) - 0.5 * kscale * 0.25 * (M(rk, i, j) + M(rk, j, i));
+    }
+    free(raw); free(s2bf);
+}
+
+/* Int4C2E::ContractGrads(D1, D2) (Int4C2E.cpp:747-763): grad[j] = sum D1 o G_j[D2], j = 3*atom + xyz */
+void ref_ContractGrads(const cf_basis* b, int natom, const double* D1, const double* D2, double kscale, double* grad, int nthreads) {
+    int nbf = oracle_nbf(b);
+    size_t n2 = (size_t)nbf * nbf;
+    double* G = (double*)malloc(sizeof(double) * 3 * natom * n2);
+    ref_getRepulsion1(b, natom, D2, kscale, G, nthreads);
+    for (int j = 0; j < 3 * natom; j++) {
+        double s = 0;
+        for (size_t i = 0; i < n2; i++) s += D1[i] * G[(size_t)j * n2 + i];
+        grad[j] = s;
+    }
+    free(G);
+}
+
 /* The whole reference path in one call (setup :49-53 of SelfConsistentField.cpp + ContractInts).
  * counts: [0] RepulsionLength, [1] ShellQuartetLength. Returns 0. */
 int ref_full_path(const cf_basis* b, double threshold, double exx, int nthreads,

@@ -141,6 +141,34 @@ class Oracle:
                                  C.c_int(nthreads or self.nthreads))
         return Jb, Kb
 
+    # first-derivative path (SURVEY 8f rank 2)
+    def eri_deriv_quartet(self, fb, s1, s2, s3, s4):
+        """[12 = centre of s1..s4 x (x,y,z)][n1][n2][n3][n4]: the 12 buffers libint2 hands the reference (Int4C2E.cpp:377-389)"""
+        b, keep = as_cf_basis(fb)
+        n = [int(fb.nfun[s]) for s in (s1, s2, s3, s4)]
+        buf = np.zeros([12] + n)
+        self.lib.oracle_eri_deriv_quartet(C.byref(b), s1, s2, s3, s4, _dp(buf))
+        return buf
+
+    def grad_matrices(self, fb, D, exx=1.0, nthreads=None):
+        """getRepulsion1 (Int4C2E.cpp:312-408): 3*natom matrices G^(atom,xyz)[D], each nbf x nbf"""
+        b, keep = as_cf_basis(fb)
+        natom = int(np.max(fb.shell2atom)) + 1
+        D = _fmat(D)
+        G = np.zeros((3 * natom, fb.nbf * fb.nbf))
+        self.lib.ref_getRepulsion1(C.byref(b), C.c_int(natom), _dp(D), C.c_double(exx), _dp(G), C.c_int(nthreads or self.nthreads))
+        return [np.asfortranarray(g.reshape(fb.nbf, fb.nbf).T) for g in G]
+
+    def contract_grads(self, fb, D1, D2, exx=1.0, nthreads=None):
+        """Int4C2E::ContractGrads(D1, D2) (Int4C2E.cpp:747-763) -> [3*natom]"""
+        b, keep = as_cf_basis(fb)
+        natom = int(np.max(fb.shell2atom)) + 1
+        D1, D2 = _fmat(D1), _fmat(D2)
+        g = np.zeros(3 * natom)
+        self.lib.ref_ContractGrads(C.byref(b), C.c_int(natom), _dp(D1), _dp(D2), C.c_double(exx), _dp(g),
+                                   C.c_int(nthreads or self.nthreads))
+        return g
+
     # stored-integral handle (B1 timing)
     def store_build(self, fb, threshold=-1.0):
         b, keep = as_cf_basis(fb)

@@ -64,6 +64,43 @@ def rhf(S, Hcore, nocc, jk, e_nuc=0.0, D0=None, max_iter=100, tol=1e-8, diis_spa
     raise RuntimeError("Convergence failed!")  # same message as Restricted/SP.cpp:76
 
 
+def rhf_incremental(S, Hcore, nocc, jk, e_nuc=0.0, max_iter=100, tol=1e-8, diis_space=12, rebuild_every=8, log=None):
+    """Direct-SCF variant of `rhf`: G = J - K is updated with the density DIFFERENCE,
+    G_n = G_(n-1) + G[D_n - D_(n-1)] (the J/K build is linear in D), with a full rebuild every `rebuild_every`
+    iterations so that screening errors cannot pile up.  `jk(D, full)` -> (J, K); `full` tells the caller whether
+    the matrix is a whole density (no density-weighted screening) or a difference.  Same convergence test as `rhf`."""
+    w, U = np.linalg.eigh(S)
+    X = U @ np.diag(w ** -0.5) @ U.T
+    def density(F):
+        e, Cp = np.linalg.eigh(X.T @ F @ X)
+        C_ = X @ Cp
+        return C_[:, :nocc] @ C_[:, :nocc].T
+    D = density(Hcore)
+    Fs, Rs = [], []
+    G, D_prev = None, None
+    for it in range(max_iter):
+        full = G is None or it % rebuild_every == 0
+        if full:
+            J, K = jk(D, True)
+            G = J - K
+        else:
+            J, K = jk(D - D_prev, False)
+            G = G + (J - K)
+        D_prev = D
+        if log is not None:
+            log.append(full)
+        F = Hcore + G
+        E = np.sum(D * (2 * Hcore + G)) + e_nuc
+        R = 2 * (F @ D @ S - S @ D @ F)
+        err = np.abs(R).max()
+        if err < tol:
+            return E, D, F, it
+        Fs.append(F); Rs.append(X.T @ R @ X)
+        Fs, Rs = Fs[-diis_space:], Rs[-diis_space:]
+        D = density(_diis_extrapolate(Fs, Rs))
+    raise RuntimeError("Convergence failed!")
+
+
 def uhf(S, Hcore, na, nb, jk, e_nuc=0.0, D0=None, max_iter=200, tol=1e-8, diis_space=12, verbose=False, level_shift=0.0):
     w, U = np.linalg.eigh(S)
     X = U @ np.diag(w ** -0.5) @ U.T

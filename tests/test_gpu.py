@@ -304,3 +304,93 @@ def test_schwarz_threshold_matches_reference_count(Int4C2E, oracle):
         # every dropped quartet has |(ab|cd)| <= thr; at most nbf^2 of them touch one element, |D| <= 1/nbf
         assert np.abs(J - Jf).max() < thr * fb.nbf * 4 and np.abs(K - Kf).max() < thr * fb.nbf * 4
         eng.close()
+
+
+def test_density_weighted_screening(Int4C2E, oracle):
+    """cf_set_density_threshold: with a small density (a late-SCF difference density) the effective
+    Schwarz threshold rises to dthr / max|D|, fewer quartets are evaluated, and J/K still match the unscreened oracle
+    far below the 1e-10 bar (every neglected contribution is < dthr)."""
+    mol, fb = load_fixture_molecule("bo3h3")
+    n = fb.nbf
+    dD = 1e-5 * H.random_symmetric_density(n, 7) * n        # entries ~1e-5: a typical late-iteration difference
+    eng = _engine(Int4C2E, fb)
+    J0, K0, _, _ = eng.ContractInts(dD, None, None, 1, 0)
+    st0 = eng.stats
+    assert st0["quartets_evaluated_last"] == st0["canonical_quartets"]
+    assert st0["threshold_effective_last"] == 0.0
+    eng.setDensityThreshold(1e-13)
+    J1, K1, _, _ = eng.ContractInts(dD, None, None, 1, 0)
+    st1 = eng.stats
+    assert 0 < st1["quartets_evaluated_last"] < st0["canonical_quartets"]
+    dmax = 2 * np.abs(dD).max()
+    assert 0.2e-13 / dmax < st1["threshold_effective_last"] < 5e-13 / dmax     # max|D| is taken in the Cartesian basis
+    Jo, Ko, _, _, _ = oracle.direct_jk(fb, dD)
+    assert np.abs(J0 - Jo).max() < TOL and np.abs(K0 - Ko).max() < TOL
+    assert np.abs(J1 - Jo).max() < TOL and np.abs(K1 - Ko).max() < TOL
+    eng.setDensityThreshold(0.0)                             # off again: bit-identical to the first build
+    J2, K2, _, _ = eng.ContractInts(dD, None, None, 1, 0)
+    assert (J2 == J0).all() and (K2 == K0).all()
+    eng.close()
+
+
+def test_incremental_scf_energy(Int4C2E, oracle):
+    """Incremental Fock builds G_n = G_(n-1) + G[D_n - D_(n-1)] with density-weighted screening reproduce the
+    energy of the plain SCF (full build every iteration) to 1e-8 Eh and skip quartets in the late iterations."""
+    mol, fb = load_fixture_molecule("sn2")
+    S, T, V = oracle.one_electron(fb, mol.Z, mol.xyz_bohr)
+    enuc = H.nuclear_repulsion(mol.Z, mol.xyz_bohr)
+    eng = _engine(Int4C2E, fb)
+    E_full, *_ = H.rhf(S, T + V, 18, lambda d, a, b: eng.ContractInts(d, a, b, 1, 0), enuc)
+    evaluated, log = [], []
+
+    def jk(D, full):
+        eng.setDensityThreshold(0.0 if full else 1e-12)
+        J, K, _, _ = eng.ContractInts(D, None, None, 1, 0)
+        evaluated.append(eng.stats["quartets_evaluated_last"])
+        return J, K
+
+    E_inc, *_ = H.rhf_incremental(S, T + V, 18, jk, enuc, log=log)
+    total = eng.stats["canonical_quartets"]
+    eng.close()
+    assert abs(E_inc - E_full) < 1e-8
+    assert abs(E_inc - (-598.514802895)) < 1e-7
+    inc = [e for e, f in zip(evaluated, log) if not f]
+    assert inc and min(inc) < 0.8 * total        # late difference densities are small: quartets are skipped
+
+
+@pytest.mark.parametrize("name,exx", [("h2o", 1.0), ("hf_tz", 0.7), ("bo3h3", 0.2)])
+def test_contract_grads_parity(Int4C2E, oracle, name, exx):
+    """ContractGrads(D1, D2) (Int4C2E.cpp:747-763 over getRepulsion1 :312-408): the fused derivative-ERI kernels vs the
+    oracle's literal restatement (12 derivative buffers per quartet, per-atom scatter, D1 o G), s..f shells."""
+    mol, fb = load_fixture_molecule(name)
+    n = fb.nbf
+    D1, D2 = H.random_symmetric_density(n, 21) * n, H.random_symmetric_density(n, 22) * n
+    eng = _engine(Int4C2E, fb, exx=exx)
+    g = eng.ContractGrads(D1, D2, 0)
+    go = oracle.contract_grads(fb, D1, D2, exx)
+    assert g.shape == go.shape
+    assert np.abs(g - go).max() < 1e-9 * max(1.0, np.abs(go).max()), (np.abs(g - go).max(), np.abs(go).max())
+    g2 = eng.ContractGrads(D1, D2, 0)
+    assert (g2 == g).all()                                       # fixed-order row sums: repeatable bit for bit
+    natom = len(go) // 3
+    assert np.abs(g.reshape(natom, 3).sum(axis=0)).max() < 1e-9 * max(1.0, np.abs(go).max())
+    # J-only (EXX <= 0) and the usual D1 == D2 call of Restricted/Grad.cpp:66
+    eng.EXX = 0.0
+    assert np.abs(eng.ContractGrads(D2, D2, 0) - oracle.contract_grads(fb, D2, D2, 0.0)).max() < 1e-9 * max(1.0, np.abs(go).max())
+    eng.close()
+
+
+def test_contract_grads_partition_sum(Int4C2E, oracle):
+    """world_size = 2: the two partitions' gradient shares add up to the whole (the caller's all-reduce)."""
+    mol, fb = load_fixture_molecule("h2o")
+    n = fb.nbf
+    D = H.random_symmetric_density(n, 23) * n
+    whole = _engine(Int4C2E, fb)
+    g = whole.ContractGrads(D, D, 0)
+    whole.close()
+    parts = []
+    for r in range(2):
+        e = _engine(Int4C2E, fb, rank=r, world_size=2)
+        parts.append(e.ContractGrads(D, D, 0))
+        e.close()
+    assert np.abs(parts[0] + parts[1] - g).max() < 1e-12 * max(1.0, np.abs(g).max())

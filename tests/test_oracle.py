@@ -156,3 +156,63 @@ def test_normalize_shell_matches_unit_norm():
     # s primitive: (2a/pi)^(3/4)
     c = normalize_shell(0, [0.5], [1.0])
     assert abs(c[0] - (2 * 0.5 / math.pi) ** 0.75) < 1e-15
+
+
+# ---- first-derivative path: the oracle's derivative ERIs and its getRepulsion1 restatement ----
+def _displaced(fb, shells, x, h):
+    import copy
+    fb2 = copy.deepcopy(fb)
+    c = np.array(fb2.center_xyz, dtype=np.float64).reshape(-1, 3).copy()
+    for s in shells:
+        c[s, x] += h
+    fb2.center_xyz = c.reshape(np.shape(fb.center_xyz))
+    return fb2
+
+
+def test_derivative_eris_finite_difference_and_translation(oracle):
+    """12 derivative buffers of a shell quartet (Int4C2E.cpp:377-389): central differences of the ERI block with ONE
+    shell displaced, and translational invariance (the four centre derivatives sum to zero)."""
+    mol, fb = load_fixture_molecule("h2o")
+    l = [abs(int(t)) for t in fb.type]
+    d = l.index(2)
+    p = [i for i, v in enumerate(l) if v == 1]
+    quartets = [(d, p[0], p[-1], 0), (d, d, p[0], 1), (p[1], 0, d, p[2]), (fb.nshell - 1, d, p[0], p[0])]
+    h = 1e-4
+    for q in quartets:
+        der = oracle.eri_deriv_quartet(fb, *q)
+        assert np.abs(der.reshape(4, 3, -1).sum(axis=0)).max() < 1e-12          # translational invariance
+        for s in set(q):
+            pos = [i for i in range(4) if q[i] == s]
+            for x in range(3):
+                fp, fm = _displaced(fb, [s], x, h), _displaced(fb, [s], x, -h)
+                fd = (oracle.eri_quartet(fp, *q) - oracle.eri_quartet(fm, *q)) / (2 * h)
+                an = sum(der[3 * i + x] for i in pos)
+                assert np.abs(fd - an).max() < 2e-7 * max(1.0, np.abs(an).max()), (q, s, x)
+
+
+def test_gradient_restatement_against_energy_finite_difference(oracle):
+    """ContractGrads(D1, D2) (Int4C2E.cpp:747-763 over getRepulsion1 :312-408) equals the derivative of
+    sum D1 o (J[2 D2] - EXX K[D2]) with respect to the nuclear positions at fixed densities."""
+    mol, fb = load_fixture_molecule("h2o")
+    n = fb.nbf
+    D1, D2 = H.random_symmetric_density(n, 11) * n, H.random_symmetric_density(n, 12) * n
+    exx = 0.7
+    g = oracle.contract_grads(fb, D1, D2, exx)
+    natom = int(np.max(fb.shell2atom)) + 1
+    assert g.shape == (3 * natom,)
+    assert np.abs(g.reshape(natom, 3).sum(axis=0)).max() < 1e-10                 # no net force from a translation
+    h = 1e-4
+
+    def energy(f):
+        J, K, _, _, _ = oracle.direct_jk(f, D2, exx=exx)
+        return np.sum(D1 * (J - K))
+
+    s2a = np.asarray(fb.shell2atom)
+    for atom, x in ((0, 1), (1, 0), (2, 2)):
+        shells = [s for s in range(fb.nshell) if s2a[s] == atom]
+        fd = (energy(_displaced(fb, shells, x, h)) - energy(_displaced(fb, shells, x, -h))) / (2 * h)
+        assert abs(fd - g[3 * atom + x]) < 5e-7 * max(1.0, abs(fd)), (atom, x, fd, g[3 * atom + x])
+    # the matrices themselves: symmetric, and D1 o G reproduces the contracted gradient
+    G = oracle.grad_matrices(fb, D2, exx)
+    assert len(G) == 3 * natom and all(np.abs(m - m.T).max() < 1e-13 for m in G)
+    assert np.abs(np.array([np.sum(D1 * m) for m in G]) - g).max() < 1e-12
