@@ -155,6 +155,73 @@ def run_reference(args):
     return 0
 
 
+def run_grad(args):
+    """ContractGrads(D, D) (Int4C2E.cpp:747-763): ms per call and canonical shell quartets/s, FP64 roofline by the
+    gradient F_alg model of DESIGN.md, the oracle's getRepulsion1 restatement timed beside it where it finishes in
+    about a minute (h2o, bo3h3).  One GPU; `--impl reference` times only the CPU restatement."""
+    from chinium_b200.inputs import load_fixture_molecule
+    import scf_harness as H
+    fixture, kind = WORKLOADS[args.workload]
+    mol, fb = load_fixture_molecule(fixture)
+    D = H.random_symmetric_density(fb.nbf, 0) * fb.nbf
+    exx = exx_of(kind)
+    npairs = fb.nshell * (fb.nshell + 1) // 2
+    total_q = npairs * (npairs + 1) // 2
+    cpu = None
+    if (args.impl == "reference" or not args.no_cpu_baseline) and fb.nbf <= 80:
+        from oracle_lib import Oracle
+        o = Oracle()
+        t = time.perf_counter(); o.contract_grads(fb, D, D, exx); dt = time.perf_counter() - t
+        cpu = dict(value=total_q / dt, unit="quartets/s", cores=o.nthreads, kind="port", seconds=dt,
+                   sample="whole workload: oracle restatement of getRepulsion1 + ContractGrads (MD derivative ERIs, OpenMP)")
+    base = {"metric": "ERI shell quartets/s (nuclear-gradient contraction ContractGrads)", "unit": "quartets/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s (%s, nbf %d, %d canonical shell quartets)" % (args.workload, kind, fb.nbf, total_q),
+                       "densities": "D1 = D2 = seeded random symmetric, EXX=%.1f" % exx}}
+    if args.impl == "reference":
+        if cpu is None:
+            print(json.dumps({"impl": "reference", "unavailable": "CPU gradient restatement is only timed for nbf <= 80"}))
+            return 0
+        base.update(impl="reference", value=cpu["value"], ms_per_step=cpu["seconds"] * 1e3, cpu_baseline=cpu,
+                    e2e={"value": cpu["value"], "unit": "quartets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(base))
+        return 0
+    import torch
+    from chinium_b200 import Int4C2E
+    from chinium_b200.fock import measure_fp64_peak
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; this engine has no CPU fallback"}))
+        return 1
+    eng = Int4C2E(fb, exx, args.threshold if args.threshold is not None else DEFAULT_THRESHOLD.get(args.workload, -1.0))
+    for _ in range(max(1, args.warmup)):
+        eng.ContractGrads(D, D, 0)
+    sampler = ClockSampler(0); sampler.start()
+    t = time.perf_counter(); dev_ms = []; launches = 0
+    for _ in range(args.steps):
+        eng.ContractGrads(D, D, 0)              # host matrices in, host vector out, synchronous
+        st = eng.stats
+        dev_ms.append(st["ms_grad_last"]); launches += st["n_launches_last"]
+    e2e_s = (time.perf_counter() - t) / args.steps
+    clocks = sampler.stop()
+    peak = measure_fp64_peak(0)
+    ms = float(np.mean(dev_ms))
+    flops = eng.stats["flops_alg_grad"]
+    q = eng.stats["canonical_quartets"]
+    base.update(value=q / (ms * 1e-3), ms_per_step=ms, gpu_launches=launches, clocks=clocks,
+                e2e={"value": q / e2e_s, "unit": "quartets/s", "ms_per_step": e2e_s * 1e3,
+                     "h2d_bytes_per_step": 2 * fb.nbf * fb.nbf * 8, "d2h_bytes_per_step": 3 * 8 * (int(np.max(fb.shell2atom)) + 1)},
+                roofline={"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                          "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None, "flops_alg": flops,
+                          "kernel": "eri_grad_generic<*> (all class-pair gradient launches of one call)",
+                          "peak_source": "measured in-run: register-resident DFMA loop (cf_measure_fp64_peak)"})
+    if cpu is not None:
+        base["cpu_baseline"] = cpu
+    print(json.dumps(base))
+    eng.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,7 +234,12 @@ def main():
                          "except h2o64, where the unscreened job is 2.7e11 quartets: 1e-13 (see DESIGN.md)")
     ap.add_argument("--per-class", action="store_true", help="also time every class-pair kernel alone (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", default="jk", choices=["jk", "grad"],
+                    help="jk: the Fock J/K build (the BASELINE metric, default); grad: the nuclear-gradient contraction "
+                         "ContractGrads(D, D) (SURVEY 8f rank 2), its own JSON line")
     args = ap.parse_args()
+    if args.path == "grad":
+        return run_grad(args)
     if args.impl == "reference":
         return run_reference(args)
 

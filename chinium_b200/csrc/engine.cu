@@ -950,7 +950,11 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
             t->nq_item = t->kind >> 4; t->swap = (t->kind >> 3) & 1; t->kind &= 7;
             // thread-per-quartet classes: tasks with few primitive quartets per shell quartet are bound by the digestion
             // (atomics, latency) -> bra-loop kernel; deeply contracted ones are FP64-bound -> one bra pair per item
-            t->braloop = (t->kind == 1 && primq < CF_BRALOOP_MAXK * nq) ? 1 : 0;
+            {   // the larger register-resident classes gain less from the bra loop and pay for its extra registers sooner
+                const int nout = cf_ncart(B.la) * cf_ncart(B.lb) * cf_ncart(K.la) * cf_ncart(K.lb);
+                const double kmax = nout <= 18 ? CF_BRALOOP_MAXK : 0.375 * CF_BRALOOP_MAXK;
+                t->braloop = (t->kind == 1 && primq < kmax * nq) ? 1 : 0;
+            }
             if (const char* e = getenv("CF_BRALOOP")) t->braloop = (t->kind == 1 && atoi(e) != 0) ? 1 : 0;   // developer override (A/B)
             if (t->braloop) {   // bra-loop kernels: (bra chunk of one a-group) x (aligned block of 32 kets)
                 // chunk length: long chunks amortise the J(c,d)/K(a,.) flushes, but the static schedule wants >= ~32 items
@@ -1015,10 +1019,15 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
             st.unique_integrals += (long long)(uniq + 0.5);
             st.primitive_quartets += (long long)(primq + 0.5);
             for (int k = 0; k < 4; k++) st.flops_alg_jk[k] += t->flops_eri + 2.0 * (2 + 4 * k) * t->nfun_sum;
+            {   // gradient model: K n_r' [40 + 12 (L_ab+2)(L_cd+2) + 48 N_c] + 32 N_c per quartet
+                const int nr1 = (L + 1) / 2 + 1;
+                const double ncq = (double)cf_ncart(B.la) * cf_ncart(B.lb) * cf_ncart(K.la) * cf_ncart(K.lb);
+                st.flops_alg_grad += primq_full * nr1 * (40.0 + 12.0 * (B.la + B.lb + 2) * (K.la + K.lb + 2) + 48.0 * ncq) + 32.0 * ncq * (double)nq_kept;
+            }
             h->tasks.push_back(t);
         }
     st.canonical_quartets_local = st.canonical_quartets / h->opt.world_size;
-    if (h->opt.world_size > 1) for (int k = 0; k < 4; k++) st.flops_alg_jk[k] /= h->opt.world_size;
+    if (h->opt.world_size > 1) { for (int k = 0; k < 4; k++) st.flops_alg_jk[k] /= h->opt.world_size; st.flops_alg_grad /= h->opt.world_size; }
     // heavy tasks first so the tail of the build is made of small kernels
     std::sort(h->tasks.begin(), h->tasks.end(), [](const ClassPairTask* a, const ClassPairTask* b) { return a->flops_eri > b->flops_eri; });
 
@@ -1314,6 +1323,8 @@ extern "C" int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const 
                                             h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[1 + k].p,
                                             h->d_B.p + (size_t)k * ns2, h->d_Bmax.p + (size_t)k * ns2);
     CUDA_TRY(cudaMemsetAsync(h->d_gpart.p, 0, sizeof(double) * (size_t)max_grid * ngrad, 0));
+    CUDA_TRY(cudaEventRecord(h->ev[1], 0));
+    int nlaunch = 2;
     for (ClassPairTask* t : h->tasks) {
         const PairClassHost& B = h->cls[t->bra];
         const PairClassHost& K = h->cls[t->ket];
@@ -1343,11 +1354,18 @@ extern "C" int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const 
         const int grid = (int)std::min<long long>(nchunk_local, max_grid);
         cudaError_t e = g_grad_launch[t->bra](t->ket, gt, grid, 0, nullptr, nullptr);
         if (e != cudaSuccess) { set_error(h, std::string("gradient kernel launch failed: ") + cudaGetErrorString(e)); return CF_ERR_CUDA; }
+        nlaunch++;
     }
+    CUDA_TRY(cudaEventRecord(h->ev[2], 0));
     grad_reduce_kernel<<<(ngrad + 127) / 128, 128>>>(h->d_gpart.p, max_grid, ngrad, h->d_grad.p);
     CUDA_TRY(cudaMemcpyAsync(grad, h->d_grad.p, sizeof(double) * ngrad, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaStreamSynchronize(0));
     CUDA_TRY(cudaGetLastError());
+    {   // CUDA-event time of the gradient kernels of this call
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->stats.ms_grad_last = ms;
+        h->stats.n_launches_last = nlaunch + 1;
+    }
     return CF_OK;
 }
 

@@ -150,8 +150,11 @@ __device__ __forceinline__ double warp_sum_fixed(double v) {
 #ifndef TPQ_MINB
 #define TPQ_MINB 2
 #endif
+// resident CTAs the register allocation is held to: the small classes sit right at the 128-register boundary
+__host__ __device__ constexpr int tpq_minb(int nout) { return nout <= 9 ? 4 : TPQ_MINB; }
+
 template <int LA, int LB, int LC, int LD>
-__global__ void __launch_bounds__(TPQ_THREADS, TPQ_MINB) eri_jk_tpq(const QuartetTask t) {
+__global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(LB) * cf_ncart(LC) * cf_ncart(LD))) eri_jk_tpq(const QuartetTask t) {
     constexpr int NA = cf_ncart(LA), NB = cf_ncart(LB), NC = cf_ncart(LC), ND = cf_ncart(LD);
     constexpr int NAB = NA * NB, NCD = NC * ND, NOUT = NAB * NCD;
     constexpr int NROOTS = (LA + LB + LC + LD) / 2 + 1;

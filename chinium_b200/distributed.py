@@ -79,5 +79,13 @@ class DistributedInt4C2E:
                 res.append(np.zeros((n, n), order="F"))
         return tuple(res)
 
+    def ContractGrads(self, D1, D2, output=0):
+        """Nuclear-gradient contraction (Int4C2E.cpp:747-763): every rank contracts its partition of the quartets,
+        the 3*natoms partial vectors are summed with one all-reduce (double; tiny)."""
+        g = torch.from_numpy(self.eng.ContractGrads(D1, D2, output)).to(self.device)
+        if self.world > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        return g.cpu().numpy()
+
     def close(self):
         self.eng.close()

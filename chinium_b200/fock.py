@@ -42,7 +42,8 @@ class CfStats(C.Structure):
                 ("unique_integrals", C.c_int64), ("primitive_quartets", C.c_int64),
                 ("flops_alg_jk", C.c_double * 4), ("n_launches_last", C.c_int),
                 ("ms_device_last", C.c_double), ("ms_eri_last", C.c_double), ("fixedpoint_scale_log2", C.c_double * 2),
-                ("threshold_effective_last", C.c_double), ("quartets_evaluated_last", C.c_int64)]
+                ("threshold_effective_last", C.c_double), ("quartets_evaluated_last", C.c_int64),
+                ("flops_alg_grad", C.c_double), ("ms_grad_last", C.c_double)]
 
     def as_dict(self):
         d = {}

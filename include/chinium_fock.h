@@ -87,6 +87,8 @@ typedef struct cf_stats {
     double  fixedpoint_scale_log2[2];  /* log2 of the J and K accumulator scales of the last build   */
     double  threshold_effective_last;  /* Schwarz threshold the last build applied: max(threshold, density_threshold / max|D|) */
     int64_t quartets_evaluated_last;   /* shell quartets this partition actually evaluated in the last build            */
+    double  flops_alg_grad;            /* F_alg of one cf_contract_grads call (DESIGN.md model), this partition          */
+    double  ms_grad_last;              /* CUDA-event time of the gradient kernels of the last cf_contract_grads call     */
 } cf_stats;
 
 /* cf_create: pair build + Schwarz bounds + class sort + task lists, all on the device.

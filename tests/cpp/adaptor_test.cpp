@@ -1,5 +1,5 @@
 // adaptor_test.cpp -- exercises chinium_b200/cpp/Int4C2E_b200.hpp the way the reference's SCF driver uses
-// Int4C2E (src/HartreeFockKohnSham/SelfConsistentField.cpp:47-53, Restricted/SP.cpp:47), with a column-major
+// Int4C2E (src/HartreeFockKohnSham/SelfConsistentField.cpp:47-53, Restricted/SP.cpp:47, Restricted/Grad.cpp:66), with a column-major
 // matrix shim standing in for Eigen::MatrixXd.  Input: a flat text dump of the basis and a density written by
 // tests/test_gpu.py; output: J and K as text.  Exit code 3 = "no GPU" (the loud failure the CPU test checks).
 #include <cstdio>
@@ -58,6 +58,9 @@ int main(int argc, char** argv) {
         for (double x : Gs[1].v) out << x << "\n";
         double ka = 0; for (double x : Ka.v) ka += x * x;
         out << ka << "\n";
+        const std::vector<double> grads = copy.ContractGrads(D, D, 1);     // Restricted/Grad.cpp:66
+        out << grads.size() << "\n";
+        for (double x : grads) out << x << "\n";
     } catch (const std::exception& e) {
         std::fprintf(stderr, "adaptor_test: %s\n", e.what());
         return std::strstr(e.what(), "no CUDA device") || std::strstr(e.what(), "no CPU fallback") ? 3 : 1;

@@ -9,8 +9,8 @@ EXE = os.path.join(ROOT, "tests", "cpp", "adaptor_test")
 
 def build():
     """g++ the adaptor test against libchinium_fock.so (rpath relative to the binary, so it travels to the GPU box)."""
-    hdr = os.path.join(ROOT, "chinium_b200", "cpp", "Int4C2E_b200.hpp")
-    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+    deps = [SRC, os.path.join(ROOT, "chinium_b200", "cpp", "Int4C2E_b200.hpp"), os.path.join(ROOT, "include", "chinium_fock.h")]
+    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(d) for d in deps):
         return EXE
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", EXE, SRC, "-L" + os.path.join(ROOT, "chinium_b200"),
                            "-lchinium_fock", "-Wl,-rpath,$ORIGIN/../../chinium_b200"])

@@ -264,6 +264,10 @@ def test_cpp_adaptor_matches_oracle(Int4C2E, oracle, tmp_path):
     assert np.abs(J - Jo).max() < TOL and np.abs(K - Ko).max() < TOL
     assert np.abs(G - (Jo - Ko)).max() < TOL
     assert v[3 * n * n] == 0.0      # absent Ka -> zeros
+    ng = int(v[3 * n * n + 1])
+    g = v[3 * n * n + 2:3 * n * n + 2 + ng]
+    go = oracle.contract_grads(fb, D, D, 0.5)
+    assert ng == len(go) and np.abs(g - go).max() < 1e-9 * max(1.0, np.abs(go).max())     # Restricted/Grad.cpp:66 call
 
 
 def test_h2o64_schwarz_screened_blocks(Int4C2E, oracle):
