@@ -261,13 +261,13 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
             for (int x = 0; x < t.nk; x++) {
                 const double* D = t.Dk[x];
                 double* d = Dx + x * NDX;
-                for (int e = lane; e < NA * NC; e += G) d[e] = D[(size_t)(cc + e % NC) * ld + ca + e / NC];
+                for (int e = lane; e < NA * NC; e += G) d[e] = D[(size_t)(ca + e / NC) * ld + cc + e % NC];
                 d += NA * NC;
-                for (int e = lane; e < NA * ND; e += G) d[e] = D[(size_t)(cdd + e % ND) * ld + ca + e / ND];
+                for (int e = lane; e < NA * ND; e += G) d[e] = D[(size_t)(ca + e / ND) * ld + cdd + e % ND];
                 d += NA * ND;
-                for (int e = lane; e < NB * NC; e += G) d[e] = D[(size_t)(cc + e % NC) * ld + cb + e / NC];
+                for (int e = lane; e < NB * NC; e += G) d[e] = D[(size_t)(cb + e / NC) * ld + cc + e % NC];
                 d += NB * NC;
-                for (int e = lane; e < NB * ND; e += G) d[e] = D[(size_t)(cdd + e % ND) * ld + cb + e / ND];
+                for (int e = lane; e < NB * ND; e += G) d[e] = D[(size_t)(cb + e / ND) * ld + cdd + e % ND];
             }
             __syncthreads();
             // J targets: NAB (bra block) + NCD (ket block)
@@ -295,22 +295,22 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
                         const int i = e / NC, k = e % NC;
                         for (int j = 0; j < NB; j++)
                             for (int l = 0; l < ND; l++) s = fma(V[((i * NB + j) * NC + k) * ND + l], dbd[j * ND + l], s);
-                        fixed_add(acc + (size_t)(cc + k) * ld + ca + i, s, scaleK);
+                        fixed_add(acc + (size_t)(ca + i) * ld + cc + k, s, scaleK);
                     } else if (e < NA * NC + NA * ND) {      // K(i,l) += sum_jk V D(j,k)
                         const int f = e - NA * NC, i = f / ND, l = f % ND;
                         for (int j = 0; j < NB; j++)
                             for (int k = 0; k < NC; k++) s = fma(V[((i * NB + j) * NC + k) * ND + l], dbc[j * NC + k], s);
-                        fixed_add(acc + (size_t)(cdd + l) * ld + ca + i, s, scaleK);
+                        fixed_add(acc + (size_t)(ca + i) * ld + cdd + l, s, scaleK);
                     } else if (e < NA * NC + NA * ND + NB * NC) {   // K(j,k) += sum_il V D(i,l)
                         const int f = e - NA * NC - NA * ND, j = f / NC, k = f % NC;
                         for (int i = 0; i < NA; i++)
                             for (int l = 0; l < ND; l++) s = fma(V[((i * NB + j) * NC + k) * ND + l], dad[i * ND + l], s);
-                        fixed_add(acc + (size_t)(cc + k) * ld + cb + j, s, scaleK);
+                        fixed_add(acc + (size_t)(cb + j) * ld + cc + k, s, scaleK);
                     } else {                                  // K(j,l) += sum_ik V D(i,k)
                         const int f = e - NA * NC - NA * ND - NB * NC, j = f / ND, l = f % ND;
                         for (int i = 0; i < NA; i++)
                             for (int k = 0; k < NC; k++) s = fma(V[((i * NB + j) * NC + k) * ND + l], dac[i * NC + k], s);
-                        fixed_add(acc + (size_t)(cdd + l) * ld + cb + j, s, scaleK);
+                        fixed_add(acc + (size_t)(cb + j) * ld + cdd + l, s, scaleK);
                     }
                 }
             }

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
             {   // K(a,c) += sum_bd V D(b,d)
                 double d[NB * ND];
 #pragma unroll
-                for (int e = 0; e < NB * ND; e++) d[e] = D[(cd0 + e % ND) * ld + cb + e / ND];
+                for (int e = 0; e < NB * ND; e++) d[e] = D[(cb + e / ND) * ld + cd0 + e % ND];
 #pragma unroll
                 for (int i = 0; i < NA; i++)
 #pragma unroll
@@ -343,13 +343,13 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
                         for (int j = 0; j < NB; j++)
 #pragma unroll
                             for (int l = 0; l < ND; l++) s = fma(gout[((i * NB + j) * NC + k) * ND + l], d[j * ND + l], s);
-                        fixed_add(acc + (cc0 + k) * ld + ca + i, s, scaleK);
+                        fixed_add(acc + (ca + i) * ld + cc0 + k, s, scaleK);
                     }
             }
             {   // K(a,d) += sum_bc V D(b,c)
                 double d[NB * NC];
 #pragma unroll
-                for (int e = 0; e < NB * NC; e++) d[e] = D[(cc0 + e % NC) * ld + cb + e / NC];
+                for (int e = 0; e < NB * NC; e++) d[e] = D[(cb + e / NC) * ld + cc0 + e % NC];
 #pragma unroll
                 for (int i = 0; i < NA; i++)
 #pragma unroll
@@ -359,13 +359,13 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
                         for (int j = 0; j < NB; j++)
 #pragma unroll
                             for (int k = 0; k < NC; k++) s = fma(gout[((i * NB + j) * NC + k) * ND + l], d[j * NC + k], s);
-                        fixed_add(acc + (cd0 + l) * ld + ca + i, s, scaleK);
+                        fixed_add(acc + (ca + i) * ld + cd0 + l, s, scaleK);
                     }
             }
             {   // K(b,c) += sum_ad V D(a,d)
                 double d[NA * ND];
 #pragma unroll
-                for (int e = 0; e < NA * ND; e++) d[e] = D[(cd0 + e % ND) * ld + ca + e / ND];
+                for (int e = 0; e < NA * ND; e++) d[e] = D[(ca + e / ND) * ld + cd0 + e % ND];
 #pragma unroll
                 for (int j = 0; j < NB; j++)
 #pragma unroll
@@ -375,13 +375,13 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
                         for (int i = 0; i < NA; i++)
 #pragma unroll
                             for (int l = 0; l < ND; l++) s = fma(gout[((i * NB + j) * NC + k) * ND + l], d[i * ND + l], s);
-                        fixed_add(acc + (cc0 + k) * ld + cb + j, s, scaleK);
+                        fixed_add(acc + (cb + j) * ld + cc0 + k, s, scaleK);
                     }
             }
             {   // K(b,d) += sum_ac V D(a,c)
                 double d[NA * NC];
 #pragma unroll
-                for (int e = 0; e < NA * NC; e++) d[e] = D[(cc0 + e % NC) * ld + ca + e / NC];
+                for (int e = 0; e < NA * NC; e++) d[e] = D[(ca + e / NC) * ld + cc0 + e % NC];
 #pragma unroll
                 for (int j = 0; j < NB; j++)
 #pragma unroll
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
                         for (int i = 0; i < NA; i++)
 #pragma unroll
                             for (int k = 0; k < NC; k++) s = fma(gout[((i * NB + j) * NC + k) * ND + l], d[i * NC + k], s);
-                        fixed_add(acc + (cd0 + l) * ld + cb + j, s, scaleK);
+                        fixed_add(acc + (cb + j) * ld + cd0 + l, s, scaleK);
                     }
             }
         }
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                 {   // K(a,c) += sum_bd V D(b,d)   (complete)
                     double d[NB * ND];
 #pragma unroll
-                    for (int e = 0; e < NB * ND; e++) d[e] = D[(cd0 + e % ND) * ld + cb + e / ND];
+                    for (int e = 0; e < NB * ND; e++) d[e] = D[(cb + e / ND) * ld + cd0 + e % ND];
 #pragma unroll
                     for (int m = 0; m < MA; m++)
 #pragma unroll
@@ -700,13 +700,13 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                             for (int j = 0; j < NB; j++)
 #pragma unroll
                                 for (int l = 0; l < ND; l++) sum = fma(gout[((m * NB + j) * NC + k) * ND + l], d[j * ND + l], sum);
-                            fixed_add(acc + (cc0 + k) * ld + ca + ia0 + m, sum, scaleK);
+                            fixed_add(acc + (ca + ia0 + m) * ld + cc0 + k, sum, scaleK);
                         }
                 }
                 {   // K(a,d) += sum_bc V D(b,c)   (complete)
                     double d[NB * NC];
 #pragma unroll
-                    for (int e = 0; e < NB * NC; e++) d[e] = D[(cc0 + e % NC) * ld + cb + e / NC];
+                    for (int e = 0; e < NB * NC; e++) d[e] = D[(cb + e / NC) * ld + cc0 + e % NC];
 #pragma unroll
                     for (int m = 0; m < MA; m++)
 #pragma unroll
@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                             for (int j = 0; j < NB; j++)
 #pragma unroll
                                 for (int k = 0; k < NC; k++) sum = fma(gout[((m * NB + j) * NC + k) * ND + l], d[j * NC + k], sum);
-                            fixed_add(acc + (cd0 + l) * ld + ca + ia0 + m, sum, scaleK);
+                            fixed_add(acc + (ca + ia0 + m) * ld + cd0 + l, sum, scaleK);
                         }
                 }
             }
@@ -728,9 +728,9 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
             for (int m = 0; m < MA; m++) {
                 double dad[ND], dac[NC];
 #pragma unroll
-                for (int l = 0; l < ND; l++) dad[l] = active ? D[(cd0 + l) * ld + ca + ia0 + m] : 0.0;
+                for (int l = 0; l < ND; l++) dad[l] = active ? D[(ca + ia0 + m) * ld + cd0 + l] : 0.0;
 #pragma unroll
-                for (int k = 0; k < NC; k++) dac[k] = active ? D[(cc0 + k) * ld + ca + ia0 + m] : 0.0;
+                for (int k = 0; k < NC; k++) dac[k] = active ? D[(ca + ia0 + m) * ld + cc0 + k] : 0.0;
 #pragma unroll
                 for (int j = 0; j < NB; j++)
 #pragma unroll
@@ -744,9 +744,9 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
             }
             reduce_add(std::integral_constant<int, NB * NC + NB * ND>{}, kp,
                        [&](int e) {
-                           if (e < NB * NC) return (size_t)(cc0 + e % NC) * ld + cb + e / NC;
+                           if (e < NB * NC) return (size_t)(cb + e / NC) * ld + cc0 + e % NC;
                            const int f = e - NB * NC;
-                           return (size_t)(cd0 + f % ND) * ld + cb + f / ND;
+                           return (size_t)(cb + f / ND) * ld + cd0 + f % ND;
                        }, acc, scaleK);
         }
     }

@@ -154,9 +154,9 @@ eri_jk_tpqa(const QuartetTask t) {
                 if (x < t.nk) {
                     const double* __restrict__ D = t.Dk[x];
 #pragma unroll
-                    for (int e = 0; e < NA * NC; e++) dkeep[x * NKA + e] = lane_ok ? D[(cc0 + e % NC) * ld + ca + e / NC] : 0.0;
+                    for (int e = 0; e < NA * NC; e++) dkeep[x * NKA + e] = lane_ok ? D[(ca + e / NC) * ld + cc0 + e % NC] : 0.0;
 #pragma unroll
-                    for (int e = 0; e < NA * ND; e++) dkeep[x * NKA + NA * NC + e] = lane_ok ? D[(cd0 + e % ND) * ld + ca + e / ND] : 0.0;
+                    for (int e = 0; e < NA * ND; e++) dkeep[x * NKA + NA * NC + e] = lane_ok ? D[(ca + e / ND) * ld + cd0 + e % ND] : 0.0;
                 }
         }
 
@@ -280,7 +280,7 @@ eri_jk_tpqa(const QuartetTask t) {
                 {   // K(a,c) += sum_bd V D(b,d)
                     double d[NB * ND];
 #pragma unroll
-                    for (int e = 0; e < NB * ND; e++) d[e] = D[(cd0 + e % ND) * ld + cb + e / ND];
+                    for (int e = 0; e < NB * ND; e++) d[e] = D[(cb + e / ND) * ld + cd0 + e % ND];
 #pragma unroll
                     for (int i = 0; i < NA; i++)
 #pragma unroll
@@ -291,13 +291,13 @@ eri_jk_tpqa(const QuartetTask t) {
 #pragma unroll
                                 for (int l = 0; l < ND; l++) s = fma(gout[((i * NB + j) * NC + k) * ND + l], d[j * ND + l], s);
                             if constexpr (ACCK) kacc[x * NKA + i * NC + k] += s;
-                            else fixed_add(acc + (cc0 + k) * ld + ca + i, s, scaleK);
+                            else fixed_add(acc + (ca + i) * ld + cc0 + k, s, scaleK);
                         }
                 }
                 {   // K(a,d) += sum_bc V D(b,c)
                     double d[NB * NC];
 #pragma unroll
-                    for (int e = 0; e < NB * NC; e++) d[e] = D[(cc0 + e % NC) * ld + cb + e / NC];
+                    for (int e = 0; e < NB * NC; e++) d[e] = D[(cb + e / NC) * ld + cc0 + e % NC];
 #pragma unroll
                     for (int i = 0; i < NA; i++)
 #pragma unroll
@@ -308,7 +308,7 @@ eri_jk_tpqa(const QuartetTask t) {
 #pragma unroll
                                 for (int k = 0; k < NC; k++) s = fma(gout[((i * NB + j) * NC + k) * ND + l], d[j * NC + k], s);
                             if constexpr (ACCK) kacc[x * NKA + NA * NC + i * ND + l] += s;
-                            else fixed_add(acc + (cd0 + l) * ld + ca + i, s, scaleK);
+                            else fixed_add(acc + (ca + i) * ld + cd0 + l, s, scaleK);
                         }
                 }
                 {   // K(b,c) += sum_ad V D(a,d)
@@ -316,7 +316,7 @@ eri_jk_tpqa(const QuartetTask t) {
 #pragma unroll
                     for (int e = 0; e < NA * ND; e++) {
                         if constexpr (KEEPD) d[e] = dkeep[x * NKA + NA * NC + e];
-                        else d[e] = D[(cd0 + e % ND) * ld + ca + e / ND];
+                        else d[e] = D[(ca + e / ND) * ld + cd0 + e % ND];
                     }
 #pragma unroll
                     for (int j = 0; j < NB; j++)
@@ -327,7 +327,7 @@ eri_jk_tpqa(const QuartetTask t) {
                             for (int i = 0; i < NA; i++)
 #pragma unroll
                                 for (int l = 0; l < ND; l++) s = fma(gout[((i * NB + j) * NC + k) * ND + l], d[i * ND + l], s);
-                            fixed_add(acc + (cc0 + k) * ld + cb + j, s, scaleK);
+                            fixed_add(acc + (cb + j) * ld + cc0 + k, s, scaleK);
                         }
                 }
                 {   // K(b,d) += sum_ac V D(a,c)
@@ -335,7 +335,7 @@ eri_jk_tpqa(const QuartetTask t) {
 #pragma unroll
                     for (int e = 0; e < NA * NC; e++) {
                         if constexpr (KEEPD) d[e] = dkeep[x * NKA + e];
-                        else d[e] = D[(cc0 + e % NC) * ld + ca + e / NC];
+                        else d[e] = D[(ca + e / NC) * ld + cc0 + e % NC];
                     }
 #pragma unroll
                     for (int j = 0; j < NB; j++)
@@ -346,7 +346,7 @@ eri_jk_tpqa(const QuartetTask t) {
                             for (int i = 0; i < NA; i++)
 #pragma unroll
                                 for (int k = 0; k < NC; k++) s = fma(gout[((i * NB + j) * NC + k) * ND + l], d[i * NC + k], s);
-                            fixed_add(acc + (cd0 + l) * ld + cb + j, s, scaleK);
+                            fixed_add(acc + (cb + j) * ld + cd0 + l, s, scaleK);
                         }
                 }
             }
@@ -364,9 +364,9 @@ eri_jk_tpqa(const QuartetTask t) {
                     if (x >= t.nk) break;
                     long long* acc = t.accK[x];
 #pragma unroll
-                    for (int e = 0; e < NA * NC; e++) fixed_add(acc + (cc0 + e % NC) * ld + ca + e / NC, kacc[x * NKA + e], scaleK);
+                    for (int e = 0; e < NA * NC; e++) fixed_add(acc + (ca + e / NC) * ld + cc0 + e % NC, kacc[x * NKA + e], scaleK);
 #pragma unroll
-                    for (int e = 0; e < NA * ND; e++) fixed_add(acc + (cd0 + e % ND) * ld + ca + e / ND, kacc[x * NKA + NA * NC + e], scaleK);
+                    for (int e = 0; e < NA * ND; e++) fixed_add(acc + (ca + e / ND) * ld + cd0 + e % ND, kacc[x * NKA + NA * NC + e], scaleK);
                 }
             }
         }

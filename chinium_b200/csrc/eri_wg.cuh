@@ -236,10 +236,10 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
                 if (!fok[m]) continue;
                 cf_prefetch_l1(t.Dtot + (cd0 + fid[m]) * ld + cc0 + fic[m]);
                 for (int x = 0; x < t.nk; x++) {
-                    cf_prefetch_l1(t.Dk[x] + (cd0 + fid[m]) * ld + ca);
-                    cf_prefetch_l1(t.Dk[x] + (cd0 + fid[m]) * ld + cb);
-                    cf_prefetch_l1(t.Dk[x] + (cc0 + fic[m]) * ld + ca);
-                    cf_prefetch_l1(t.Dk[x] + (cc0 + fic[m]) * ld + cb);
+                    cf_prefetch_l1(t.Dk[x] + (ca) * ld + cd0 + fid[m]);
+                    cf_prefetch_l1(t.Dk[x] + (cb) * ld + cd0 + fid[m]);
+                    cf_prefetch_l1(t.Dk[x] + (ca) * ld + cc0 + fic[m]);
+                    cf_prefetch_l1(t.Dk[x] + (cb) * ld + cc0 + fic[m]);
                 }
             }
         }
@@ -406,9 +406,9 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
                     if (!fok[m]) continue;
                     double dbd[NB], dad[NAP];
 #pragma unroll
-                    for (int j = 0; j < NB; j++) dbd[j] = D[(cd0 + fid[m]) * ld + cb + j];
+                    for (int j = 0; j < NB; j++) dbd[j] = D[(cb + j) * ld + cd0 + fid[m]];
 #pragma unroll
-                    for (int i = 0; i < NAP; i++) dad[i] = D[(cd0 + fid[m]) * ld + ca + IA0 + i];
+                    for (int i = 0; i < NAP; i++) dad[i] = D[(ca + IA0 + i) * ld + cd0 + fid[m]];
                     double kbc[NB];
 #pragma unroll
                     for (int j = 0; j < NB; j++) kbc[j] = 0.0;
@@ -425,13 +425,13 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
             }
             __syncwarp();
             if (active)
-                for (int tg = g; tg < (NAP + NB) * NC; tg += GS) {     // rows fastest: consecutive lanes -> consecutive addresses
-                    const int k = tg / (NAP + NB), r = tg - k * (NAP + NB);
+                for (int tg = g; tg < (NAP + NB) * NC; tg += GS) {     // c components fastest: consecutive lanes -> consecutive addresses
+                    const int r = tg / NC, k = tg - r * NC;
                     double s = 0.0;
 #pragma unroll
                     for (int l = 0; l < ND; l++) s += myq[(r * NC + k) * ND + l];
                     const int row = r < NAP ? ca + IA0 + r : cb + (r - NAP);
-                    fixed_add(accK + (cc0 + k) * ld + row, s, scaleK);
+                    fixed_add(accK + (row) * ld + cc0 + k, s, scaleK);
                 }
             __syncwarp();
             // half 2: K(a,d) += sum_bc V D(b,c) ; K(b,d) += sum_ac V D(a,c)   -> slots [.., id, ic], summed over ic
@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
                     if (!fok[m]) continue;
                     double dbc[NB], dac[NAP];
 #pragma unroll
-                    for (int j = 0; j < NB; j++) dbc[j] = D[(cc0 + fic[m]) * ld + cb + j];
+                    for (int j = 0; j < NB; j++) dbc[j] = D[(cb + j) * ld + cc0 + fic[m]];
 #pragma unroll
-                    for (int i = 0; i < NAP; i++) dac[i] = D[(cc0 + fic[m]) * ld + ca + IA0 + i];
+                    for (int i = 0; i < NAP; i++) dac[i] = D[(ca + IA0 + i) * ld + cc0 + fic[m]];
                     double kbd[NB];
 #pragma unroll
                     for (int j = 0; j < NB; j++) kbd[j] = 0.0;
@@ -461,12 +461,12 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
             __syncwarp();
             if (active)
                 for (int tg = g; tg < (NAP + NB) * ND; tg += GS) {
-                    const int l = tg / (NAP + NB), r = tg - l * (NAP + NB);
+                    const int r = tg / ND, l = tg - r * ND;
                     double s = 0.0;
 #pragma unroll
                     for (int k = 0; k < NC; k++) s += myq[(r * ND + l) * NC + k];
                     const int row = r < NAP ? ca + IA0 + r : cb + (r - NAP);
-                    fixed_add(accK + (cd0 + l) * ld + row, s, scaleK);
+                    fixed_add(accK + (row) * ld + cd0 + l, s, scaleK);
                 }
             __syncwarp();
         }
