@@ -222,6 +222,43 @@ def run_grad(args):
     return 0
 
 
+def run_multi(args):
+    """ContractInts(std::vector<EigenMatrix>&) (Int4C2E.cpp:685-745) with three densities: one batched pass over the
+    integrals against three separate J/K builds (what the call cost before batching).  Host API, one GPU."""
+    import torch
+    from chinium_b200 import Int4C2E
+    from chinium_b200.inputs import load_fixture_molecule
+    import scf_harness as H
+    fixture, kind = WORKLOADS[args.workload]
+    mol, fb = load_fixture_molecule(fixture)
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; this engine has no CPU fallback"}))
+        return 1
+    Ds = [H.random_symmetric_density(fb.nbf, s) for s in range(3)]
+    eng = Int4C2E(fb, 1.0, args.threshold if args.threshold is not None else DEFAULT_THRESHOLD.get(args.workload, -1.0))
+    for _ in range(max(1, args.warmup)):
+        eng.ContractInts(Ds, 1, 0)
+    t = time.perf_counter(); dev = []
+    for _ in range(args.steps):
+        eng.ContractInts(Ds, 1, 0); dev.append(eng.stats["ms_eri_last"])
+    batched = (time.perf_counter() - t) / args.steps
+    eng.ContractInts(Ds[0], None, None, 1, 0)
+    t = time.perf_counter(); dev1 = []
+    for _ in range(args.steps):
+        for D in Ds:
+            eng.ContractInts(D, None, None, 1, 0); dev1.append(eng.stats["ms_eri_last"])
+    single = (time.perf_counter() - t) / args.steps
+    q = eng.stats["canonical_quartets"]
+    print(json.dumps({"metric": "multi-density build ContractInts(vector) with 3 matrices", "unit": "ms", "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "higher_is_better": False, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "%s (nbf %d, %d canonical shell quartets), 3 seeded symmetric densities, EXX=1" % (args.workload, fb.nbf, q)},
+                      "value": batched * 1e3, "ms_eri_kernels_batched": float(np.mean(dev)),
+                      "three_separate_builds_ms": single * 1e3, "ms_eri_kernels_three_builds": float(np.sum(dev1) / args.steps),
+                      "speedup_vs_separate": single / batched}))
+    eng.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -234,12 +271,14 @@ def main():
                          "except h2o64, where the unscreened job is 2.7e11 quartets: 1e-13 (see DESIGN.md)")
     ap.add_argument("--per-class", action="store_true", help="also time every class-pair kernel alone (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--path", default="jk", choices=["jk", "grad"],
+    ap.add_argument("--path", default="jk", choices=["jk", "grad", "multi"],
                     help="jk: the Fock J/K build (the BASELINE metric, default); grad: the nuclear-gradient contraction "
                          "ContractGrads(D, D) (SURVEY 8f rank 2), its own JSON line")
     args = ap.parse_args()
     if args.path == "grad":
         return run_grad(args)
+    if args.path == "multi":
+        return run_multi(args)
     if args.impl == "reference":
         return run_reference(args)
 

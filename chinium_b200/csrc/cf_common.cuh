@@ -61,6 +61,9 @@ struct QuartetTask {
     int ncart;              // leading dimension of the Cartesian matrices
     int nk;                 // number of exchange densities (0..3)
     const double* Dtot;     // [ncart*ncart] Cartesian total density (2Dd+Da+Db), symmetric
+    int nj;                 // Coulomb densities digested by this launch: 1 for the J/K build (Dj[0] == Dtot, accJm[0] == accJ), up to 3
+    const double* Dj[3];    //   for the multi-density build (Int4C2E.cpp:685-745), where J_k and K_k share the integrals
+    long long* accJm[3];
     const double* Dk[3];    // Cartesian exchange densities
     long long* accJ;        // [ncart*ncart] fixed-point raw J
     long long* accK[3];

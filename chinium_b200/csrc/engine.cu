@@ -1037,7 +1037,7 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     for (auto& b : h->d_Dpure) ok = ok && b.alloc(n2p) == cudaSuccess;
     for (auto& b : h->d_Dcart) ok = ok && b.alloc(n2c) == cudaSuccess;
     for (auto& b : h->d_out) ok = ok && b.alloc(n2p) == cudaSuccess;
-    ok = ok && h->d_acc.alloc(4 * n2c) == cudaSuccess && h->d_partial.alloc(4 * 256) == cudaSuccess && h->d_scales.alloc(8) == cudaSuccess && h->d_nq.alloc(CF_NQ_SLOTS) == cudaSuccess;
+    ok = ok && h->d_acc.alloc(6 * n2c) == cudaSuccess && h->d_partial.alloc(4 * 256) == cudaSuccess && h->d_scales.alloc(8) == cudaSuccess && h->d_nq.alloc(CF_NQ_SLOTS) == cudaSuccess;
     if (!ok) return fail("cudaMalloc failed (work space)");
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(std::string("setup kernels failed: ") + cudaGetErrorString(cudaGetLastError()));
     if (h->opt.verbose > 0) {
@@ -1131,6 +1131,7 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
         qt.Dtot = h->d_Dcart[0].p;
         for (int x = 0; x < nk; x++) { qt.Dk[x] = h->d_Dcart[1 + x].p; qt.accK[x] = (long long*)acc + (size_t)(1 + x) * n2c; }
         qt.accJ = (long long*)acc;
+        qt.nj = 1; qt.Dj[0] = qt.Dtot; qt.accJm[0] = qt.accJ;
         qt.scales = h->d_scales.p; qt.nq_done = h->d_nq.p;
         qt.store = nullptr; qt.diag = 0; qt.prim_cut = 1e-22;
         fill_rys(qt, h);
@@ -1272,6 +1273,7 @@ extern "C" int cf_profile_tasks(cf_handle* h, int nbf, const double* Dd_dev, con
         qt.Dtot = h->d_Dcart[0].p;
         for (int x = 0; x < nk; x++) { qt.Dk[x] = h->d_Dcart[1 + x].p; qt.accK[x] = h->d_acc.p + (size_t)(1 + x) * n2c; }
         qt.accJ = h->d_acc.p; qt.scales = h->d_scales.p; qt.prim_cut = 1e-22;
+        qt.nj = 1; qt.Dj[0] = qt.Dtot; qt.accJm[0] = qt.accJ;
         fill_rys(qt, h);
         float best = 1e30f;
         for (int rep = 0; rep < 2; rep++) {
@@ -1369,17 +1371,100 @@ extern "C" int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const 
     return CF_OK;
 }
 
-// G_k = J[2 D_k] - exx K[D_k]  (GhfMultiple, Int4C2E.cpp:685-731): one J/K build per matrix for now
+// B[0] = max_k B[1+k] (block 1-norms and max-norms of the batch): the J accumulators of a multi-density build share one scale
+__global__ void rowmax_kernel(int n, int nmat, double* __restrict__ B, double* __restrict__ Bmax) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = 0.0, m = 0.0;
+    for (int k = 0; k < nmat; k++) { a = fmax(a, B[(size_t)(1 + k) * n + i]); m = fmax(m, Bmax[(size_t)(1 + k) * n + i]); }
+    B[i] = a; Bmax[i] = m;
+}
+// G = J - K on the pure matrices of one batch member
+__global__ void sub_kernel(size_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] - b[i];
+}
+
+// One batch (<= 3 densities, already in d_Dpure[0..nmat-1]) of the multi-density build: ONE pass over the integrals digests
+// J[D_k] and K[D_k] of every member (QuartetTask::nj / nk), accumulators [J_0..J_2 | K_0..K_2]; G_k -> d_out[k].
+static int build_g_batch(cf_handle* h, int nmat, double exx) {
+    const int ns = h->nshell, nbf = h->nbf, ncart = h->ncart;
+    const size_t n2c = (size_t)ncart * ncart, ns2 = (size_t)ns * ns, n2p = (size_t)nbf * nbf;
+    const int nk = exx > 0.0 ? nmat : 0;
+    cudaStream_t s = 0;
+    long long* acc = h->d_acc.p;
+    h->stats.n_launches_last = 0;
+    CUDA_TRY(cudaEventRecord(h->ev[0], s));
+    dim3 grid2(ns, ns);
+    for (int k = 0; k < nmat; k++)
+        pure_to_cart_kernel<<<grid2, 64, 0, s>>>(ns, nbf, ncart, h->d_Dpure[k].p, nullptr, nullptr, 1.0, 0.0, 0.0, h->d_ctrans.p, h->d_ct_off.p,
+                                                 h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[1 + k].p,
+                                                 h->d_B.p + (size_t)(1 + k) * ns2, h->d_Bmax.p + (size_t)(1 + k) * ns2);
+    rowmax_kernel<<<(int)((ns2 + 255) / 256), 256, 0, s>>>((int)ns2, nmat, h->d_B.p, h->d_Bmax.p);
+    bounds_kernel<<<1 + nmat, 1024, 0, s>>>(ns, h->d_QS.p, h->d_B.p, h->d_Bmax.p, h->d_rwork.p, h->d_partial.p);
+    scales_kernel<<<1, 32, 0, s>>>(h->d_partial.p, nmat, h->qmax_cart, h->opt.threshold, h->density_threshold, h->d_scales.p);
+    h->stats.n_launches_last += nmat + 3;
+    CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * 6 * n2c, s));
+    CUDA_TRY(cudaMemsetAsync(h->d_nq.p, 0, sizeof(unsigned long long) * CF_NQ_SLOTS, s));
+    CUDA_TRY(cudaEventRecord(h->ev[1], s));
+    CUDA_TRY(cudaEventRecord(h->ev_fork, s));
+    for (int i = 0; i < 3; i++) CUDA_TRY(cudaStreamWaitEvent(h->side[i], h->ev_fork, 0));
+    int it = 0;
+    for (ClassPairTask* t : h->tasks) {
+        QuartetTask qt{};
+        qt.rank = h->opt.rank; qt.world = h->opt.world_size;
+        qt.ncart = ncart; qt.nk = nk; qt.nj = nmat;
+        for (int x = 0; x < nmat; x++) {
+            qt.Dj[x] = h->d_Dcart[1 + x].p; qt.accJm[x] = acc + (size_t)x * n2c;
+            qt.Dk[x] = h->d_Dcart[1 + x].p; qt.accK[x] = acc + (size_t)(3 + x) * n2c;
+        }
+        qt.Dtot = qt.Dj[0]; qt.accJ = qt.accJm[0];
+        qt.scales = h->d_scales.p; qt.nq_done = h->d_nq.p;
+        qt.store = nullptr; qt.diag = 0; qt.prim_cut = 1e-22;
+        fill_rys(qt, h);
+        cudaStream_t ts = (it % 4 == 0) ? s : h->side[it % 4 - 1];
+        it++;
+        int rc = launch_task(h, t, qt, 0, ts);
+        if (rc != CF_OK) return rc;
+    }
+    for (int i = 0; i < 3; i++) { CUDA_TRY(cudaEventRecord(h->ev_join[i], h->side[i])); CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join[i], 0)); }
+    CUDA_TRY(cudaEventRecord(h->ev[2], s));
+    // G_k = J[2 D_k] - exx K[D_k] = 1/2 (rawJ + rawJ^T) - exx/8 (rawK + rawK^T)   (Int4C2E.cpp:726-728 with the J of D_k, not 2 D_k)
+    for (int k = 0; k < nmat; k++) {
+        finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, acc + (size_t)k * n2c, h->d_scales.p, 0, 0.5, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
+                                             h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, nk ? h->d_out[3].p : h->d_out[k].p);
+        h->stats.n_launches_last++;
+        if (nk) {
+            finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, acc + (size_t)(3 + k) * n2c, h->d_scales.p, 1, 0.125 * exx, h->d_ctrans.p, h->d_ct_off.p,
+                                                 h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dpure[k].p);   // D_k is consumed: reuse its buffer
+            sub_kernel<<<(int)((n2p + 255) / 256), 256, 0, s>>>(n2p, h->d_out[3].p, h->d_Dpure[k].p, h->d_out[k].p);
+            h->stats.n_launches_last += 2;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev[3], s));
+    return CF_OK;
+}
+
+// G_k = J[2 D_k] - exx K[D_k]  (GhfMultiple, Int4C2E.cpp:685-745): batches of three densities share one pass over the integrals
 extern "C" int cf_build_g_multi(cf_handle* h, int nbf, int nmat, const double* Ds, double exx, double* Gs) {
     if (!h || !Ds || !Gs || nmat <= 0) return CF_ERR_BAD_ARGUMENT;
     if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
-    const size_t n2 = (size_t)nbf * nbf;
-    std::vector<double> J(n2), K(n2);
-    for (int k = 0; k < nmat; k++) {
-        int rc = cf_build_jk(h, nbf, Ds + k * n2, nullptr, nullptr, exx, J.data(), K.data(), nullptr, nullptr);
+    cudaSetDevice(h->device);
+    const size_t n2 = (size_t)nbf * nbf, bytes = sizeof(double) * n2;
+    for (int k0 = 0; k0 < nmat; k0 += 3) {
+        const int nb = std::min(3, nmat - k0);
+        for (int k = 0; k < nb; k++) CUDA_TRY(cudaMemcpyAsync(h->d_Dpure[k].p, Ds + (size_t)(k0 + k) * n2, bytes, cudaMemcpyHostToDevice, 0));
+        int rc = build_g_batch(h, nb, exx);
         if (rc != CF_OK) return rc;
-        // ContractInts(Dd=D) returns J[2D] and exx*K[D]
-        for (size_t i = 0; i < n2; i++) Gs[k * n2 + i] = J[i] - K[i];
+        for (int k = 0; k < nb; k++) CUDA_TRY(cudaMemcpyAsync(Gs + (size_t)(k0 + k) * n2, h->d_out[k].p, bytes, cudaMemcpyDeviceToHost, 0));
+        CUDA_TRY(cudaMemcpyAsync(h->scales_host, h->d_scales.p, sizeof(h->scales_host), cudaMemcpyDeviceToHost, 0));
+        CUDA_TRY(cudaMemcpyAsync(h->nq_host, h->d_nq.p, sizeof(h->nq_host), cudaMemcpyDeviceToHost, 0));
+        CUDA_TRY(cudaStreamSynchronize(0));
+        CUDA_TRY(cudaGetLastError());
+        fetch_times(h);
+        rc = check_scales(h);
+        if (rc != CF_OK) return rc;
     }
     return CF_OK;
 }

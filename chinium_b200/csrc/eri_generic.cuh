@@ -282,6 +282,21 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
                     fixed_add(t.accJ + (size_t)(cdd + kl % ND) * ld + cc + kl / ND, s, scaleJ);
                 }
             }
+            for (int xj = 1; xj < t.nj; xj++) {   // further Coulomb densities of the multi-density build: D read from global memory
+                const double* DJ = t.Dj[xj];
+                long long* aJ = t.accJm[xj];
+                for (int e = lane; e < NAB + NCD; e += G) {
+                    double s = 0.0;
+                    if (e < NAB) {
+                        for (int kl = 0; kl < NCD; kl++) s = fma(V[e * NCD + kl], DJ[(size_t)(cdd + kl % ND) * ld + cc + kl / ND], s);
+                        fixed_add(aJ + (size_t)(cb + e % NB) * ld + ca + e / NB, s, scaleJ);
+                    } else {
+                        const int kl = e - NAB;
+                        for (int ij = 0; ij < NAB; ij++) s = fma(V[ij * NCD + kl], DJ[(size_t)(cb + ij % NB) * ld + ca + ij / NB], s);
+                        fixed_add(aJ + (size_t)(cdd + kl % ND) * ld + cc + kl / ND, s, scaleJ);
+                    }
+                }
+            }
             // K targets, per density: ac, ad, bc, bd
             for (int x = 0; x < t.nk; x++) {
                 const double* dac = Dx + x * NDX;

@@ -60,6 +60,7 @@ static cudaError_t launch_pair(const QuartetTask& t, int store, int grid, cudaSt
             // low contraction (digestion/atomics-bound): bra-loop kernel; high contraction (FP64-bound): the leaner
             // one-bra-pair-per-item kernel.  The engine decides per task (QuartetTask::braloop) and builds the matching items.
             if (!t.braloop) e = go(eri_jk_tpq<LA, LB, LC, LD>);
+            else if (t.nj > 1) e = go(eri_jk_tpqa<LA, LB, LC, LD, 3, 3>);      // multi-density build
             else if (t.nk <= 1) e = go(eri_jk_tpqa<LA, LB, LC, LD, 1>);
             else if (t.nk == 2) e = go(eri_jk_tpqa<LA, LB, LC, LD, 2>);
             else e = go(eri_jk_tpqa<LA, LB, LC, LD, 3>);

@@ -303,14 +303,16 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
         int cc0 = 0, cd0 = 0;
         if (active) { cc0 = t.ket.cao_a[ik]; cd0 = t.ket.cao_b[ik]; }
         const size_t ld = (size_t)t.ncart;
-        {   // J(a,b) += sum_cd V Dtot(c,d) ; J(c,d) += sum_ab V Dtot(a,b)
+        for (int xj = 0; xj < t.nj; xj++) {   // J(a,b) += sum_cd V Dj(c,d) ; J(c,d) += sum_ab V Dj(a,b)
+            const double* __restrict__ DJ = t.Dj[xj];
+            long long* aJ = t.accJm[xj];
             double dcd[NCD], jcd[NCD];
 #pragma unroll
-            for (int kl = 0; kl < NCD; kl++) { dcd[kl] = active ? t.Dtot[(cd0 + kl % ND) * ld + cc0 + kl / ND] : 0.0; jcd[kl] = 0.0; }
+            for (int kl = 0; kl < NCD; kl++) { dcd[kl] = active ? DJ[(cd0 + kl % ND) * ld + cc0 + kl / ND] : 0.0; jcd[kl] = 0.0; }
 #pragma unroll
             for (int ij = 0; ij < NAB; ij++) {
                 const size_t off = (cb + ij % NB) * ld + ca + ij / NB;
-                const double dab = t.Dtot[off];
+                const double dab = DJ[off];
                 double s = 0.0;
 #pragma unroll
                 for (int kl = 0; kl < NCD; kl++) {
@@ -319,11 +321,11 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
                 }
                 // the bra pair is common to the warp's 32 quartets: one add per element and warp instead of 32
                 s = warp_sum_fixed(s);
-                if (lane == 0) fixed_add(t.accJ + off, s, scaleJ);
+                if (lane == 0) fixed_add(aJ + off, s, scaleJ);
             }
             if (active) {
 #pragma unroll
-                for (int kl = 0; kl < NCD; kl++) fixed_add(t.accJ + (cd0 + kl % ND) * ld + cc0 + kl / ND, jcd[kl], scaleJ);
+                for (int kl = 0; kl < NCD; kl++) fixed_add(aJ + (cd0 + kl % ND) * ld + cc0 + kl / ND, jcd[kl], scaleJ);
             }
         }
         if (!active) continue;
@@ -660,16 +662,18 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                     }
             }
         };
-        {   // J(a,b) complete; J(c,d) partial over the owned a components
+        for (int xj = 0; xj < t.nj; xj++) {   // J(a,b) complete; J(c,d) partial over the owned a components
+            const double* __restrict__ DJ = t.Dj[xj];
+            long long* aJ = t.accJm[xj];
             double dcd[NCD], jcd[NCD];
 #pragma unroll
-            for (int kl = 0; kl < NCD; kl++) { dcd[kl] = active ? t.Dtot[(cd0 + kl % ND) * ld + cc0 + kl / ND] : 0.0; jcd[kl] = 0.0; }
+            for (int kl = 0; kl < NCD; kl++) { dcd[kl] = active ? DJ[(cd0 + kl % ND) * ld + cc0 + kl / ND] : 0.0; jcd[kl] = 0.0; }
 #pragma unroll
             for (int m = 0; m < MA; m++)
 #pragma unroll
                 for (int j = 0; j < NB; j++) {
                     const size_t off = (cb + j) * ld + ca + ia0 + m;
-                    const double dab = active ? t.Dtot[off] : 0.0;
+                    const double dab = active ? DJ[off] : 0.0;
                     double sum = 0.0;
 #pragma unroll
                     for (int kl = 0; kl < NCD; kl++) {
@@ -678,10 +682,10 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                     }
                     // the bra pair and the slice are warp-uniform: one add per element and warp
                     sum = warp_sum_fixed(sum);
-                    if ((threadIdx.x & 31) == 0) fixed_add(t.accJ + off, sum, scaleJ);
+                    if ((threadIdx.x & 31) == 0) fixed_add(aJ + off, sum, scaleJ);
                 }
             reduce_add(std::integral_constant<int, NCD>{}, jcd,
-                       [&](int kl) { return (size_t)(cd0 + kl % ND) * ld + cc0 + kl / ND; }, t.accJ, scaleJ);
+                       [&](int kl) { return (size_t)(cd0 + kl % ND) * ld + cc0 + kl / ND; }, aJ, scaleJ);
         }
         for (int x = 0; x < t.nk; x++) {
             const double* __restrict__ D = t.Dk[x];

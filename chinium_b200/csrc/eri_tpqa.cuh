@@ -46,8 +46,10 @@ __host__ __device__ constexpr int tpqa_minb(int nout, int nkmax) {
 #endif
 }
 
-template <int LA, int LB, int LC, int LD, int NKMAX>
-__global__ void __launch_bounds__(TPQ_THREADS, tpqa_minb(cf_ncart(LA) * cf_ncart(LB) * cf_ncart(LC) * cf_ncart(LD), NKMAX))
+// NKMAX / NJMAX: exchange / Coulomb densities the register accumulators are sized for (NJMAX = 3 only for the
+// multi-density build, Int4C2E.cpp:685-745)
+template <int LA, int LB, int LC, int LD, int NKMAX, int NJMAX = 1>
+__global__ void __launch_bounds__(TPQ_THREADS, tpqa_minb(cf_ncart(LA) * cf_ncart(LB) * cf_ncart(LC) * cf_ncart(LD), NKMAX * NJMAX))
 eri_jk_tpqa(const QuartetTask t) {
     constexpr int NA = cf_ncart(LA), NB = cf_ncart(LB), NC = cf_ncart(LC), ND = cf_ncart(LD);
     constexpr int NAB = NA * NB, NCD = NC * ND, NOUT = NAB * NCD;
@@ -141,9 +143,14 @@ eri_jk_tpqa(const QuartetTask t) {
         stage(ri0.w, min(MAXBP, ri0.y >> 16));
         __syncwarp();
 
-        double dcd[NCD], jcd[NCD];
+        double dcd[NJMAX * NCD], jcd[NJMAX * NCD];
 #pragma unroll
-        for (int kl = 0; kl < NCD; kl++) { dcd[kl] = lane_ok ? t.Dtot[(cd0 + kl % ND) * ld + cc0 + kl / ND] : 0.0; jcd[kl] = 0.0; }
+        for (int xj = 0; xj < NJMAX; xj++)
+#pragma unroll
+            for (int kl = 0; kl < NCD; kl++) {
+                dcd[xj * NCD + kl] = (lane_ok && xj < t.nj) ? t.Dj[xj][(cd0 + kl % ND) * ld + cc0 + kl / ND] : 0.0;
+                jcd[xj * NCD + kl] = 0.0;
+            }
         double kacc[NKACC];      // [x][ K(a,c): i*NC+k | K(a,d): NA*NC + i*ND+l ]
 #pragma unroll
         for (int e = 0; e < NKACC; e++) kacc[e] = 0.0;
@@ -259,17 +266,23 @@ eri_jk_tpqa(const QuartetTask t) {
 
             // ---- digestion of this bra pair (inactive lanes hold gout == 0 and only join the warp-wide J(a,b) sums)
 #pragma unroll
-            for (int ij = 0; ij < NAB; ij++) {
-                const size_t off = (cb + ij % NB) * ld + ca + ij / NB;
-                const double dab = t.Dtot[off];
-                double s = 0.0;
+            for (int xj = 0; xj < NJMAX; xj++) {
+                if (xj >= t.nj) break;
+                const double* __restrict__ DJ = t.Dj[xj];
+                long long* aJ = t.accJm[xj];
 #pragma unroll
-                for (int kl = 0; kl < NCD; kl++) {
-                    s = fma(gout[ij * NCD + kl], dcd[kl], s);
-                    jcd[kl] = fma(gout[ij * NCD + kl], dab, jcd[kl]);
+                for (int ij = 0; ij < NAB; ij++) {
+                    const size_t off = (cb + ij % NB) * ld + ca + ij / NB;
+                    const double dab = DJ[off];
+                    double s = 0.0;
+#pragma unroll
+                    for (int kl = 0; kl < NCD; kl++) {
+                        s = fma(gout[ij * NCD + kl], dcd[xj * NCD + kl], s);
+                        jcd[xj * NCD + kl] = fma(gout[ij * NCD + kl], dab, jcd[xj * NCD + kl]);
+                    }
+                    s = warp_sum_fixed(s);
+                    if (lane == 0) fixed_add(aJ + off, s, scaleJ);
                 }
-                s = warp_sum_fixed(s);
-                if (lane == 0) fixed_add(t.accJ + off, s, scaleJ);
             }
             if (!act) continue;
 #pragma unroll
@@ -357,7 +370,11 @@ eri_jk_tpqa(const QuartetTask t) {
         if (lane == 0 && t.nq_done) atomicAdd(t.nq_done + cf_nq_slot(), (unsigned long long)nact);
         if (lane_ok) {
 #pragma unroll
-            for (int kl = 0; kl < NCD; kl++) fixed_add(t.accJ + (cd0 + kl % ND) * ld + cc0 + kl / ND, jcd[kl], scaleJ);
+            for (int xj = 0; xj < NJMAX; xj++) {
+                if (xj >= t.nj) break;
+#pragma unroll
+                for (int kl = 0; kl < NCD; kl++) fixed_add(t.accJm[xj] + (cd0 + kl % ND) * ld + cc0 + kl / ND, jcd[xj * NCD + kl], scaleJ);
+            }
             if constexpr (ACCK) {
 #pragma unroll
                 for (int x = 0; x < NKMAX; x++) {

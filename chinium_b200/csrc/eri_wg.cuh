@@ -361,13 +361,15 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
         }
 
         // ---- digestion (warp-synchronous; the quartet's scratch is free now) -----------------------------------
-        {   // J(c,d) complete per lane; J(a,b) partial over the lanes of the group
+        for (int xj = 0; xj < t.nj; xj++) {   // J(c,d) complete per lane; J(a,b) partial over the lanes of the group
+            const double* __restrict__ DJ = t.Dj[xj];
+            long long* aJ = t.accJm[xj];
             double dcd[MK], jcd[MK];
 #pragma unroll
-            for (int m = 0; m < MK; m++) { dcd[m] = (active && fok[m]) ? t.Dtot[(cd0 + fid[m]) * ld + cc0 + fic[m]] : 0.0; jcd[m] = 0.0; }
+            for (int m = 0; m < MK; m++) { dcd[m] = (active && fok[m]) ? DJ[(cd0 + fid[m]) * ld + cc0 + fic[m]] : 0.0; jcd[m] = 0.0; }
 #pragma unroll
             for (int e = 0; e < NE; e++) {
-                const double dab = t.Dtot[(cb + e % NB) * ld + ca + IA0 + e / NB];
+                const double dab = DJ[(cb + e % NB) * ld + ca + IA0 + e / NB];
                 double pab = 0.0;
 #pragma unroll
                 for (int m = 0; m < MK; m++) { pab = fma(acc[m][e], dcd[m], pab); jcd[m] = fma(acc[m][e], dab, jcd[m]); }
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
             }
 #pragma unroll
             for (int m = 0; m < MK; m++)
-                if (active && fok[m]) fixed_add(t.accJ + (cd0 + fid[m]) * ld + cc0 + fic[m], jcd[m], scaleJ);
+                if (active && fok[m]) fixed_add(aJ + (cd0 + fid[m]) * ld + cc0 + fic[m], jcd[m], scaleJ);
             __syncwarp();
             // J(a,b) is common to every quartet of the item: sum over ALL active quartets of the warp (fixed order) and
             // issue one add per element and warp; lanes map to consecutive rows i, i.e. consecutive addresses
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
 #pragma unroll
                             for (int g2 = 0; g2 < GS; g2++) s += wq[(size_t)q2 * C::SCR + e * GS + g2];
                         }
-                    if (amask) fixed_add(t.accJ + (cb + j) * ld + ca + IA0 + i, s, scaleJ);
+                    if (amask) fixed_add(aJ + (cb + j) * ld + ca + IA0 + i, s, scaleJ);
                 }
             }
             __syncwarp();

@@ -213,15 +213,22 @@ def test_scf_energy_h2o_uhf_triplet(Int4C2E, oracle):
     assert abs(E_gpu - E_cpu) < 1e-8
 
 
-def test_multi_density(Int4C2E, oracle):
-    """ContractInts(std::vector<EigenMatrix>&) (Int4C2E.cpp:685-745): G_k = J[2 D_k] - EXX K[D_k]."""
-    mol, fb = load_fixture_molecule("h2o")
-    Ds = [H.random_symmetric_density(fb.nbf, s) for s in range(3)]
-    eng = _engine(Int4C2E, fb, exx=0.5)
+@pytest.mark.parametrize("name,nmat,exx", [("h2o", 3, 0.5), ("bo3h3", 4, 0.2), ("hf_tz", 2, 1.0), ("h2o", 5, 0.0)])
+def test_multi_density(Int4C2E, oracle, name, nmat, exx):
+    """ContractInts(std::vector<EigenMatrix>&) (Int4C2E.cpp:685-745): G_k = J[2 D_k] - EXX K[D_k].  Batches of three
+    densities share one pass over the integrals (QuartetTask::nj); 4 and 5 matrices exercise the 3+1 / 3+2 split,
+    EXX = 0 the Coulomb-only form."""
+    mol, fb = load_fixture_molecule(name)
+    Ds = [H.random_symmetric_density(fb.nbf, 30 + s) * (1.0 + s) for s in range(nmat)]
+    eng = _engine(Int4C2E, fb, exx=exx)
     Gs = eng.ContractInts(Ds, 1, 0)
+    assert len(Gs) == nmat
     for D, G in zip(Ds, Gs):
-        J, K, _, _, _ = oracle.direct_jk(fb, D, exx=0.5)
+        J, K, _, _, _ = oracle.direct_jk(fb, D, exx=exx)
         assert np.abs(G - (J - K)).max() < TOL
+        assert np.abs(G - G.T).max() == 0.0
+    st = eng.stats
+    assert st["quartets_evaluated_last"] == st["canonical_quartets"]      # one pass per batch, every quartet once
     eng.close()
 
 
