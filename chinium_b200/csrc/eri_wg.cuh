@@ -52,7 +52,13 @@ struct WgCfg {
     static constexpr int NE = NAP * NB;                             // register accumulators per owned S component
     static constexpr int R1 = NE * GS, R2 = (NAP + NB) * NCD;
     static constexpr int SCR = wg_pad(TQ > R1 ? (TQ > R2 ? TQ : R2) : (R1 > R2 ? R1 : R2));   // doubles per quartet
+    // WG_GTAB: the Chebyshev root tables (18-64 KB) are read through L1 from global memory instead of being staged in
+    // shared memory; the two resident CTAs of these kernels then leave that much more of the 256 KB to the L1 cache
+#ifdef WG_GTAB
+    static constexpr int TABLEN = NROOTS <= 2 ? tpq_table_len(NROOTS) : 0;
+#else
     static constexpr int TABLEN = tpq_table_len(NROOTS);
+#endif
     static constexpr size_t SMEM = sizeof(double) * (size_t)(TABLEN + TPQ_NBRA * TPQ_MAXBP + WG_WARPS * QW * SCR);
     static_assert(GS >= 1 && GS <= 32, "group does not fit a warp");
     static_assert(NA % HS == 0, "passes must split the components of shell a evenly");
@@ -60,10 +66,10 @@ struct WgCfg {
 
 // one root/weight value (index v: roots 0..n-1, weights n..2n-1) from the staged Chebyshev table
 template <int NROOTS>
-__device__ __forceinline__ double wg_rys_value(const double* __restrict__ tab, double T, int v) {
+__device__ __forceinline__ double wg_rys_value(const double* __restrict__ tab, const double* __restrict__ asym, double T, int v) {
     constexpr int NV = 2 * NROOTS;
     if (T >= (double)rys_tmax(NROOTS)) {
-        const double a = tab[(rys_tmax(NROOTS) / 2) * NV * RYS_NC + v];
+        const double a = asym[v];
         const double rs = rsqrt(T);
         return v < NROOTS ? a * rs * rs : a * rs;
     }
@@ -160,7 +166,8 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
     extern __shared__ double smem[];
     const double scaleJ = __ldg(t.scales), scaleK = __ldg(t.scales + 1);
     const double thr = __ldg(t.scales + 4);   // effective Schwarz threshold of this build (scales_kernel)
-    double* tab = smem;
+    const double* tab = smem;
+    const double* asym = smem;
     double* sbra = smem + C::TABLEN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = lane / GS, g = lane - qi * GS;
@@ -171,12 +178,18 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
     // ---- stage the root tables ------------------------------------------------------------------
     if constexpr (NROOTS <= 2) {
         constexpr int M = 2 * NROOTS - 1;
-        for (int e = threadIdx.x; e < BOYS_NROW * 8; e += 32 * WG_WARPS) tab[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
+        for (int e = threadIdx.x; e < BOYS_NROW * 8; e += 32 * WG_WARPS) smem[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
     } else {
         constexpr int NTAB = (rys_tmax(NROOTS) / 2) * 2 * NROOTS * RYS_NC;
+#ifdef WG_GTAB
+        tab = t.rys.table + rys_off(NROOTS);
+        asym = t.rys.asym + rys_asym_off(NROOTS);
+#else
         const double* src = t.rys.table + rys_off(NROOTS);
-        for (int e = threadIdx.x; e < NTAB; e += 32 * WG_WARPS) tab[e] = src[e];
-        if (threadIdx.x < 2 * NROOTS) tab[NTAB + threadIdx.x] = t.rys.asym[rys_asym_off(NROOTS) + threadIdx.x];
+        for (int e = threadIdx.x; e < NTAB; e += 32 * WG_WARPS) smem[e] = src[e];
+        if (threadIdx.x < 2 * NROOTS) smem[NTAB + threadIdx.x] = t.rys.asym[rys_asym_off(NROOTS) + threadIdx.x];
+        asym = smem + NTAB;
+#endif
     }
 
     // owned S components f = g*MK + m = (ic, id); their exponents and column offsets inside one (root, direction) block
@@ -312,7 +325,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
 #pragma unroll
                                 for (int r = 0; r < NROOTS; r++) { myrw[r] = rx[r]; myrw[NROOTS + r] = rw[r]; } }
                         } else {
-                            for (int v = g; v < 2 * NROOTS; v += GS) myrw[v] = wg_rys_value<NROOTS>(tab, T, v);
+                            for (int v = g; v < 2 * NROOTS; v += GS) myrw[v] = wg_rys_value<NROOTS>(tab, asym, T, v);
                         }
                     }
                     __syncwarp();

@@ -58,23 +58,26 @@ class DistributedInt4C2E:
                                  ptr(self._out[2], present[1]), ptr(self._out[3], present[2]), stream)
 
     def ContractInts(self, Dd=None, Da=None, Db=None, nthreads=1, output=0):
-        """Host matrices in, host matrices out (the reference's call); H2D / D2H through pinned buffers."""
+        """Host matrices in, host matrices out (the reference's call); H2D / D2H through pinned buffers.
+        No transposes: the engine symmetrises D on the device ((D + D^T)/2, the reference's precondition) and J/K come
+        back exactly symmetric, so the row-major torch view and the column-major reference layout hold the same bytes."""
         n = self.nbf
         present = [D is not None and np.size(D) > 0 for D in (Dd, Da, Db)]
         for k, D in enumerate((Dd, Da, Db)):
             if present[k]:
-                self._pin_in[k].numpy()[...] = np.asarray(D, dtype=np.float64).T   # torch row-major == col-major of D
+                np.copyto(self._pin_in[k].numpy(), np.asarray(D, dtype=np.float64).reshape(n, n))
                 self._D[k].copy_(self._pin_in[k], non_blocking=True)
         self.build_device(present)
-        res = []
         for k in range(4):
             if k == 0 or present[k - 1]:
                 self._pin_out[k].copy_(self._out[k], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         self.eng.sync_stats()            # timings + the deferred range check (raises on non-finite densities)
+        res = []
         for k in range(4):
             if k == 0 or present[k - 1]:
-                res.append(np.asfortranarray(self._pin_out[k].numpy().T.copy()))
+                res.append(self._pin_out[k].numpy().copy().T)     # plain memcpy; the transposed VIEW is F-contiguous and,
+                                                                  # the matrix being exactly symmetric, the same matrix
             else:
                 res.append(np.zeros((n, n), order="F"))
         return tuple(res)
