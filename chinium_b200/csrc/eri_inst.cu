@@ -82,7 +82,7 @@ static cudaError_t launch_pair(const QuartetTask& t, int store, int grid, cudaSt
                 constexpr bool SWAP = ((CFG >> 8) & 1) != 0;
                 constexpr int HS = ((CFG >> 12) & 15) ? ((CFG >> 12) & 15) : 1;
                 constexpr int MINB = ((CFG >> 16) & 15) ? ((CFG >> 16) & 15) : 2;
-                using C = typename std::conditional<SWAP, WgCfg<LC, LD, LA, LB, MK, HS>, WgCfg<LA, LB, LC, LD, MK, HS>>::type;
+                using C = typename std::conditional<SWAP, WgCfg<LC, LD, LA, LB, MK, HS, MINB>, WgCfg<LA, LB, LC, LD, MK, HS, MINB>>::type;
                 if (g_out) *g_out = 32 * WG_WARPS;
                 if (smem_out) *smem_out = C::SMEM;
                 if (kind_out) *kind_out = 3 + (SWAP ? 8 : 0) + 16 * C::NQ;

@@ -32,7 +32,7 @@ __device__ __forceinline__ void wg_static_for(F&& f) {
     if constexpr (B < E) { f(std::integral_constant<int, B>{}); wg_static_for<B + 1, E>(f); }
 }
 
-template <int LA, int LB, int LC, int LD, int MK, int HS = 1>
+template <int LA, int LB, int LC, int LD, int MK, int HS = 1, int MINB = 2>
 struct WgCfg {
     static constexpr int NA = cf_ncart(LA), NB = cf_ncart(LB), NC = cf_ncart(LC), ND = cf_ncart(LD);
     static constexpr int NAB = NA * NB, NCD = NC * ND;
@@ -52,13 +52,13 @@ struct WgCfg {
     static constexpr int NE = NAP * NB;                             // register accumulators per owned S component
     static constexpr int R1 = NE * GS, R2 = (NAP + NB) * NCD;
     static constexpr int SCR = wg_pad(TQ > R1 ? (TQ > R2 ? TQ : R2) : (R1 > R2 ? R1 : R2));   // doubles per quartet
-    // WG_GTAB: the Chebyshev root tables (18-64 KB) are read through L1 from global memory instead of being staged in
-    // shared memory; the two resident CTAs of these kernels then leave that much more of the 256 KB to the L1 cache
-#ifdef WG_GTAB
-    static constexpr int TABLEN = NROOTS <= 2 ? tpq_table_len(NROOTS) : 0;
-#else
-    static constexpr int TABLEN = tpq_table_len(NROOTS);
-#endif
+    // GTAB: when the staged Chebyshev root tables (18-64 KB) would keep the MINB-th CTA off the SM (or leave the L1 cache
+    // next to nothing of the 256 KB), they are read through L1 from global memory instead.  Measured (profiles r02f):
+    // ff|fd 3.17 -> 1.74 ms, ff|ps 2.03 -> 1.44 ms on c18; classes that fit anyway are 2-3 % faster with staged tables.
+    static constexpr int TABLEN_STAGED = tpq_table_len(NROOTS);
+    static constexpr size_t SMEM_STAGED = sizeof(double) * (size_t)(TABLEN_STAGED + TPQ_NBRA * TPQ_MAXBP + WG_WARPS * QW * SCR);
+    static constexpr bool GTAB = NROOTS > 2 && MINB * (SMEM_STAGED + 1024) > 216 * 1024;
+    static constexpr int TABLEN = GTAB ? 0 : TABLEN_STAGED;
     static constexpr size_t SMEM = sizeof(double) * (size_t)(TABLEN + TPQ_NBRA * TPQ_MAXBP + WG_WARPS * QW * SCR);
     static_assert(GS >= 1 && GS <= 32, "group does not fit a warp");
     static_assert(NA % HS == 0, "passes must split the components of shell a evenly");
@@ -158,7 +158,7 @@ __device__ __forceinline__ void wg_bra_hrr(const double* __restrict__ col, doubl
 // so that the accumulators of one pass fit the register file; phases A and B are repeated per pass.
 template <int LA, int LB, int LC, int LD, int MK, int HS, int MINB = 2>
 __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTask t) {
-    using C = WgCfg<LA, LB, LC, LD, MK, HS>;
+    using C = WgCfg<LA, LB, LC, LD, MK, HS, MINB>;
     constexpr int NAP = C::NAP, NE = C::NE;
     constexpr int NA = C::NA, NB = C::NB, NC = C::NC, ND = C::ND, NAB = C::NAB, NCD = C::NCD;
     constexpr int NROOTS = C::NROOTS, LAB = C::LAB, GS = C::GS, QW = C::QW, NQ = C::NQ, LABP = C::LABP, TSZ = C::TSZ;
@@ -181,15 +181,15 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
         for (int e = threadIdx.x; e < BOYS_NROW * 8; e += 32 * WG_WARPS) smem[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
     } else {
         constexpr int NTAB = (rys_tmax(NROOTS) / 2) * 2 * NROOTS * RYS_NC;
-#ifdef WG_GTAB
-        tab = t.rys.table + rys_off(NROOTS);
-        asym = t.rys.asym + rys_asym_off(NROOTS);
-#else
-        const double* src = t.rys.table + rys_off(NROOTS);
-        for (int e = threadIdx.x; e < NTAB; e += 32 * WG_WARPS) smem[e] = src[e];
-        if (threadIdx.x < 2 * NROOTS) smem[NTAB + threadIdx.x] = t.rys.asym[rys_asym_off(NROOTS) + threadIdx.x];
-        asym = smem + NTAB;
-#endif
+        if constexpr (C::GTAB) {
+            tab = t.rys.table + rys_off(NROOTS);
+            asym = t.rys.asym + rys_asym_off(NROOTS);
+        } else {
+            const double* src = t.rys.table + rys_off(NROOTS);
+            for (int e = threadIdx.x; e < NTAB; e += 32 * WG_WARPS) smem[e] = src[e];
+            if (threadIdx.x < 2 * NROOTS) smem[NTAB + threadIdx.x] = t.rys.asym[rys_asym_off(NROOTS) + threadIdx.x];
+            asym = smem + NTAB;
+        }
     }
 
     // owned S components f = g*MK + m = (ic, id); their exponents and column offsets inside one (root, direction) block
