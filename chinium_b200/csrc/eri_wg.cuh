@@ -531,6 +531,10 @@ __host__ __device__ constexpr int wg_cfg_base(int key) {
         case 96: return 1 | (2 << 12);          // ff|fs
         case 97: return 4 | 256 | (2 << 12);    // ff|fp  (H = fp, two passes)
         case 98: return 2 | (5 << 12);          // ff|fd  five passes of 2 a-components
+        case 99: return 4 | (10 << 12);         // ff|ff  ten passes of 1 a-component (was the generic CTA-per-quartet kernel)
+        case 71: return 1;                      // fp|ps  (measured against the sliced thread-per-quartet kernel: 4.63 -> 3.86 ms on c18)
+        case 51: return 1;                      // dd|ps  (2.49 -> 2.31 ms)
+        case 66: return 1;                      // fs|fs  (1.89 -> 1.48 ms); pp|pp, fs|pp and dp|ds stay with the sliced kernels (slower here)
         default: return 0;
     }
 }
