@@ -1350,7 +1350,10 @@ extern "C" int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const 
         long long chunk = t->nquartet / ((long long)max_grid * 4 * std::max(1, gt.world));
         chunk = std::max(1LL, std::min(64LL, chunk));
         gt.chunk = (int)chunk;
-        const long long nchunk_total = (t->nquartet + chunk - 1) / chunk;
+        int G = 0;
+        g_grad_launch[t->bra](t->ket, gt, 0, 0, &G, nullptr);       // query: G < 0 = thread-per-quartet kernel, |G| quartets per CTA block
+        const long long per = G < 0 ? -G : chunk;
+        const long long nchunk_total = (t->nquartet + per - 1) / per;
         const long long nchunk_local = (nchunk_total - gt.rank + gt.world - 1) / gt.world;
         if (nchunk_local <= 0) continue;
         const int grid = (int)std::min<long long>(nchunk_local, max_grid);

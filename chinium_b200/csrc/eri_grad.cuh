@@ -15,6 +15,7 @@
 #pragma once
 #include "cf_common.cuh"
 #include "eri_generic.cuh"
+#include "eri_tpq.cuh"
 
 struct GradTask {
     PairClassDev bra, ket;
@@ -197,5 +198,157 @@ __global__ void __launch_bounds__(G) eri_grad_generic(const GradTask t) {
                 }
             }
         }
+    }
+}
+
+// ================================================================================================
+// Thread-per-quartet gradient kernel for the smallest classes (<= 9 Cartesian components, raised 2-D tables of <= 36
+// entries): the CTA-per-quartet kernel above spends three barriers per primitive quartet with most lanes idle there
+// (bo3h3: ps|ss and ss|ss were 50 % of the gradient).  Here every thread owns one shell quartet of the same (ib, ik)
+// enumeration, keeps the raised tables of one root in registers and accumulates its 12 scalars; the lanes of a warp then
+// add them one after the other (fixed order) into the warp's shared-memory row, and the rows go to the CTA's private
+// global row at the end -- still no floating-point atomics, still bit-repeatable for a given launch geometry.
+// ================================================================================================
+#define GRAD_TPQ_THREADS 128
+__host__ __device__ constexpr bool grad_tpq_ok(int la, int lb, int lc, int ld) {
+    return cf_ncart(la) * cf_ncart(lb) * cf_ncart(lc) * cf_ncart(ld) <= 9 && (la + 2) * (lb + 2) * (lc + 2) * (ld + 2) <= 36;
+}
+
+template <int LA, int LB, int LC, int LD>
+__global__ void __launch_bounds__(GRAD_TPQ_THREADS) eri_grad_tpq(const GradTask t) {
+    constexpr int NA = cf_ncart(LA), NB = cf_ncart(LB), NC = cf_ncart(LC), ND = cf_ncart(LD);
+    constexpr int NOUT = NA * NB * NC * ND;
+    constexpr int NR = (LA + LB + LC + LD + 1) / 2 + 1;
+    constexpr int GSZ2 = (LA + 2) * (LB + 2) * (LC + 2) * (LD + 2);
+    constexpr int SA = (LB + 2) * (LC + 2) * (LD + 2), SB = (LC + 2) * (LD + 2), SC = (LD + 2);
+    static_assert(NR <= 2, "roots from the Boys function (closed-form 1- and 2-point rules)");
+    extern __shared__ double smem[];
+    double* tab = smem;                                       // Boys rows, as in eri_tpq.cuh
+    double* rows = smem + BOYS_NROW * 8;                      // [warps][ngrad]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* myrow = rows + (size_t)warp * t.ngrad;
+    {
+        constexpr int M = 2 * NR - 1;
+        for (int e = threadIdx.x; e < BOYS_NROW * 8; e += GRAD_TPQ_THREADS) tab[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
+        for (int e = threadIdx.x; e < (GRAD_TPQ_THREADS / 32) * t.ngrad; e += GRAD_TPQ_THREADS) rows[e] = 0.0;
+    }
+    __syncthreads();
+    const size_t ld = (size_t)t.ncart;
+    const long long nblk_total = (t.nquartet + GRAD_TPQ_THREADS - 1) / GRAD_TPQ_THREADS;
+    const long long nblk_local = (nblk_total - t.rank + t.world - 1) / t.world;
+    for (long long lb_ = blockIdx.x; lb_ < nblk_local; lb_ += gridDim.x) {
+        const long long q = (lb_ * t.world + t.rank) * GRAD_TPQ_THREADS + threadIdx.x;
+        bool act = q < t.nquartet;
+        int ib = 0, ik = 0;
+        if (act) {
+            int lo = 0, hi = t.bra.npair;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (t.qoff[mid] <= q) lo = mid; else hi = mid;
+            }
+            ib = lo; ik = (int)(q - t.qoff[ib]);
+            if (t.thr > 0.0 && !(t.bra.Q[ib] * t.ket.Q[ik] > t.thr)) act = false;
+        }
+        double acc[9];
+#pragma unroll
+        for (int e = 0; e < 9; e++) acc[e] = 0.0;
+        int atA = 0, atB = 0, atC = 0, atD = 0;
+        if (act) {
+            const int sa = t.bra.sa[ib], sb = t.bra.sb[ib], sc = t.ket.sa[ik], sd = t.ket.sb[ik];
+            atA = t.shell2atom[sa]; atB = t.shell2atom[sb]; atC = t.shell2atom[sc]; atD = t.shell2atom[sd];
+            const double Ax = t.bra.A[3 * ib], Ay = t.bra.A[3 * ib + 1], Az = t.bra.A[3 * ib + 2];
+            const double ABx = t.bra.AB[3 * ib], ABy = t.bra.AB[3 * ib + 1], ABz = t.bra.AB[3 * ib + 2];
+            const double Cx = t.ket.A[3 * ik], Cy = t.ket.A[3 * ik + 1], Cz = t.ket.A[3 * ik + 2];
+            const double CDx = t.ket.AB[3 * ik], CDy = t.ket.AB[3 * ik + 1], CDz = t.ket.AB[3 * ik + 2];
+            const int pab0 = t.bra.pbase[ib], npab = t.bra.nprim[ib];
+            const int pcd0 = t.ket.pbase[ik], npcd = t.ket.nprim[ik];
+            double wgt = (sa == sb ? 1.0 : 2.0) * (sc == sd ? 1.0 : 2.0);
+            wgt *= (t.same_class && ib == ik) ? 1.0 : 2.0;
+            const int ca = t.bra.cao_a[ib], cb = t.bra.cao_b[ib], cc = t.ket.cao_a[ik], cdd = t.ket.cao_b[ik];
+            double gam[NOUT];
+#pragma unroll
+            for (int n = 0; n < NOUT; n++) {
+                const int a = ca + n / (ND * NC * NB), b = cb + (n / (ND * NC)) % NB, c = cc + (n / ND) % NC, d = cdd + n % ND;
+                double v = t.D1[b * ld + a] * t.D2[d * ld + c] + t.D1[d * ld + c] * t.D2[b * ld + a];
+                if (t.exx > 0.0)
+                    v -= 0.25 * t.exx * (t.D1[c * ld + a] * t.D2[d * ld + b] + t.D1[c * ld + b] * t.D2[d * ld + a] +
+                                         t.D1[d * ld + a] * t.D2[c * ld + b] + t.D1[d * ld + b] * t.D2[c * ld + a]);
+                gam[n] = v * wgt;
+            }
+            for (int iab = 0; iab < npab; iab++) {
+                const int sab = pab0 + iab * CF_PSTRIDE;
+                const double p = t.bra.p[sab], cab = t.bra.c[sab], hp = t.bra.hp[sab];
+                const double Px = t.bra.Px[sab], Py = t.bra.Py[sab], Pz = t.bra.Pz[sab];
+                const double ta = 2.0 * t.bra_aexp[sab], tb = 2.0 * p - ta;
+                for (int icd = 0; icd < npcd; icd++) {
+                    const int scd = pcd0 + icd * CF_PSTRIDE;
+                    const double cc_ = cab * t.ket.c[scd];
+                    if (fabs(cc_) < t.prim_cut) continue;
+                    const double qe = t.ket.p[scd], hq = t.ket.hp[scd];
+                    const double Qx = t.ket.Px[scd], Qy = t.ket.Py[scd], Qz = t.ket.Pz[scd];
+                    const double tc = 2.0 * t.ket_aexp[scd];
+                    const double pq = p + qe;
+                    const double rs = rsqrt(pq), ipq = rs * rs;
+                    const double PQx = Px - Qx, PQy = Py - Qy, PQz = Pz - Qz;
+                    const double T = (p * qe * ipq) * fma(PQx, PQx, fma(PQy, PQy, PQz * PQz));
+                    double rx[NR], rw[NR];
+                    tpq_roots<NR>(tab, T, rx, rw);
+                    const double qi = qe * ipq, pi_ = p * ipq, hi = 0.5 * ipq;
+#pragma unroll
+                    for (int r = 0; r < NR; r++) {
+                        const double xr = rx[r];
+                        const double rxp = xr * qi, rxq = xr * pi_, b00 = xr * hi;
+                        const double b10 = fma(-rxp, hp, hp), b01 = fma(-rxq, hq, hq);
+                        double g3[3][GSZ2];
+                        rys_2d<LA + 1, LB + 1, LC + 1, LD + 1>(1.0, fma(-rxp, PQx, Px - Ax), fma(rxq, PQx, Qx - Cx), b10, b01, b00, ABx, CDx, g3[0]);
+                        rys_2d<LA + 1, LB + 1, LC + 1, LD + 1>(1.0, fma(-rxp, PQy, Py - Ay), fma(rxq, PQy, Qy - Cy), b10, b01, b00, ABy, CDy, g3[1]);
+                        rys_2d<LA + 1, LB + 1, LC + 1, LD + 1>(rw[r] * cc_ * rs, fma(-rxp, PQz, Pz - Az), fma(rxq, PQz, Qz - Cz), b10, b01, b00, ABz, CDz, g3[2]);
+#pragma unroll
+                        for (int n = 0; n < NOUT; n++) {
+                            const int id = n % ND, ic = (n / ND) % NC, jb = (n / (ND * NC)) % NB, ia = n / (ND * NC * NB);
+                            const int ea[3] = {cart_lx(LA, ia), cart_ly(LA, ia), cart_lz(LA, ia)};
+                            const int eb[3] = {cart_lx(LB, jb), cart_ly(LB, jb), cart_lz(LB, jb)};
+                            const int ec[3] = {cart_lx(LC, ic), cart_ly(LC, ic), cart_lz(LC, ic)};
+                            const int ed[3] = {cart_lx(LD, id), cart_ly(LD, id), cart_lz(LD, id)};
+                            double f[3], dA[3], dB[3], dC[3];
+#pragma unroll
+                            for (int d = 0; d < 3; d++) {
+                                const int i0 = ea[d] * SA + eb[d] * SB + ec[d] * SC + ed[d];
+                                f[d] = g3[d][i0];
+                                dA[d] = ta * g3[d][i0 + SA]; if (ea[d] > 0) dA[d] -= ea[d] * g3[d][i0 - SA];
+                                dB[d] = tb * g3[d][i0 + SB]; if (eb[d] > 0) dB[d] -= eb[d] * g3[d][i0 - SB];
+                                dC[d] = tc * g3[d][i0 + SC]; if (ec[d] > 0) dC[d] -= ec[d] * g3[d][i0 - SC];
+                            }
+                            const double fyz = f[1] * f[2] * gam[n], fxz = f[0] * f[2] * gam[n], fxy = f[0] * f[1] * gam[n];
+                            acc[0] = fma(dA[0], fyz, acc[0]); acc[1] = fma(dA[1], fxz, acc[1]); acc[2] = fma(dA[2], fxy, acc[2]);
+                            acc[3] = fma(dB[0], fyz, acc[3]); acc[4] = fma(dB[1], fxz, acc[4]); acc[5] = fma(dB[2], fxy, acc[5]);
+                            acc[6] = fma(dC[0], fyz, acc[6]); acc[7] = fma(dC[1], fxz, acc[7]); acc[8] = fma(dC[2], fxy, acc[8]);
+                        }
+                    }
+                }
+            }
+        }
+        // lanes add one after the other (fixed order) into the warp's row
+        const unsigned amask = __ballot_sync(0xffffffffu, act);
+        for (unsigned rest = amask; rest; rest &= rest - 1) {
+            const int l = __ffs(rest) - 1;
+            if (lane == l) {
+#pragma unroll
+                for (int x = 0; x < 3; x++) {
+                    myrow[3 * atA + x] += acc[x];
+                    myrow[3 * atB + x] += acc[3 + x];
+                    myrow[3 * atC + x] += acc[6 + x];
+                    myrow[3 * atD + x] -= acc[x] + acc[3 + x] + acc[6 + x];
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double* grow = t.gpart + (size_t)blockIdx.x * t.ngrad;
+    for (int j = threadIdx.x; j < t.ngrad; j += GRAD_TPQ_THREADS) {
+        double s = 0.0;
+        for (int w = 0; w < GRAD_TPQ_THREADS / 32; w++) s += rows[(size_t)w * t.ngrad + j];
+        grow[j] += s;
     }
 }

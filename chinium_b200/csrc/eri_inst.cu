@@ -157,6 +157,19 @@ template <int BRA, int KET>
 static cudaError_t launch_grad_pair(const GradTask& t, int grid, cudaStream_t s, int* g_out, size_t* smem_out) {
     constexpr int LA = ClassL<BRA>::a, LB = ClassL<BRA>::b, LC = ClassL<KET>::a, LD = ClassL<KET>::b;
     constexpr int NOUT = cf_ncart(LA) * cf_ncart(LB) * cf_ncart(LC) * cf_ncart(LD);
+    if constexpr (grad_tpq_ok(LA, LB, LC, LD)) {
+        // smallest classes: thread per quartet, per-warp shared-memory rows of the gradient (needs 4 * ngrad doubles)
+        const size_t smem_t = sizeof(double) * (size_t)(BOYS_NROW * 8 + (GRAD_TPQ_THREADS / 32) * t.ngrad);
+        if (smem_t <= 96 * 1024) {
+            if (g_out) *g_out = -GRAD_TPQ_THREADS;          // negative: quartets per CTA block, thread-per-quartet enumeration
+            if (smem_out) *smem_out = smem_t;
+            if (grid <= 0) return cudaSuccess;
+            auto k = eri_grad_tpq<LA, LB, LC, LD>;
+            if (smem_t > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t); if (e != cudaSuccess) return e; }
+            k<<<grid, GRAD_TPQ_THREADS, smem_t, s>>>(t);
+            return cudaGetLastError();
+        }
+    }
     constexpr int G = group_size(NOUT) < 64 ? 64 : group_size(NOUT);
     const size_t smem = eri_grad_smem<LA, LB, LC, LD>(G);
     if (g_out) *g_out = G;
