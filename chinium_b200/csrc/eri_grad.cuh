@@ -202,16 +202,26 @@ __global__ void __launch_bounds__(G) eri_grad_generic(const GradTask t) {
 }
 
 // ================================================================================================
-// Thread-per-quartet gradient kernel for the smallest classes (<= 9 Cartesian components, raised 2-D tables of <= 36
-// entries): the CTA-per-quartet kernel above spends three barriers per primitive quartet with most lanes idle there
-// (bo3h3: ps|ss and ss|ss were 50 % of the gradient).  Here every thread owns one shell quartet of the same (ib, ik)
+// Thread-per-quartet gradient kernel for the small and medium classes (<= 108 Cartesian components, raised 2-D tables of
+// <= 100 entries, <= 4 roots): the CTA-per-quartet kernel above spends three barriers per primitive quartet with most
+// lanes idle there (bo3h3: ps|ss and ss|ss were 50 % of the gradient).  The larger of these classes spill their tables to
+// local memory and still win when the task has enough quartets to fill the machine (c18 3.97 -> 1.21 s); tasks with few
+// quartets of a larger class stay with the CTA-per-quartet kernel (launch_grad_pair in eri_inst.cu).  Here every thread owns one shell quartet of the same (ib, ik)
 // enumeration, keeps the raised tables of one root in registers and accumulates its 12 scalars; the lanes of a warp then
 // add them one after the other (fixed order) into the warp's shared-memory row, and the rows go to the CTA's private
 // global row at the end -- still no floating-point atomics, still bit-repeatable for a given launch geometry.
 // ================================================================================================
 #define GRAD_TPQ_THREADS 128
 __host__ __device__ constexpr bool grad_tpq_ok(int la, int lb, int lc, int ld) {
-    return cf_ncart(la) * cf_ncart(lb) * cf_ncart(lc) * cf_ncart(ld) <= 9 && (la + 2) * (lb + 2) * (lc + 2) * (ld + 2) <= 36;
+#ifndef GRAD_TPQ_MAXOUT
+#define GRAD_TPQ_MAXOUT 108
+#define GRAD_TPQ_MAXTAB 100
+#endif
+#ifndef GRAD_TPQ_MAXNR
+#define GRAD_TPQ_MAXNR 4
+#endif
+    return cf_ncart(la) * cf_ncart(lb) * cf_ncart(lc) * cf_ncart(ld) <= GRAD_TPQ_MAXOUT &&
+           (la + 2) * (lb + 2) * (lc + 2) * (ld + 2) <= GRAD_TPQ_MAXTAB && (la + lb + lc + ld + 1) / 2 + 1 <= GRAD_TPQ_MAXNR;
 }
 
 template <int LA, int LB, int LC, int LD>
@@ -221,17 +231,22 @@ __global__ void __launch_bounds__(GRAD_TPQ_THREADS) eri_grad_tpq(const GradTask 
     constexpr int NR = (LA + LB + LC + LD + 1) / 2 + 1;
     constexpr int GSZ2 = (LA + 2) * (LB + 2) * (LC + 2) * (LD + 2);
     constexpr int SA = (LB + 2) * (LC + 2) * (LD + 2), SB = (LC + 2) * (LD + 2), SC = (LD + 2);
-    static_assert(NR <= 2, "roots from the Boys function (closed-form 1- and 2-point rules)");
+    constexpr int TABLEN = tpq_table_len(NR);
     extern __shared__ double smem[];
-    double* tab = smem;                                       // Boys rows, as in eri_tpq.cuh
-    double* rows = smem + BOYS_NROW * 8;                      // [warps][ngrad]
+    double* tab = smem;                                       // Boys rows (1-2 roots) or Chebyshev tables, as in eri_tpq.cuh
+    double* rows = smem + TABLEN;                             // [warps][ngrad]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* myrow = rows + (size_t)warp * t.ngrad;
-    {
+    if constexpr (NR <= 2) {
         constexpr int M = 2 * NR - 1;
         for (int e = threadIdx.x; e < BOYS_NROW * 8; e += GRAD_TPQ_THREADS) tab[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
-        for (int e = threadIdx.x; e < (GRAD_TPQ_THREADS / 32) * t.ngrad; e += GRAD_TPQ_THREADS) rows[e] = 0.0;
+    } else {
+        constexpr int NT = (rys_tmax(NR) / 2) * 2 * NR * RYS_NC;
+        const double* src = t.rys.table + rys_off(NR);
+        for (int e = threadIdx.x; e < NT; e += GRAD_TPQ_THREADS) tab[e] = src[e];
+        if (threadIdx.x < 2 * NR) tab[NT + threadIdx.x] = t.rys.asym[rys_asym_off(NR) + threadIdx.x];
     }
+    for (int e = threadIdx.x; e < (GRAD_TPQ_THREADS / 32) * t.ngrad; e += GRAD_TPQ_THREADS) rows[e] = 0.0;
     __syncthreads();
     const size_t ld = (size_t)t.ncart;
     const long long nblk_total = (t.nquartet + GRAD_TPQ_THREADS - 1) / GRAD_TPQ_THREADS;

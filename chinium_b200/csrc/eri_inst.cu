@@ -158,9 +158,13 @@ static cudaError_t launch_grad_pair(const GradTask& t, int grid, cudaStream_t s,
     constexpr int LA = ClassL<BRA>::a, LB = ClassL<BRA>::b, LC = ClassL<KET>::a, LD = ClassL<KET>::b;
     constexpr int NOUT = cf_ncart(LA) * cf_ncart(LB) * cf_ncart(LC) * cf_ncart(LD);
     if constexpr (grad_tpq_ok(LA, LB, LC, LD)) {
-        // smallest classes: thread per quartet, per-warp shared-memory rows of the gradient (needs 4 * ngrad doubles)
-        const size_t smem_t = sizeof(double) * (size_t)(BOYS_NROW * 8 + (GRAD_TPQ_THREADS / 32) * t.ngrad);
-        if (smem_t <= 96 * 1024) {
+        // thread per quartet, per-warp shared-memory rows of the gradient (needs 4 * ngrad doubles); the larger classes only
+        // when the task has enough quartets to fill the machine (CF_GRAD_TPQ_MINQ: developer/test override)
+        constexpr int NRG = (LA + LB + LC + LD + 1) / 2 + 1;
+        const size_t smem_t = sizeof(double) * (size_t)(tpq_table_len(NRG) + (GRAD_TPQ_THREADS / 32) * t.ngrad);
+        static long long minq = -1;
+        if (minq < 0) { const char* e = getenv("CF_GRAD_TPQ_MINQ"); minq = e ? atoll(e) : 30000; }
+        if (smem_t <= 96 * 1024 && (NOUT <= 9 || t.nquartet >= minq)) {
             if (g_out) *g_out = -GRAD_TPQ_THREADS;          // negative: quartets per CTA block, thread-per-quartet enumeration
             if (smem_out) *smem_out = smem_t;
             if (grid <= 0) return cudaSuccess;

@@ -11,6 +11,7 @@ from chinium_b200.inputs import load_fixture_molecule
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -389,6 +390,39 @@ def test_contract_grads_parity(Int4C2E, oracle, name, exx):
     eng.EXX = 0.0
     assert np.abs(eng.ContractGrads(D2, D2, 0) - oracle.contract_grads(fb, D2, D2, 0.0)).max() < 1e-9 * max(1.0, np.abs(go).max())
     eng.close()
+
+
+@pytest.mark.parametrize("minq", ["0", "1000000000000"])
+def test_contract_grads_both_kernel_families(oracle, minq, tmp_path):
+    """Every class that has a thread-per-quartet gradient kernel also has the CTA-per-quartet one; which one runs
+    depends on the task's quartet count.  Force each family in turn (fresh process: the switch is read once) on a
+    molecule with s..f shells."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, os
+        sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+        import numpy as np
+        from chinium_b200 import Int4C2E
+        from chinium_b200.inputs import load_fixture_molecule
+        from oracle_lib import Oracle
+        import scf_harness as H
+        worst = 0.0
+        for name, exx in (("hf_tz", 0.7), ("bo3h3", 0.2)):
+            mol, fb = load_fixture_molecule(name)
+            n = fb.nbf
+            D1, D2 = H.random_symmetric_density(n, 41) * n, H.random_symmetric_density(n, 42) * n
+            eng = Int4C2E(fb, exx, -1.0)
+            g = eng.ContractGrads(D1, D2, 0)
+            go = Oracle().contract_grads(fb, D1, D2, exx)
+            worst = max(worst, float(np.abs(g - go).max() / max(1.0, np.abs(go).max())))
+            eng.close()
+        print("WORST", worst)
+    """ % (ROOT, ROOT))
+    env = dict(os.environ, CF_GRAD_TPQ_MINQ=minq)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float(r.stdout.strip().split("WORST")[-1])
+    assert worst < 1e-9, worst
 
 
 def test_contract_grads_partition_sum(Int4C2E, oracle):
