@@ -16,7 +16,9 @@
  *   - PARITY PIN: weak external pin only -- the RHF/cc-pVDZ energy of CH3ClF- recorded in
  *     tools/sn2/sn2.cnm.log:204 (reproduced by tests/test_oracle.py through this oracle to
  *     < 1e-7 Eh), plus first-principles checks (Boys vs mpmath, permutational symmetry,
- *     diag(S)=1, brute-force einsum).  The device kernels use a DIFFERENT algorithm (Rys
+ *     diag(S)=1, brute-force einsum); for the derivative path the forces recorded in the same
+ *     log (:211-216), reproduced to < 7e-6 Eh/bohr (tests/test_oracle.py::test_sn2_recorded_forces).
+ *     The device kernels use a DIFFERENT algorithm (Rys
  *     quadrature), so oracle == device agreement is a two-route check.
  */
 #include <math.h>

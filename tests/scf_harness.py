@@ -133,6 +133,47 @@ def uhf(S, Hcore, na, nb, jk, e_nuc=0.0, D0=None, max_iter=200, tol=1e-8, diis_s
     raise RuntimeError("Convergence failed!")
 
 
+def rhf_total_gradient(oracle, fb, mol, D, F, S, nocc, g2e, h=1e-4):
+    """Total RHF nuclear gradient around the 2e contraction under test, assembled like Restricted/Grad.cpp:60-70:
+    Gradient = 2 D o dT + 2 D o dV - 2 W o dS + ContractGrads(D, D) + dE_nuc, W = C_occ eps C_occ^T (energy-weighted
+    density).  The one-electron derivative integrals (Int2C1E in the reference, outside this engine's scope) are taken by
+    central differences of the oracle's S/T/V with the atom's basis functions AND its nucleus displaced."""
+    import copy
+    from scipy.linalg import eigh as _eigh
+    eps, C_ = _eigh(F, S)
+    W = (C_[:, :nocc] * eps[:nocc]) @ C_[:, :nocc].T
+    s2a = np.asarray(fb.shell2atom)
+    natom = len(mol.Z)
+    g = np.zeros((natom, 3))
+
+    def displaced(atom, x, d):
+        fb2 = copy.deepcopy(fb)
+        c = np.array(fb2.center_xyz, dtype=np.float64).reshape(-1, 3).copy()
+        c[s2a == atom, x] += d
+        fb2.center_xyz = c.reshape(np.shape(fb.center_xyz))
+        xyz = np.array(mol.xyz_bohr, dtype=np.float64).copy()
+        xyz[atom, x] += d
+        return fb2, xyz
+
+    for a in range(natom):
+        for x in range(3):
+            fp, xp = displaced(a, x, h)
+            fm, xm = displaced(a, x, -h)
+            Sp, Tp, Vp = oracle.one_electron(fp, mol.Z, xp)
+            Sm, Tm, Vm = oracle.one_electron(fm, mol.Z, xm)
+            dH = ((Tp + Vp) - (Tm + Vm)) / (2 * h)
+            dS = (Sp - Sm) / (2 * h)
+            dEn = (nuclear_repulsion(mol.Z, xp) - nuclear_repulsion(mol.Z, xm)) / (2 * h)
+            g[a, x] = 2 * np.sum(D * dH) - 2 * np.sum(W * dS) + g2e[3 * a + x] + dEn
+    return g
+
+
+# forces (= -gradient, Hartree/bohr) Chinium recorded for CH3ClF- RHF/cc-pVDZ: tools/sn2/sn2.cnm.log:211-216
+SN2_FORCES_LOG = np.array([[-0.000000540, -0.000000141, 0.011105685], [-0.000000007, -0.001921870, 0.018273089],
+                           [0.001664462, 0.000961020, 0.018272376], [-0.001664066, 0.000960766, 0.018273287],
+                           [0.000000384, -0.000000163, -0.006215591], [-0.000000233, 0.000000389, -0.059708847]])
+
+
 def core_density(S, Hcore, nocc):
     """D_core of SURVEY 8d: occupied projector of Hcore in the S-orthonormal basis."""
     e, C_ = eigh(Hcore, S)

@@ -439,3 +439,20 @@ def test_contract_grads_partition_sum(Int4C2E, oracle):
         parts.append(e.ContractGrads(D, D, 0))
         e.close()
     assert np.abs(parts[0] + parts[1] - g).max() < 1e-12 * max(1.0, np.abs(g).max())
+
+
+def test_sn2_recorded_forces_gpu(Int4C2E, oracle):
+    """The forces Chinium recorded for CH3ClF- (tools/sn2/sn2.cnm.log:211-216) with the engine's ContractGrads in the
+    reference's gradient assembly (Restricted/Grad.cpp:60-70); see tests/test_oracle.py::test_sn2_recorded_forces for
+    why the bound is 1e-5 Eh/bohr."""
+    mol, fb = load_fixture_molecule("sn2")
+    S, T, V = oracle.one_electron(fb, mol.Z, mol.xyz_bohr)
+    enuc = H.nuclear_repulsion(mol.Z, mol.xyz_bohr)
+    eng = _engine(Int4C2E, fb)
+    E, D, F, _ = H.rhf(S, T + V, 18, lambda d, a, b: eng.ContractInts(d, a, b, 1, 0), enuc, tol=1e-9)
+    g2 = eng.ContractGrads(D, D, 0)
+    eng.close()
+    forces = -H.rhf_total_gradient(oracle, fb, mol, D, F, S, 18, g2)
+    assert abs(E - (-598.514802895)) < 1e-7
+    assert np.abs(forces - H.SN2_FORCES_LOG).max() < 1e-5, forces
+    assert np.abs(forces.sum(axis=0)).max() < 1e-7
