@@ -534,7 +534,8 @@ __host__ __device__ constexpr int wg_cfg_base(int key) {
         case 99: return 4 | (10 << 12);         // ff|ff  ten passes of 1 a-component (was the generic CTA-per-quartet kernel)
         case 71: return 1;                      // fp|ps  (measured against the sliced thread-per-quartet kernel: 4.63 -> 3.86 ms on c18)
         case 51: return 1;                      // dd|ps  (2.49 -> 2.31 ms)
-        case 66: return 1;                      // fs|fs  (1.89 -> 1.48 ms); pp|pp, fs|pp and dp|ds stay with the sliced kernels (slower here)
+        case 66: return 1;                      // fs|fs  (1.89 -> 1.48 ms); pp|pp and fs|pp stay with the sliced kernels (slower as warp-group kernels)
+        case 43: return 2;                      // dp|ds, two S components per lane (4.67 -> 4.63 ms on c18, 100 -> 86 ms on (H2O)64)
         default: return 0;
     }
 }
