@@ -104,6 +104,15 @@ def test_bench_reference_arm_runs_on_cpu():
     assert line["impl"] == "reference" and line["value"] > 0 and "cpu_baseline" in line
 
 
+def test_bench_gradient_reference_arm_runs_on_cpu():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--path", "grad", "--impl", "reference", "--workload", "h2o"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
 def test_cpp_adaptor_compiles_and_fails_loudly_without_gpu(tmp_path, have_gpu):
     """The C++ adaptor (reference's Int4C2E method names) builds against the C ABI; with no GPU it throws
     instead of falling back."""
