@@ -60,6 +60,11 @@ def test_golden_fixture_and_reference_stored_path(Int4C2E, oracle):
         assert np.abs(J2 - g[name + "_J_ab"]).max() < TOL
         assert np.abs(Ka - g[name + "_Ka"]).max() < TOL and np.abs(Kb - g[name + "_Kb"]).max() < TOL
         assert eng.RepulsionLength == int(g[name + "_counts"][0])    # the reference's RepulsionLength
+        n = fb.nbf                                                    # gradient fixture (tests/golden/make_jk_golden.py)
+        eng.EXX = 0.7
+        gr = eng.ContractGrads(H.random_symmetric_density(n, 21) * n, H.random_symmetric_density(n, 22) * n, 0)
+        ref = g[name + "_grad"]
+        assert gr.shape == ref.shape and np.abs(gr - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
         eng.close()
 
 

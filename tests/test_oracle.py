@@ -139,6 +139,9 @@ def test_golden_fixture_reproducible(oracle):
     D = H.random_symmetric_density(fb.nbf, 0)
     J, K, _, _, _ = oracle.reference_jk(fb, D)
     assert np.abs(J - g["h2o_J"]).max() < 1e-13 and np.abs(K - g["h2o_K"]).max() < 1e-13
+    n = fb.nbf
+    gr = oracle.contract_grads(fb, H.random_symmetric_density(n, 21) * n, H.random_symmetric_density(n, 22) * n, 0.7)
+    assert np.abs(gr - g["h2o_grad"]).max() < 1e-11      # generator: tests/golden/make_jk_golden.py
 
 
 def test_jk_block_matches_full(oracle):
