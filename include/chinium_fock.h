@@ -112,6 +112,11 @@ int cf_set_density_threshold(cf_handle* h, double dthr);
  * (the reference's Diag1212, Int4C2E.cpp:19-77). */
 int cf_get_repulsion_diag(cf_handle* h, double* diag1212);
 
+/* NOTE on partitions: a handle created with world_size > 1 evaluates ITS share of the quartets only.  The host calls
+ * below (cf_build_jk, cf_build_g_multi, cf_contract_grads) then return partial results; the multi-GPU route is
+ * cf_accumulate_device -> integer all-reduce of the accumulator -> cf_finalize_device (chinium_b200/distributed.py),
+ * respectively a sum of the partial gradient vectors. */
+
 /* The hot call; replaces Int4C2E::ContractInts(Dd,Da,Db,nthreads,output) (Int4C2E.cpp:673-683).
  * HOST pointers. Dd/Da/Db: nullable (absent = the reference's 0x0 matrix). J is always written;
  * KX is written iff DX is given (zeros when exx <= 0, Int4C2E.cpp:638), and may be NULL otherwise. */

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """torchrun check of the multi-GPU paths: DistributedInt4C2E.ContractInts and .ContractGrads on N ranks (NCCL) against the
-CPU oracle (rank 0).  usage: torchrun --nproc-per-node N tools/dist_grad_check.py [molecule]"""
+CPU oracle (rank 0).  usage: torchrun --nproc-per-node N tests/dist_grad_check.py [molecule]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

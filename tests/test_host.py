@@ -46,7 +46,12 @@ def test_fails_loudly_without_gpu(have_gpu):
 
 
 def test_product_never_imports_oracle():
-    """The product path must not route through the oracle (or any CPU fallback)."""
+    """The product path must not route through the oracle (or any CPU fallback); developer scripts that use the oracle as a
+    checker live under tests/ (dev_*.py, dist_grad_check.py), never under tools/ or the package."""
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".sh")):
+            src = open(os.path.join(ROOT, "tools", f)).read()
+            assert "liboracle" not in src and "oracle_lib" not in src, f
     for dirpath, _, files in os.walk(os.path.join(ROOT, "chinium_b200")):
         if "build" in dirpath:
             continue
