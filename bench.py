@@ -105,9 +105,14 @@ def cpu_sample(fb, kind, seconds_target=15.0):
     total_q = npairs * (npairs + 1) // 2
     want = rate * seconds_target
     stride2 = max(1, int(round(total_q / max(want, 1))))
-    if stride2 < stride:
+    for _ in range(3):      # the thin calibration sample over-estimates the rate (cheap pairs first): refine until ~seconds_target
+        if stride2 >= stride:
+            break
         t = time.perf_counter(); *_, c = o.direct_jk(fb, Dd, Da, Db, exx=exx_of(kind), stride=stride2, offset=stride2 // 2); dt = time.perf_counter() - t
         stride = stride2
+        if dt >= 0.6 * seconds_target or stride == 1:
+            break
+        stride2 = max(1, int(stride * dt / seconds_target))
     return dict(value=c[0] / dt, unit="quartets/s", cores=o.nthreads, kind="port", quartets=int(c[0]), seconds=dt,
                 sample="direct CPU build (oracle MD ERIs + digestion, OpenMP, all host threads) over every %d-th bra shell pair "
                        "(%d of %d canonical quartets)" % (stride, c[0], total_q))
