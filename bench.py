@@ -96,6 +96,7 @@ def cpu_sample(fb, kind, seconds_target=15.0):
     """Bounded CPU baseline on the host cores with the oracle (kind 'port': our restatement, not libint2)."""
     from oracle_lib import Oracle
     o = Oracle()
+    o.set_threads(0)      # all online cores, whatever OMP_NUM_THREADS the launcher exported (torchrun: 1)
     Dd, Da, Db = densities(fb.nbf, kind)
     npairs = fb.nshell * (fb.nshell + 1) // 2
     # calibrate on a thin sample, then size the stride for ~seconds_target
@@ -120,7 +121,11 @@ def cpu_sample(fb, kind, seconds_target=15.0):
 
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation of the path, restated (it cannot be built here:
-    libint2 / Eigen / libmwfn absent).  Rank 0 only."""
+    libint2 / Eigen / libmwfn absent).  Rank 0 only.  Every step is a BOUNDED sample whose real duration is what
+    ms_per_step reports (nothing extrapolated in the contract keys); the whole-build extrapolation is a separate key.
+      B1 (stored list fits host RAM: h2o, bo3h3, fe4s4): the literal Gunified stream over the stored unique integrals,
+         Int4C2E.cpp:601-671 -- the reference's real per-iteration cost; one step = one whole contraction.
+      B2 (c18: 159 GiB, (H2O)64: 104 TiB do not fit): a direct CPU build over every n-th bra shell pair."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
     from chinium_b200.inputs import load_fixture_molecule
@@ -128,34 +133,46 @@ def run_reference(args):
     fixture, kind = WORKLOADS[args.workload]
     mol, fb = load_fixture_molecule(fixture)
     o = Oracle()
+    cores = o.set_threads(0)
     npairs = fb.nshell * (fb.nshell + 1) // 2
     total_q = npairs * (npairs + 1) // 2
     Dd, Da, Db = densities(fb.nbf, kind)
     nint_est = (fb.nbf * (fb.nbf + 1) // 2) ** 2 / 2 * 16 / 2 ** 30
-    if nint_est < 2.0:   # stored list fits: the reference's real per-iteration path (B1)
+    steps = max(1, args.steps)
+    extra = {}
+    if nint_est < 6.0 and not args.direct_cpu:   # stored list fits: the reference's real per-iteration path (B1)
+        t = time.perf_counter()
         h = o.store_build(fb)
+        build_s = time.perf_counter() - t
         for _ in range(args.warmup):
             o.store_contract(h, fb.nbf, Dd, Da, Db, exx_of(kind))
-        t = time.perf_counter()
-        for _ in range(max(1, args.steps)):
-            o.store_contract(h, fb.nbf, Dd, Da, Db, exx_of(kind))
-        dt = (time.perf_counter() - t) / max(1, args.steps)
+        ts = []
+        for _ in range(steps):
+            t = time.perf_counter(); o.store_contract(h, fb.nbf, Dd, Da, Db, exx_of(kind)); ts.append(time.perf_counter() - t)
+        dt = float(np.median(ts))
         nint = o.store_len(h)
         o.store_free(h)
-        cb = dict(value=total_q / dt, unit="quartets/s", cores=o.nthreads, kind="port",
-                  sample="whole workload: Gunified stream over the stored list of %d unique integrals (reference's per-iteration path)" % nint)
+        value = total_q / dt
+        cb = dict(value=value, unit="quartets/s", cores=cores, kind="port",
+                  sample="whole workload per step: Gunified stream over the stored list of %d unique integrals (%.2f GiB; the "
+                         "reference's per-iteration path B1); one-off integral generation by the oracle took %.1f s and is not "
+                         "part of a step, as in the reference" % (nint, nint * 16 / 2 ** 30, build_s))
+        extra = {"stored_integrals": int(nint), "integrals_per_s": nint / dt, "stream_GBps": nint * 16 / dt / 1e9}
     else:
-        per = max(3.0, 40.0 / max(1, args.steps + args.warmup))
-        cbs = [cpu_sample(fb, kind, per) for _ in range(args.warmup + max(1, args.steps))][args.warmup:]
-        q = sum(c["quartets"] for c in cbs); s = sum(c["seconds"] for c in cbs)
-        dt = total_q / (q / s)
-        cb = dict(value=q / s, unit="quartets/s", cores=cbs[0]["cores"], kind="port",
+        per = max(3.0, 60.0 / max(1, steps + args.warmup))
+        cbs = [cpu_sample(fb, kind, per) for _ in range(args.warmup + steps)][args.warmup:]
+        q = sum(c["quartets"] for c in cbs); sec = sum(c["seconds"] for c in cbs)
+        dt = sec / len(cbs)                      # what one step (= one sample) really took
+        value = q / sec
+        cb = dict(value=value, unit="quartets/s", cores=cbs[0]["cores"], kind="port",
                   sample=cbs[0]["sample"] + "; the stored-integral list of the reference would need %.0f GiB" % nint_est)
-    line = {"metric": "ERI shell quartets/s (Fock J+K build)", "value": cb["value"], "unit": "quartets/s", "impl": "reference",
+        extra = {"extrapolated_build_ms": total_q / value * 1e3, "quartets_per_step": q / len(cbs)}
+    line = {"metric": "ERI shell quartets/s (Fock J+K build)", "value": value, "unit": "quartets/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s (%s, nbf %d, %d canonical shell quartets)" % (args.workload, kind, fb.nbf, total_q)},
-            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "quartets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": cb, "e2e": {"value": value, "unit": "quartets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line.update(extra)
     print(json.dumps(line))
     return 0
 
@@ -210,9 +227,10 @@ def run_grad(args):
     e2e_s = (time.perf_counter() - t) / args.steps
     clocks = sampler.stop()
     peak = measure_fp64_peak(0)
-    ms = float(np.mean(dev_ms))
     flops = eng.stats["flops_alg_grad"]
     q = eng.stats["canonical_quartets"]
+    base["config"]["workload"] = "%s (%s, nbf %d, %d canonical shell quartets evaluated of %d)" % (args.workload, kind, fb.nbf, q, total_q)
+    ms = float(np.median(dev_ms))
     base.update(value=q / (ms * 1e-3), ms_per_step=ms, gpu_launches=launches, clocks=clocks,
                 e2e={"value": q / e2e_s, "unit": "quartets/s", "ms_per_step": e2e_s * 1e3,
                      "h2d_bytes_per_step": 2 * fb.nbf * fb.nbf * 8, "d2h_bytes_per_step": 3 * 8 * (int(np.max(fb.shell2atom)) + 1)},
@@ -276,6 +294,10 @@ def main():
                          "except h2o64, where the unscreened job is 2.7e11 quartets: 1e-13 (see DESIGN.md)")
     ap.add_argument("--per-class", action="store_true", help="also time every class-pair kernel alone (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--direct-cpu", action="store_true", help="reference arm: time the direct CPU build (B2) even where the stored list fits")
+    ap.add_argument("--density", default="stress", choices=["stress", "core"],
+                    help="stress: seeded random symmetric U(-1,1)/nbf (SURVEY 8d density 3, default); core: the core-Hamiltonian "
+                         "projector (density 1, O(1) entries; RHF workloads)")
     ap.add_argument("--path", default="jk", choices=["jk", "grad", "multi"],
                     help="jk: the Fock J/K build (the BASELINE metric, default); grad: the nuclear-gradient contraction "
                          "ContractGrads(D, D) (SURVEY 8f rank 2), its own JSON line")
@@ -311,6 +333,15 @@ def main():
     eng = DistributedInt4C2E(fb, exx_of(kind), thr)
     setup_s = time.perf_counter() - t0
     Dd, Da, Db = densities(fb.nbf, kind)
+    dens_note = "seeded random symmetric U(-1,1)/nbf (SURVEY 8d stress density)"
+    if args.density == "core":
+        if kind == "uhf":
+            raise SystemExit("--density core is implemented for the RHF workloads")
+        from oracle_lib import Oracle
+        import scf_harness as H
+        S, T, V = Oracle().one_electron(fb, mol.Z, mol.xyz_bohr)     # input preparation only (host, outside every timed region)
+        Dd = H.core_density(S, T + V, mol.nelec // 2)
+        dens_note = "core-Hamiltonian projector (SURVEY 8d density 1, O(1) entries)"
     present = [D is not None for D in (Dd, Da, Db)]
     for k, D in enumerate((Dd, Da, Db)):
         if D is not None:
@@ -333,7 +364,6 @@ def main():
     if rank == 0:
         sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    eri_ms = []
     launches = 0
     barrier()
     for i in range(args.steps):
@@ -345,20 +375,52 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in evs]
-    st = eng.eng.sync_stats()
-    eri_ms_last = st["ms_eri_last"]
     tot = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     ms_per_step = float(tot.item()) / args.steps
+    # ERI-kernel time of a build (CUDA events inside the library, first to last class-pair kernel): median over `steps`
+    # further builds, each synchronised so that its events can be read (outside the timed region above)
+    eri_ms = []
+    for i in range(args.steps):
+        flush.zero_()
+        eng.build_device(present)
+        torch.cuda.synchronize()
+        st = eng.eng.sync_stats()
+        eri_ms.append(st["ms_eri_last"])
+    eri_med = float(np.median(eri_ms))
+    em = torch.tensor([eri_med], dtype=torch.float64, device=dev)
+    ex = torch.tensor([float(st["flops_executed_last"]), float(st["primitive_quartets_executed_last"]), float(st["quartets_evaluated_last"])],
+                      dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(em, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ex, op=dist.ReduceOp.SUM)
+    eri_med = float(em.item())
+    flops_exec, prim_exec, q_eval = (float(x) for x in ex.tolist())
 
-    # ---- end to end through the host API (host matrices in, host J/K out, pinned staging inside) ---------
+    # ---- end to end through the reference-facing HOST call: host matrices (pinned) in, host J/K (pinned) out -----------
+    # N = 1: cf_build_jk, the C entry point the C++ adaptor's ContractInts calls (H2D, all kernels, D2H inside the call);
+    # N > 1: the same through the per-rank partition + NCCL int64 all-reduce (chinium_b200/distributed.py)
+    n = fb.nbf
+    if world == 1:
+        pin = lambda: torch.empty((n, n), dtype=torch.float64).pin_memory()
+        hin = [pin() if p else None for p in present]
+        for k, D in enumerate((Dd, Da, Db)):
+            if D is not None:
+                hin[k].numpy()[...] = D
+        hout = [pin() for _ in range(4)]
+        fview = lambda t: None if t is None else t.numpy().T        # F-ordered view of the pinned block (matrices are symmetric)
+        args_in = [fview(t) for t in hin]
+        outs = [fview(t) for t in hout]
+        call = lambda: eng.eng._contract(args_in[0], args_in[1], args_in[2], out=outs)
+    else:
+        call = lambda: eng.ContractInts(Dd, Da, Db, 1, 0)
     for _ in range(2):
-        eng.ContractInts(Dd, Da, Db, 1, 0)
+        call()
     barrier()
     t = time.perf_counter()
     for _ in range(args.steps):
-        out = eng.ContractInts(Dd, Da, Db, 1, 0)
+        out = call()
     torch.cuda.synchronize()
     e2e_s = torch.tensor([(time.perf_counter() - t) / args.steps], dtype=torch.float64, device=dev)
     if world > 1:
@@ -377,13 +439,15 @@ def main():
         except Exception:
             pass
         flops = st0["flops_alg_jk"][nk] * world      # whole job (stats are per partition)
+        tf_nom = flops / (eri_med * 1e-3) / 1e12 / world
+        tf_exec = flops_exec / (eri_med * 1e-3) / 1e12 / world
         line = {
             "metric": "ERI shell quartets/s (Fock J+K build)", "value": total_q / (ms_per_step * 1e-3), "unit": "quartets/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s (%s, nbf %d, %d canonical shell quartets, %d unique integrals)" % (
-                           args.workload, kind, fb.nbf, total_q, st0["unique_integrals"]),
-                       "densities": "seeded random symmetric (SURVEY 8d stress density), nK=%d, EXX=%.1f" % (nk, exx_of(kind)),
+            "config": {"workload": "%s (%s, nbf %d, %d canonical shell quartets, reference RepulsionLength %d)" % (
+                           args.workload, kind, fb.nbf, total_q, st0["ref_repulsion_length"]),
+                       "densities": "%s, nK=%d, EXX=%.1f" % (dens_note, nk, exx_of(kind)),
                        "schwarz_threshold": thr,
                        "l2": "flushed between timed iterations (256 MiB write, outside the step events)",
                        "partition": "static chunk-interleaved split of every class-pair quartet range over %d rank(s); "
@@ -391,23 +455,34 @@ def main():
                        "setup_s": setup_s},
             "fock_build_ms": ms_per_step,
             "e2e": {"value": total_q / e2e_s, "unit": "quartets/s", "ms_per_step": e2e_s * 1e3,
-                    "h2d_bytes_per_step": n2 * sum(present), "d2h_bytes_per_step": n2 * (1 + nk)},
+                    "h2d_bytes_per_step": n2 * sum(present), "d2h_bytes_per_step": n2 * (1 + nk),
+                    "call": "cf_build_jk (C ABI host call, pinned host buffers)" if world == 1 else "DistributedInt4C2E.ContractInts"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "achieved": flops / (eri_ms_last * 1e-3) / 1e12 / world, "peak": peak, "unit": "TFLOP/s",
-                         "frac": flops / (eri_ms_last * 1e-3) / 1e12 / world / peak, "traffic": traffic, "traffic_source": traffic_note,
+            # `frac` / `achieved`: model flops of the work the kernels really EXECUTED (device counters of primitive quartets
+            # that passed both primitive cutoffs, x the per-primitive flops of SURVEY 8d, + digestion of the evaluated
+            # quartets).  `frac_nominal` divides the same time into F_alg at NOMINAL contraction depths (every primitive
+            # quartet of every surviving shell pair, the SURVEY 8d definition) -- work that is skipped counts there.
+            "roofline": {"bound": "fp64", "achieved": tf_exec, "peak": peak, "unit": "TFLOP/s", "frac": tf_exec / peak,
+                         "frac_executed": tf_exec / peak, "frac_nominal": tf_nom / peak, "achieved_nominal": tf_nom,
+                         "traffic": traffic, "traffic_source": traffic_note,
                          # D in + J/K out + 6 doubles per primitive pair (P pairs <-> P(P+1)/2 primitive quartets)
                          "algorithmic_bytes": 2 * (1 + nk) * n2 + 48 * (2.0 * st0["primitive_quartets"]) ** 0.5,
-                         "kernel": "eri_jk_tpq/tpqs/wg<*> (all class-pair ERI+digestion launches of one build, per GPU)", "ms": eri_ms_last,
-                         "flops_alg": flops, "peak_source": "measured in-run: register-resident DFMA loop (cf_measure_fp64_peak); "
-                                                            "MEASURED_PEAKS.json has no FP64 entry"},
+                         "kernel": "eri_jk_tpq/tpqa/tpqs/wg<*> (all class-pair ERI+digestion launches of one build, per GPU)",
+                         "ms": eri_med, "ms_all_steps": eri_ms,
+                         "flops_executed": flops_exec, "primitive_quartets_executed": prim_exec, "quartets_evaluated": q_eval,
+                         "primitive_quartets_nominal_kept_pairs": st0["primitive_quartets"],
+                         "flops_alg_nominal": flops, "j_two_limb": st["j_two_limb_last"],
+                         "peak_source": "measured in-run: register-resident DFMA loop (cf_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry"},
         }
         if args.per_class and world == 1:
             rows = eng.eng.profile_tasks(eng._D[0].data_ptr() if present[0] else None, eng._D[1].data_ptr() if present[1] else None,
                                          eng._D[2].data_ptr() if present[2] else None)
             for r in rows:
-                r["tflops"] = r["flops_alg"] / (r["ms"] * 1e-3) / 1e12
+                r["tflops"] = r["flops_executed"] / (r["ms"] * 1e-3) / 1e12
                 r["frac"] = r["tflops"] / peak
+                r["frac_nominal"] = r["flops_alg"] / (r["ms"] * 1e-3) / 1e12 / peak
             line["per_class"] = rows
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_sample(fb, kind, 15.0)

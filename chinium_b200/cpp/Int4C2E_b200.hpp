@@ -89,8 +89,8 @@ class Int4C2E_T {
         if (stage_ < 1) throw std::runtime_error("Diagonal elements of repulsion integrals are missing!");   // Int4C2E.cpp:514
         cf_stats st;
         check(cf_get_stats(h_.get(), &st));
-        RepulsionLength = (long int)st.unique_integrals;
-        ShellQuartetLength = (long int)st.canonical_quartets;
+        RepulsionLength = (long int)st.ref_repulsion_length;         // the reference's own counts (its loop nest and uniqueness
+        ShellQuartetLength = (long int)st.ref_shell_quartet_length;  // predicate, Int4C2E.cpp:79-128), not the engine's work metric
         if (output > 0) {
             const long nb = st.nbf, ns = st.nshell;
             std::printf("Before screening: %ld integrals and %ld shell quartets\n", nb * (nb + 1) * (nb * (nb + 1) / 2 + 1) / 4,

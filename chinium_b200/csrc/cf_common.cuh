@@ -40,9 +40,23 @@ struct PairClassDev {
     const double* c;        // ca*cb*exp(-ab/p |AB|^2) * sqrt(2) pi^(5/4) / p
 };
 
-// the evaluated-quartet counter is spread over CF_NQ_SLOTS words (same-address atomics serialise in L2)
-#define CF_NQ_SLOTS 1024
-__device__ __forceinline__ int cf_nq_slot() { return (int)((blockIdx.x * 8u + (threadIdx.x >> 5)) & (CF_NQ_SLOTS - 1)); }
+// Work counters of one build, per class-pair task: CF_CNT_SLOTS words of evaluated shell quartets followed by
+// CF_CNT_SLOTS words of EXECUTED primitive quartets (those that passed the primitive cutoff and were really run
+// through roots + recurrences + assembly).  Every warp keeps its counts in registers over all its work items and
+// flushes them once at the end of the kernel; the slots spread the flushes (same-address atomics serialise in L2).
+#define CF_CNT_SLOTS 32
+#define CF_CNT_WORDS (2 * CF_CNT_SLOTS)
+__device__ __forceinline__ int cf_cnt_slot() { return (int)((blockIdx.x * 4u + (threadIdx.x >> 5)) & (CF_CNT_SLOTS - 1)); }
+// warp-level flush (all 32 lanes call it): nq / np are per-lane counts
+__device__ __forceinline__ void cf_cnt_flush(unsigned long long* cnt, unsigned nq, unsigned np) {
+    if (!cnt) return;
+    nq = __reduce_add_sync(0xffffffffu, nq);
+    np = __reduce_add_sync(0xffffffffu, np);
+    if ((threadIdx.x & 31) == 0) {
+        if (nq) atomicAdd(cnt + cf_cnt_slot(), (unsigned long long)nq);
+        if (np) atomicAdd(cnt + CF_CNT_SLOTS + cf_cnt_slot(), (unsigned long long)np);
+    }
+}
 
 struct RysTablesDev {
     const double* table;
@@ -67,7 +81,12 @@ struct QuartetTask {
     const double* Dk[3];    // Cartesian exchange densities
     long long* accJ;        // [ncart*ncart] fixed-point raw J
     long long* accK[3];
-    const double* scales;   // device: [0] J scale, [1] K scale (powers of two, written by scales_kernel of this build)
+    const double* scales;   // device: [0] J scale, [1] K scale (powers of two, written by scales_kernel of this build),
+                            //   [4] effective Schwarz threshold, [6] != 0: the J adds also feed the low limb
+    long long jlo_off;      // words from a J accumulator (accJm[x]) to its LOW LIMB: contributions are rounded to the grid
+                            //   1/scaleJ of the high limb and the rounding residual, scaled by 2^31, goes to the low limb.
+                            //   Used when scales[6] != 0 (large systems, where ~1e6 roundings per element would add up to
+                            //   the 1e-10 bar); integer adds in both limbs, so the result stays bit-identical for any schedule
     double* store;          // STORE mode: Cartesian blocks, NOUT doubles per quartet in flat order
     int diag;               // Schwarz mode: quartet q is (pair q | pair q)
     RysTablesDev rys;
@@ -90,5 +109,5 @@ struct QuartetTask {
     const double* brec_d;
     const double* bprim;
     long long bprim_stride;
-    unsigned long long* nq_done;   // [CF_NQ_SLOTS] counters of the shell quartets actually evaluated by this build (may be null)
+    unsigned long long* cnt;       // [CF_CNT_WORDS] this task's work counters of the build (null: Schwarz/STORE mode)
 };

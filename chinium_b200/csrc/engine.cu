@@ -231,8 +231,11 @@ struct ClassPairTask {
     int braloop = 0;                 // kind 1: bra-loop kernel (eri_tpqa.cuh) with chunk items
     int G = 32;
     size_t smem[4] = {0, 0, 0, 0};   // by nk
-    double flops_eri = 0;            // F_alg without the digestion term
+    double flops_eri = 0;            // F_alg without the digestion term (NOMINAL contraction depths)
     double nfun_sum = 0;             // sum over quartets of N_s (pure functions) for the digestion term
+    double per_prim = 0;             // model flops of ONE primitive quartet of this class pair
+    double nfun_q = 0;               // N_s of one quartet
+    int index = 0;                   // position in cf_handle::tasks = slot of the task's device counters
 };
 
 struct cf_handle {
@@ -253,18 +256,21 @@ struct cf_handle {
     std::vector<ClassPairTask*> tasks;
     DevBuf<double> d_rys_table, d_rys_asym, d_boys;
     // per-build work space
-    DevBuf<double> d_Dpure[3], d_Dcart[4] /* 0: Dtot, 1..3: Dk */, d_out[4] /* pure J,Kd,Ka,Kb */, d_partial, d_scales, d_diag,
+    DevBuf<double> d_Dpure[3], d_Dcart[4] /* 0: Dtot, 1..3: Dk */, d_out[4] /* pure J,Kd,Ka,Kb */, d_partial, d_diag,
         d_QS /* [nshell^2] Cartesian Schwarz bound per shell pair */, d_B /* [4][nshell^2] block 1-norms of |D_cart| */, d_Bmax /* same, max-norms */, d_rwork;
     DevBuf<long long> d_acc;
-    DevBuf<unsigned long long> d_nq;         // shell quartets evaluated by the last build (device counter)
-    unsigned long long nq_host[CF_NQ_SLOTS] = {0};
+    DevBuf<unsigned long long> d_cnt;        // [ntask][CF_CNT_WORDS] work counters of the last build (cf_common.cuh)
+    std::vector<unsigned long long> cnt_host;
     double qmax_cart = 0;
-    double scales_host[8] = {1, 1, 0, 0, 0, 0, 0, 0};   // copy of d_scales of the last synchronised build
+    double scales_host[8] = {1, 1, 0, 0, 0, 0, 0, 0};   // copy of the scale tail of the last synchronised build
+    const long long* last_tail = nullptr;    // device address of that tail (the accumulator of the last *_device call)
+    int last_nk = 0;                         // exchange densities of the last build (flops_executed_last)
     double density_threshold = 0.0;          // > 0: density-weighted screening (cf_set_density_threshold)
     cudaEvent_t ev[4];
     cudaStream_t side[3];
     cudaEvent_t ev_fork, ev_join[3];
     cf_stats stats{};
+    long long ref_counts[2] = {0, 0};        // the reference's RepulsionLength / ShellQuartetLength
     std::string err;
     bool diag_ready = false;
 };
@@ -273,6 +279,16 @@ static void set_error(cf_handle* h, const std::string& s) {
     if (h) h->err = s;
     g_last_error = s;
 }
+
+// every entry point works on the handle's device and leaves the caller's current device as it found it
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+// accumulator layout (int64 words): [J | K_0 .. K_{nk-1} | J low limb | tail], tail = CF_ACC_TAIL words holding the
+// fixed-point scales of THAT build as doubles -- scales travel with the accumulator they belong to
+#define CF_ACC_TAIL 8
 
 // ------------------------------------------------------------------------------------------------
 // small device kernels
@@ -320,9 +336,13 @@ __global__ void pure_to_cart_kernel(int nshell, int nbf, int ncart, const double
 }
 
 // out_pure(block) = factor * C_a [ (acc + acc^T) / scale ] C_b^T ; integer sum first (exact), one conversion.
+// The integer sum is taken modulo 2^64 (unsigned arithmetic): partial sums of the build may have wrapped around, the
+// final value fits by construction of the scale (scales_kernel), so the wrapped sum IS the exact value.
+// acc_lo != nullptr and scales[6] != 0: the J low limb (rounding residuals scaled by 2^31) is added.
 // Only blocks sb <= sa (and m >= n inside diagonal blocks) are computed and mirrored, so the output is EXACTLY
 // symmetric like the reference's 1/4 (raw + raw^T) (Int4C2E.cpp:661-664).
-__global__ void finalize_kernel(int nbf, int ncart, const long long* __restrict__ acc, const double* __restrict__ scales, int which_scale,
+__global__ void finalize_kernel(int nbf, int ncart, const long long* __restrict__ acc, const long long* __restrict__ acc_lo,
+                                const double* __restrict__ scales, int which_scale,
                                 double factor, const double* __restrict__ ctrans, const int* __restrict__ ct_off,
                                 const int* __restrict__ bf_off, const int* __restrict__ cao_off, const int* __restrict__ nfun,
                                 const int* __restrict__ ncsh, double* __restrict__ out) {
@@ -332,6 +352,7 @@ __global__ void finalize_kernel(int nbf, int ncart, const long long* __restrict_
     const double* Ca = ctrans + ct_off[sa];
     const double* Cb = ctrans + ct_off[sb];
     const double f = factor / scales[which_scale];
+    const bool lo_on = acc_lo != nullptr && scales[6] != 0.0;
     for (int e = threadIdx.x; e < na * nb; e += blockDim.x) {
         const int m = e / nb, n = e % nb;
         if (sa == sb && n > m) continue;
@@ -341,8 +362,13 @@ __global__ void finalize_kernel(int nbf, int ncart, const long long* __restrict_
             if (cam == 0.0) continue;
             for (int y = 0; y < ncb; y++) {
                 const size_t i = cao_off[sa] + x, j = cao_off[sb] + y;
-                const long long v = acc[j * ncart + i] + acc[i * ncart + j];
-                s = fma(cam * Cb[n * ncb + y], (double)v, s);
+                const long long v = (long long)((unsigned long long)acc[j * ncart + i] + (unsigned long long)acc[i * ncart + j]);
+                double dv = (double)v;
+                if (lo_on) {
+                    const long long vl = (long long)((unsigned long long)acc_lo[j * ncart + i] + (unsigned long long)acc_lo[i * ncart + j]);
+                    dv += (double)vl * 0x1p-31;
+                }
+                s = fma(cam * Cb[n * ncb + y], dv, s);
             }
         }
         s *= f;
@@ -401,18 +427,30 @@ __global__ void bounds_kernel(int ns, const double* __restrict__ QS, const doubl
 }
 // scales[0] = J scale, scales[1] = K scale (powers of two), scales[2..3] = the bounds themselves,
 // scales[4] = effective Schwarz threshold of this build: a quartet is evaluated iff Q_ab Q_cd > thr (the reference's
-// test, Int4C2E.cpp:108-113) AND Q_ab Q_cd max|D| > dthr (density-weighted, off when dthr <= 0), scales[5] = max|D|
-__global__ void scales_kernel(const double* __restrict__ bounds, int nk, double qmax, double thr, double dthr, double* __restrict__ scales) {
+// test, Int4C2E.cpp:108-113) AND Q_ab Q_cd max|D| > dthr (density-weighted, off when dthr <= 0), scales[5] = max|D|,
+// scales[6] = 1: the J adds feed the low limb as well, scales[7] = estimated worst rounding error of J without it.
+//
+// Range: the accumulators are summed modulo 2^64, so only the FINAL value of an element has to fit.  The value read by
+// finalize_kernel is raw + raw^T = 4 J_cart (J) resp. 8 K_cart (K), and by Cauchy-Schwarz
+//   |J_cart(i,j)| <= Q_ij sum_kl Q_kl |D_kl| <= Qmax * bounds[0],   |K_cart(i,k)| <= sum_jl Q_ij Q_kl |D_jl| <= Qmax * bounds[1+x]
+// (every partial sum of any subset of the contributions obeys the same bound, so each double -> int64 conversion is in
+// range as well).  A margin of 2^-10 covers the rounding of the bounds and of up to 2^52 individual conversions.
+// Resolution: 1/scale per contribution; n roundings of +-1/2 unit pile up like sqrt(n/12).  For J on large systems
+// (n ~ 10^6 shell pairs per element) that can approach the 1e-10 bar: the low limb is then switched on (jlo_mode 0:
+// when the estimate exceeds 1e-11; 1: always; -1: never).
+__global__ void scales_kernel(const double* __restrict__ bounds, int nk, double qmax, double thr, double dthr, double npair,
+                              int jlo_mode, double* __restrict__ scales) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double nkmax = 0.0;
     for (int x = 0; x < nk; x++) nkmax = fmax(nkmax, bounds[1 + x]);
-    const double bj = 16.0 * qmax * bounds[0], bk = 16.0 * qmax * nkmax;
+    const double margin = 1.0 + 0x1p-10;
+    const double bj = 4.0 * qmax * bounds[0] * margin, bk = 8.0 * qmax * nkmax * margin;
     int ej, ek;
-    frexp(fmax(bj, 1e-300), &ej);
+    frexp(fmax(bj, 1e-300), &ej);      // bj = m 2^ej, m in [1/2, 1)  ->  bj 2^(63-ej) < 2^63
     frexp(fmax(bk, 1e-300), &ek);
     // zero / tiny densities: cap the exponent so the scale stays finite (contributions are then exactly 0 anyway)
-    scales[0] = ldexp(1.0, min(62 - ej, 512));
-    scales[1] = ldexp(1.0, min(62 - ek, 512));
+    scales[0] = ldexp(1.0, min(63 - ej, 512));
+    scales[1] = ldexp(1.0, min(63 - ek, 512));
     scales[2] = bj;
     scales[3] = bk;
     double dmax = bounds[4];
@@ -421,6 +459,9 @@ __global__ void scales_kernel(const double* __restrict__ bounds, int nk, double 
     if (dthr > 0.0) eff = fmax(eff, dmax > 0.0 ? dthr / dmax : 1e300);
     scales[4] = eff;
     scales[5] = dmax;
+    const double est = 0.25 / scales[0] * sqrt(npair / 6.0) * 6.0;     // J = raw / 4; ~6 sigma of sqrt(n/12)-type noise, two orientations
+    scales[6] = (jlo_mode > 0 || (jlo_mode == 0 && est > 1e-11)) ? 1.0 : 0.0;
+    scales[7] = est;
 }
 
 // Schwarz bounds of one pair class from the stored Cartesian (ab|ab) blocks: one CTA per pair
@@ -528,6 +569,52 @@ __global__ void item_list_a_kernel(int nchunk, const int* __restrict__ cstart, c
         n++;
     }
     if (counts) counts[ic] = n;
+}
+
+// The reference's screening counts (getRepulsionLength, Int4C2E.cpp:79-128) for threshold > 0, part s3 == s1 of its loop
+// nest s1; s2 <= s1; s3 <= s1; s4 <= max(s2, s3): the two shell pairs share shell s1, so the uniqueness predicate
+// bf2 <= bf1 && bf3 <= bf1 && bf4 <= (bf1 == bf3 ? bf2 : bf3) couples them and the test has to be made function by
+// function on Diag1212.  One CTA per s1, threads over (s2, s4); P = shell-pair maxima of sqrt|Diag| prune most pairs.
+__global__ void ref_count_special_kernel(int ns, int nbf, const int* __restrict__ bf_off, const int* __restrict__ nfun,
+                                         const double* __restrict__ diag, const double* __restrict__ P, double thr,
+                                         unsigned long long* __restrict__ out) {
+    const int s1 = blockIdx.x;
+    const int n1 = nfun[s1], o1 = bf_off[s1];
+    unsigned long long nq = 0, ni = 0;
+    const long long npairs = (long long)(s1 + 1) * (s1 + 1);
+    for (long long e = threadIdx.x; e < npairs; e += blockDim.x) {
+        const int s2 = (int)(e / (s1 + 1)), s4 = (int)(e % (s1 + 1));
+        if (!(P[(size_t)s1 * ns + s2] * P[(size_t)s1 * ns + s4] > thr)) continue;
+        const int n2 = nfun[s2], o2 = bf_off[s2], n4 = nfun[s4], o4 = bf_off[s4];
+        int uniq = 0; bool keep = false;
+        for (int f1 = 0; f1 < n1; f1++) {
+            const int bf1 = o1 + f1;
+            for (int f2 = 0; f2 < n2; f2++) {
+                const int bf2 = o2 + f2;
+                if (bf2 > bf1) break;
+                const double d12 = diag[(size_t)bf2 * nbf + bf1];
+                for (int f3 = 0; f3 <= f1; f3++) {
+                    const int bf3 = o1 + f3;
+                    const int lim = (bf1 == bf3) ? bf2 : bf3;
+                    for (int f4 = 0; f4 < n4; f4++) {
+                        const int bf4 = o4 + f4;
+                        if (bf4 > lim) break;
+                        uniq++;
+                        if (sqrt(fabs(d12 * diag[(size_t)bf4 * nbf + bf3])) > thr) keep = true;
+                    }
+                }
+            }
+        }
+        if (keep) { nq++; ni += (unsigned long long)uniq; }
+    }
+    __shared__ unsigned long long sh[2][256];
+    sh[0][threadIdx.x] = nq; sh[1][threadIdx.x] = ni;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) { sh[0][threadIdx.x] += sh[0][threadIdx.x + w]; sh[1][threadIdx.x] += sh[1][threadIdx.x + w]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { atomicAdd(out, sh[0][0]); atomicAdd(out + 1, sh[1][0]); }
 }
 
 // register-resident DFMA loop: the FP64 roofline denominator measured on the device itself
@@ -691,7 +778,7 @@ extern "C" int cf_measure_fp64_peak(int device, double* tflops) {
 
 extern "C" void cf_destroy(cf_handle* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     for (auto& c : h->cls) c.release();
     for (auto* t : h->tasks) { t->d_qoff.release(); t->d_items.release(); delete t; }
     h->d_ctrans.release(); h->d_ct_off.release(); h->d_bf_off.release(); h->d_cao_off.release(); h->d_nfun.release(); h->d_ncartsh.release();
@@ -699,7 +786,7 @@ extern "C" void cf_destroy(cf_handle* h) {
     for (auto& b : h->d_Dpure) b.release();
     for (auto& b : h->d_Dcart) b.release();
     for (auto& b : h->d_out) b.release();
-    h->d_partial.release(); h->d_scales.release(); h->d_diag.release(); h->d_acc.release(); h->d_nq.release();
+    h->d_partial.release(); h->d_diag.release(); h->d_acc.release(); h->d_cnt.release();
     h->d_QS.release(); h->d_B.release(); h->d_Bmax.release(); h->d_rwork.release();
     h->d_shell2atom.release(); h->d_gpart.release(); h->d_grad.release();
     for (auto& e : h->ev) cudaEventDestroy(e);
@@ -721,6 +808,7 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
         set_error(nullptr, "cf_create: null or empty basis");
         return nullptr;
     }
+    struct RestoreDevice { int prev = -1; RestoreDevice() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; } ~RestoreDevice() { if (prev >= 0) cudaSetDevice(prev); } } restore_device;
     cf_handle* h = new cf_handle();
     if (opts) h->opt = *opts;
     if (h->opt.world_size <= 0) { h->opt.world_size = 1; h->opt.rank = 0; }
@@ -884,6 +972,63 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
         if (h->d_QS.upload(QS) != cudaSuccess || h->d_B.alloc(4 * (size_t)ns * ns) != cudaSuccess || h->d_Bmax.alloc(4 * (size_t)ns * ns) != cudaSuccess || h->d_rwork.alloc(4 * (size_t)ns) != cudaSuccess)
             return fail("cudaMalloc failed (Schwarz matrix)");
     }
+    {   // ---- the reference's own counts RepulsionLength / ShellQuartetLength (getRepulsionLength, Int4C2E.cpp:79-128):
+        // loop nest s1; s2 <= s1; s3 <= s1; s4 <= max(s2,s3), a shell quartet counts iff one of its UNIQUE function
+        // quartets has sqrt|Diag(bf1,bf2) Diag(bf3,bf4)| > threshold, and then contributes all its unique function quartets.
+        const double thr0 = h->opt.threshold;
+        long long nq_ref = 0, ni_ref = 0;
+        if (!(thr0 > 0.0)) {   // nothing is screened (the reference's default -1): closed forms
+            const long long N = (long long)nbf * (nbf + 1) / 2;
+            ni_ref = N * (N + 1) / 2;
+            for (long long s1 = 0; s1 < ns; s1++)   // s3 < s1: every s4 <= s3 holds unique functions; s3 == s1: s4 <= s1 (s4 <= s2 for one-function shells)
+                nq_ref += (s1 + 1) * (s1 + 1) * s1 / 2 + (h->nfun[s1] >= 2 ? (s1 + 1) * (s1 + 1) : (s1 + 1) * (s1 + 2) / 2);
+        } else {
+            // P[a,b] = max over the shell pair's functions of sqrt|Diag1212| (0 for pairs without surviving primitives)
+            std::vector<double> P((size_t)ns * ns, 0.0);
+            for (auto& c : h->cls)
+                for (int i = 0; i < c.npair(); i++) { P[(size_t)c.sa[i] * ns + c.sb[i]] = c.Qpure[i]; P[(size_t)c.sb[i] * ns + c.sa[i]] = c.Qpure[i]; }
+            // part s3 < s1 (then only s4 <= s3 holds unique functions, and every function quartet with bf2 <= bf1, bf4 <= bf3
+            // is unique): kept iff P12 P34 > thr.  Pairs (s3,s4) enter a Fenwick tree over their rank in P as s1 advances.
+            const long long npr = (long long)ns * (ns + 1) / 2;
+            std::vector<int> rank_of(npr);
+            {
+                std::vector<long long> idx(npr);
+                std::iota(idx.begin(), idx.end(), 0LL);
+                auto pv = [&](long long e) { long long a = (long long)((std::sqrt(8.0 * e + 1.0) - 1.0) / 2.0); while (a * (a + 1) / 2 > e) a--; while ((a + 1) * (a + 2) / 2 <= e) a++; return P[(size_t)a * ns + (e - a * (a + 1) / 2)]; };
+                std::vector<double> pvals(npr);
+                for (long long e = 0; e < npr; e++) pvals[e] = pv(e);
+                std::stable_sort(idx.begin(), idx.end(), [&](long long x, long long y) { return pvals[x] > pvals[y]; });
+                std::vector<double> sorted(npr);
+                for (long long r = 0; r < npr; r++) { rank_of[idx[r]] = (int)r; sorted[r] = pvals[idx[r]]; }
+                std::vector<long long> fen_n(npr + 1, 0), fen_u(npr + 1, 0);
+                auto add = [&](int r, long long u) { for (int i = r + 1; i <= npr; i += i & -i) { fen_n[i]++; fen_u[i] += u; } };
+                auto query = [&](int cnt, long long& n, long long& u) { n = 0; u = 0; for (int i = cnt; i > 0; i -= i & -i) { n += fen_n[i]; u += fen_u[i]; } };
+                auto upair = [&](int a, int b) { return a == b ? (long long)h->nfun[a] * (h->nfun[a] + 1) / 2 : (long long)h->nfun[a] * h->nfun[b]; };
+                for (int s1 = 0; s1 < ns; s1++) {
+                    if (s1 > 0) for (int s4 = 0; s4 <= s1 - 1; s4++) add(rank_of[(long long)(s1 - 1) * s1 / 2 + s4], upair(s1 - 1, s4));   // pairs with s3 = s1 - 1
+                    for (int s2 = 0; s2 <= s1; s2++) {
+                        const double p12 = P[(size_t)s1 * ns + s2];
+                        if (!(p12 > 0.0)) continue;
+                        // number of ranks r with sorted[r] * p12 > thr (sorted descends)
+                        const int cnt = (int)(std::partition_point(sorted.begin(), sorted.end(), [&](double q) { return q * p12 > thr0; }) - sorted.begin());
+                        long long n, u;
+                        query(cnt, n, u);
+                        nq_ref += n; ni_ref += u * upair(s1, s2);
+                    }
+                }
+            }
+            // part s3 == s1 on the device
+            DevBuf<double> dP; DevBuf<unsigned long long> dout;
+            if (dP.upload(P) != cudaSuccess || dout.alloc(2) != cudaSuccess) return fail("cudaMalloc failed (reference counts)");
+            cudaMemset(dout.p, 0, 2 * sizeof(unsigned long long));
+            ref_count_special_kernel<<<ns, 256>>>(ns, nbf, h->d_bf_off.p, h->d_nfun.p, h->d_diag.p, dP.p, thr0, dout.p);
+            unsigned long long o2[2] = {0, 0};
+            if (cudaMemcpy(o2, dout.p, sizeof(o2), cudaMemcpyDeviceToHost) != cudaSuccess) return fail("reference count kernel failed");
+            nq_ref += (long long)o2[0]; ni_ref += (long long)o2[1];
+            dP.release(); dout.release();
+        }
+        h->ref_counts[0] = ni_ref; h->ref_counts[1] = nq_ref;
+    }
 
     // ---- class-pair tasks.  Quartet (ib, ik) of a task is canonical iff ik <= ib when bra class == ket class.
     // Schwarz screening (threshold > 0, Int4C2E.cpp:108-113) is a per-quartet test Q_b * Q_k > thr inside the kernels;
@@ -892,6 +1037,7 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     cf_stats& st = h->stats;
     st = cf_stats{};
     st.nshell = ns; st.nbf = nbf; st.ncart = ncart;
+    st.ref_repulsion_length = h->ref_counts[0]; st.ref_shell_quartet_length = h->ref_counts[1];
     st.shell_pairs_total = (long long)ns * (ns + 1) / 2;
     st.shell_pairs_kept = pairs_kept;
     for (int cb = 0; cb < CF_NCLS; cb++)
@@ -1014,7 +1160,9 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
                 if (t->d_qoff.upload(qoff) != cudaSuccess) { delete t; return fail("qoff upload failed"); }
             }
             t->flops_eri = primq_full * per_prim;
-            t->nfun_sum = (double)nq_kept * nfa * nfb * nfc * nfd;
+            t->per_prim = per_prim;
+            t->nfun_q = (double)nfa * nfb * nfc * nfd;
+            t->nfun_sum = (double)nq_kept * t->nfun_q;
             st.canonical_quartets += nq_kept;
             st.unique_integrals += (long long)(uniq + 0.5);
             st.primitive_quartets += (long long)(primq + 0.5);
@@ -1030,6 +1178,8 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     if (h->opt.world_size > 1) { for (int k = 0; k < 4; k++) st.flops_alg_jk[k] /= h->opt.world_size; st.flops_alg_grad /= h->opt.world_size; }
     // heavy tasks first so the tail of the build is made of small kernels
     std::sort(h->tasks.begin(), h->tasks.end(), [](const ClassPairTask* a, const ClassPairTask* b) { return a->flops_eri > b->flops_eri; });
+    for (size_t i = 0; i < h->tasks.size(); i++) h->tasks[i]->index = (int)i;
+    h->cnt_host.assign(h->tasks.size() * CF_CNT_WORDS, 0ull);
 
     // ---- work space
     const size_t n2p = (size_t)nbf * nbf, n2c = (size_t)ncart * ncart;
@@ -1037,13 +1187,15 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     for (auto& b : h->d_Dpure) ok = ok && b.alloc(n2p) == cudaSuccess;
     for (auto& b : h->d_Dcart) ok = ok && b.alloc(n2c) == cudaSuccess;
     for (auto& b : h->d_out) ok = ok && b.alloc(n2p) == cudaSuccess;
-    ok = ok && h->d_acc.alloc(6 * n2c) == cudaSuccess && h->d_partial.alloc(4 * 256) == cudaSuccess && h->d_scales.alloc(8) == cudaSuccess && h->d_nq.alloc(CF_NQ_SLOTS) == cudaSuccess;
+    // accumulator of the host calls: up to [J_0..J_2 | K_0..K_2 | Jlo_0..Jlo_2 | tail] (multi-density build)
+    ok = ok && h->d_acc.alloc(9 * n2c + CF_ACC_TAIL) == cudaSuccess && h->d_partial.alloc(4 * 256) == cudaSuccess &&
+         h->d_cnt.alloc(std::max<size_t>(1, h->tasks.size()) * CF_CNT_WORDS) == cudaSuccess;
     if (!ok) return fail("cudaMalloc failed (work space)");
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(std::string("setup kernels failed: ") + cudaGetErrorString(cudaGetLastError()));
     if (h->opt.verbose > 0) {
         // the reference prints one line per setup stage (Int4C2E.cpp:500-587); the stages are fused here
         std::printf("Calculating diagonal elements of repulsion integrals ... Done in %f s\n", now_s() - t_start);
-        std::printf("After screening: %lld integrals and %lld shell quartets\n", (long long)st.unique_integrals, (long long)st.canonical_quartets);
+        std::printf("After screening: %lld integrals and %lld shell quartets\n", (long long)st.ref_repulsion_length, (long long)st.ref_shell_quartet_length);
     }
     return h;
 }
@@ -1065,14 +1217,19 @@ extern "C" int cf_get_stats(const cf_handle* h, cf_stats* out) {
 extern "C" int cf_get_repulsion_diag(cf_handle* h, double* diag1212) {
     if (!h || !diag1212) return CF_ERR_BAD_ARGUMENT;
     if (!h->diag_ready) { set_error(h, "Diagonal elements of repulsion integrals are missing!"); return CF_ERR_STATE; }
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     CUDA_TRY(cudaMemcpy(diag1212, h->d_diag.p, sizeof(double) * (size_t)h->nbf * h->nbf, cudaMemcpyDeviceToHost));
     return CF_OK;
 }
 
-extern "C" size_t cf_acc_len(const cf_handle* h, int nk) {
+// words to ALLOCATE for an accumulator of nk exchange densities / the leading words a multi-GPU caller all-reduces
+extern "C" size_t cf_acc_reduce_len(const cf_handle* h, int nk) {
     if (!h || nk < 0 || nk > 3) return 0;
-    return (size_t)(1 + nk) * h->ncart * h->ncart;
+    return (size_t)(2 + nk) * h->ncart * h->ncart;
+}
+extern "C" size_t cf_acc_len(const cf_handle* h, int nk) {
+    const size_t n = cf_acc_reduce_len(h, nk);
+    return n ? n + CF_ACC_TAIL : 0;
 }
 
 // densities present -> compact list of exchange densities
@@ -1092,12 +1249,14 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
     if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
     if (!Dd && !Da && !Db) { set_error(h, "at least one density is required"); return CF_ERR_BAD_ARGUMENT; }
     if (!acc) { set_error(h, "null accumulator"); return CF_ERR_BAD_ARGUMENT; }
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     const double* dk[3]; int slot[3];
     const int nk = exchange_list(Dd, Da, Db, exx, dk, slot);
     const int ns = h->nshell, ncart = h->ncart;
     const size_t n2c = (size_t)ncart * ncart;
+    double* tail = reinterpret_cast<double*>((long long*)acc + (size_t)(2 + nk) * n2c);     // scales of THIS build
+    h->last_tail = (const long long*)tail; h->last_nk = nk;
     h->stats.n_launches_last = 0;
     CUDA_TRY(cudaEventRecord(h->ev[0], s));
     dim3 grid2(ns, ns);
@@ -1113,10 +1272,11 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
         h->stats.n_launches_last++;
     }
     bounds_kernel<<<1 + nk, 1024, 0, s>>>(ns, h->d_QS.p, h->d_B.p, h->d_Bmax.p, h->d_rwork.p, h->d_partial.p);
-    scales_kernel<<<1, 32, 0, s>>>(h->d_partial.p, nk, h->qmax_cart, h->opt.threshold, h->density_threshold, h->d_scales.p);
+    scales_kernel<<<1, 32, 0, s>>>(h->d_partial.p, nk, h->qmax_cart, h->opt.threshold, h->density_threshold,
+                                   (double)h->stats.shell_pairs_kept, h->opt.j_two_limb, tail);
     h->stats.n_launches_last += 2;
-    CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * (1 + nk) * n2c, s));
-    CUDA_TRY(cudaMemsetAsync(h->d_nq.p, 0, sizeof(unsigned long long) * CF_NQ_SLOTS, s));
+    CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * (2 + nk) * n2c, s));
+    CUDA_TRY(cudaMemsetAsync(h->d_cnt.p, 0, sizeof(unsigned long long) * h->d_cnt.n, s));
     // the scales stay on the device (kernels read them through QuartetTask::scales): no host synchronisation inside the
     // build; the range check happens after the caller's synchronisation (check_scales)
     CUDA_TRY(cudaEventRecord(h->ev[1], s));
@@ -1132,7 +1292,8 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
         for (int x = 0; x < nk; x++) { qt.Dk[x] = h->d_Dcart[1 + x].p; qt.accK[x] = (long long*)acc + (size_t)(1 + x) * n2c; }
         qt.accJ = (long long*)acc;
         qt.nj = 1; qt.Dj[0] = qt.Dtot; qt.accJm[0] = qt.accJ;
-        qt.scales = h->d_scales.p; qt.nq_done = h->d_nq.p;
+        qt.jlo_off = (long long)((size_t)(1 + nk) * n2c);
+        qt.scales = tail; qt.cnt = h->d_cnt.p + (size_t)t->index * CF_CNT_WORDS;
         qt.store = nullptr; qt.diag = 0; qt.prim_cut = 1e-22;
         fill_rys(qt, h);
         cudaStream_t ts = (it % 4 == 0) ? s : h->side[it % 4 - 1];
@@ -1149,13 +1310,16 @@ extern "C" int cf_finalize_device(cf_handle* h, int nbf, const int64_t* acc, dou
                                   double* J, double* Kd, double* Ka, double* Kb, void* stream) {
     if (!h || !acc || !J) return CF_ERR_BAD_ARGUMENT;
     if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     const int ns = h->nshell, ncart = h->ncart;
     const size_t n2c = (size_t)ncart * ncart, n2p = (size_t)nbf * nbf;
+    const int nk = exx > 0.0 ? (has_d != 0) + (has_a != 0) + (has_b != 0) : 0;      // layout of THIS accumulator
+    const long long* a = (const long long*)acc;
+    const double* tail = reinterpret_cast<const double*>(a + (size_t)(2 + nk) * n2c);
     dim3 grid2(ns, ns);
     // J = 1/4 (raw + raw^T), K = 1/8 (raw + raw^T) * EXX   (Int4C2E.cpp:661-670)
-    finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, (const long long*)acc, h->d_scales.p, 0, 0.25, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
+    finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, a, a + (size_t)(1 + nk) * n2c, tail, 0, 0.25, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
                                          h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, J);
     h->stats.n_launches_last++;
     double* outs[3] = {Kd, Ka, Kb};
@@ -1165,7 +1329,7 @@ extern "C" int cf_finalize_device(cf_handle* h, int nbf, const int64_t* acc, dou
         if (!has[k]) continue;
         if (!outs[k]) { set_error(h, "K output missing for a density that was given"); return CF_ERR_BAD_ARGUMENT; }
         if (exx > 0.0) {
-            finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, (const long long*)acc + (size_t)(1 + x) * n2c, h->d_scales.p, 1, 0.125 * exx,
+            finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, a + (size_t)(1 + x) * n2c, nullptr, tail, 1, 0.125 * exx,
                                                  h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, outs[k]);
             h->stats.n_launches_last++;
             x++;
@@ -1181,22 +1345,37 @@ extern "C" int cf_finalize_device(cf_handle* h, int nbf, const int64_t* acc, dou
 extern "C" int cf_build_jk_device(cf_handle* h, int nbf, const double* Dd, const double* Da, const double* Db, double exx,
                                   double* J, double* Kd, double* Ka, double* Kb, void* stream) {
     if (!h) return CF_ERR_BAD_ARGUMENT;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     int rc = cf_accumulate_device(h, nbf, Dd, Da, Db, exx, (int64_t*)h->d_acc.p, stream);
     if (rc != CF_OK) return rc;
     rc = cf_finalize_device(h, nbf, (const int64_t*)h->d_acc.p, exx, Dd != nullptr, Da != nullptr, Db != nullptr, J, Kd, Ka, Kb, stream);
     return rc;
 }
 
-// after a build has been synchronised: J/K scales and bounds of that build -> stats, and the range check.
-// 62 bits below the rigorous bound are always available; the only way to leave the representable range is a
-// non-finite or astronomically large density
+// after a build has been synchronised: J/K scales and bounds of that build -> stats, the work counters, and the range
+// check.  The scale leaves 2^-10 of head room above the rigorous bound of the final values; the only way to leave the
+// representable range is a non-finite or astronomically large density
 static int check_scales(cf_handle* h) {
     const double* sc = h->scales_host;
     h->stats.fixedpoint_scale_log2[0] = std::log2(sc[0]);
     h->stats.fixedpoint_scale_log2[1] = std::log2(sc[1]);
     h->stats.threshold_effective_last = sc[4];
-    { unsigned long long tot = 0; for (int i = 0; i < CF_NQ_SLOTS; i++) tot += h->nq_host[i]; h->stats.quartets_evaluated_last = (int64_t)tot; }
+    h->stats.j_two_limb_last = sc[6] != 0.0 ? 1 : 0;
+    h->stats.j_rounding_estimate_last = sc[7];
+    {   // per-task counters -> evaluated shell quartets, EXECUTED primitive quartets and the model flops they stand for
+        unsigned long long nq = 0, np = 0;
+        double fl = 0.0;
+        for (const ClassPairTask* t : h->tasks) {
+            const unsigned long long* c = h->cnt_host.data() + (size_t)t->index * CF_CNT_WORDS;
+            unsigned long long q = 0, pq = 0;
+            for (int i = 0; i < CF_CNT_SLOTS; i++) { q += c[i]; pq += c[CF_CNT_SLOTS + i]; }
+            nq += q; np += pq;
+            fl += (double)pq * t->per_prim + 2.0 * (2 + 4 * h->last_nk) * (double)q * t->nfun_q;
+        }
+        h->stats.quartets_evaluated_last = (int64_t)nq;
+        h->stats.primitive_quartets_executed_last = (int64_t)np;
+        h->stats.flops_executed_last = fl;
+    }
     if (!(sc[0] > 0x1p-900) || !(sc[1] > 0x1p-900) || !std::isfinite(sc[2]) || !std::isfinite(sc[3])) {
         set_error(h, "fixed-point accumulator range exceeded: density contains non-finite or astronomically large entries");
         return CF_ERR_RANGE;
@@ -1212,12 +1391,21 @@ static int fetch_times(cf_handle* h) {
     return CF_OK;
 }
 
+// scale tail + work counters of the last build -> host (enqueued on stream s)
+static int fetch_build_info(cf_handle* h, cudaStream_t s) {
+    if (!h->last_tail) return CF_OK;
+    CUDA_TRY(cudaMemcpyAsync(h->scales_host, h->last_tail, sizeof(h->scales_host), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h->cnt_host.data(), h->d_cnt.p, sizeof(unsigned long long) * h->cnt_host.size(), cudaMemcpyDeviceToHost, s));
+    return CF_OK;
+}
+
 extern "C" int cf_sync_stats(cf_handle* h) {   // after a *_device call has been synchronised by the caller
     if (!h) return CF_ERR_BAD_ARGUMENT;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     fetch_times(h);
-    CUDA_TRY(cudaMemcpy(h->scales_host, h->d_scales.p, sizeof(h->scales_host), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(h->nq_host, h->d_nq.p, sizeof(h->nq_host), cudaMemcpyDeviceToHost));
+    int rc = fetch_build_info(h, 0);
+    if (rc != CF_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(0));
     return check_scales(h);
 }
 
@@ -1228,7 +1416,7 @@ extern "C" int cf_build_jk(cf_handle* h, int nbf, const double* Dd, const double
     if (!J) { set_error(h, "J output is required"); return CF_ERR_BAD_ARGUMENT; }
     if (!Dd && !Da && !Db) { set_error(h, "at least one density is required"); return CF_ERR_BAD_ARGUMENT; }
     if ((Dd && !Kd) || (Da && !Ka) || (Db && !Kb)) { set_error(h, "K output missing for a density that was given"); return CF_ERR_BAD_ARGUMENT; }
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const double t0 = now_s();
     if (h->opt.verbose > 0) std::printf("Contracting 4c-2e repulsion integrals with 1 matrix ... ");
     const size_t bytes = sizeof(double) * (size_t)nbf * nbf;
@@ -1242,8 +1430,8 @@ extern "C" int cf_build_jk(cf_handle* h, int nbf, const double* Dd, const double
     double* outs[3] = {Kd, Ka, Kb};
     for (int k = 0; k < 3; k++)
         if (src[k]) CUDA_TRY(cudaMemcpyAsync(outs[k], h->d_out[1 + k].p, bytes, cudaMemcpyDeviceToHost, 0));
-    CUDA_TRY(cudaMemcpyAsync(h->scales_host, h->d_scales.p, sizeof(h->scales_host), cudaMemcpyDeviceToHost, 0));
-    CUDA_TRY(cudaMemcpyAsync(h->nq_host, h->d_nq.p, sizeof(h->nq_host), cudaMemcpyDeviceToHost, 0));
+    rc = fetch_build_info(h, 0);
+    if (rc != CF_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(0));
     CUDA_TRY(cudaGetLastError());
     fetch_times(h);
@@ -1253,10 +1441,12 @@ extern "C" int cf_build_jk(cf_handle* h, int nbf, const double* Dd, const double
 }
 
 // Per-class-pair timing of the last densities' build (serialised, CUDA events): the measurement behind the
-// per-kernel roofline table.  rows of 6 doubles: bra class, ket class, quartets, ms, F_alg (for nk), group size
+// per-kernel roofline table.  rows of 8 doubles: bra class, ket class, quartets, ms, F_alg at nominal contraction (for nk),
+// group size, primitive quartets EXECUTED by the launch, model flops of those (+ digestion of the evaluated quartets)
 extern "C" int cf_profile_tasks(cf_handle* h, int nbf, const double* Dd_dev, const double* Da_dev, const double* Db_dev, double exx,
                                 double* rows, int max_rows, int* nrows) {
     if (!h || !rows || !nrows) return CF_ERR_BAD_ARGUMENT;
+    DeviceGuard guard(h->device);
     int rc = cf_accumulate_device(h, nbf, Dd_dev, Da_dev, Db_dev, exx, (int64_t*)h->d_acc.p, nullptr);   // sets densities + scales
     if (rc != CF_OK) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
@@ -1266,17 +1456,20 @@ extern "C" int cf_profile_tasks(cf_handle* h, int nbf, const double* Dd_dev, con
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     int n = 0;
+    std::vector<unsigned long long> c(CF_CNT_WORDS);
     for (ClassPairTask* t : h->tasks) {
         if (n >= max_rows) break;
         QuartetTask qt{};
         qt.rank = h->opt.rank; qt.world = h->opt.world_size; qt.ncart = h->ncart; qt.nk = nk;
         qt.Dtot = h->d_Dcart[0].p;
         for (int x = 0; x < nk; x++) { qt.Dk[x] = h->d_Dcart[1 + x].p; qt.accK[x] = h->d_acc.p + (size_t)(1 + x) * n2c; }
-        qt.accJ = h->d_acc.p; qt.scales = h->d_scales.p; qt.prim_cut = 1e-22;
-        qt.nj = 1; qt.Dj[0] = qt.Dtot; qt.accJm[0] = qt.accJ;
+        qt.accJ = h->d_acc.p; qt.scales = reinterpret_cast<const double*>(h->d_acc.p + (size_t)(2 + nk) * n2c); qt.prim_cut = 1e-22;
+        qt.nj = 1; qt.Dj[0] = qt.Dtot; qt.accJm[0] = qt.accJ; qt.jlo_off = (long long)((size_t)(1 + nk) * n2c);
+        qt.cnt = h->d_cnt.p + (size_t)t->index * CF_CNT_WORDS;
         fill_rys(qt, h);
         float best = 1e30f;
         for (int rep = 0; rep < 2; rep++) {
+            CUDA_TRY(cudaMemsetAsync(qt.cnt, 0, sizeof(unsigned long long) * CF_CNT_WORDS, 0));
             cudaEventRecord(e0, 0);
             rc = launch_task(h, t, qt, 0, 0);
             cudaEventRecord(e1, 0);
@@ -1285,9 +1478,13 @@ extern "C" int cf_profile_tasks(cf_handle* h, int nbf, const double* Dd_dev, con
             float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
             best = std::min(best, ms);
         }
-        double* r = rows + 6 * n;
+        CUDA_TRY(cudaMemcpy(c.data(), qt.cnt, sizeof(unsigned long long) * CF_CNT_WORDS, cudaMemcpyDeviceToHost));
+        unsigned long long q = 0, pq = 0;
+        for (int i = 0; i < CF_CNT_SLOTS; i++) { q += c[i]; pq += c[CF_CNT_SLOTS + i]; }
+        double* r = rows + 8 * n;
         r[0] = t->bra; r[1] = t->ket; r[2] = (double)t->nquartet / h->opt.world_size; r[3] = best;
         r[4] = (t->flops_eri + 2.0 * (2 + 4 * nk) * t->nfun_sum) / h->opt.world_size; r[5] = t->G;
+        r[6] = (double)pq; r[7] = (double)pq * t->per_prim + 2.0 * (2 + 4 * nk) * (double)q * t->nfun_q;
         n++;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -1310,7 +1507,7 @@ extern "C" int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const 
     if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
     if (h->shell2atom.empty()) { set_error(h, "cf_contract_grads needs cf_basis.shell2atom"); return CF_ERR_BAD_ARGUMENT; }
     for (int a : h->shell2atom) if (a < 0 || a >= natom) { set_error(h, "shell2atom entry outside [0, natom)"); return CF_ERR_BAD_ARGUMENT; }
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const int ns = h->nshell, ncart = h->ncart, ngrad = 3 * natom;
     const size_t bytes = sizeof(double) * (size_t)nbf * nbf, ns2 = (size_t)ns * ns;
     const int max_grid = 148 * 8;
@@ -1395,7 +1592,9 @@ static int build_g_batch(cf_handle* h, int nmat, double exx) {
     const size_t n2c = (size_t)ncart * ncart, ns2 = (size_t)ns * ns, n2p = (size_t)nbf * nbf;
     const int nk = exx > 0.0 ? nmat : 0;
     cudaStream_t s = 0;
-    long long* acc = h->d_acc.p;
+    long long* acc = h->d_acc.p;                 // [J_0..J_2 | K_0..K_2 | Jlo_0..Jlo_2 | tail]
+    double* tail = reinterpret_cast<double*>(acc + 9 * n2c);
+    h->last_tail = (const long long*)tail; h->last_nk = nk;
     h->stats.n_launches_last = 0;
     CUDA_TRY(cudaEventRecord(h->ev[0], s));
     dim3 grid2(ns, ns);
@@ -1405,10 +1604,11 @@ static int build_g_batch(cf_handle* h, int nmat, double exx) {
                                                  h->d_B.p + (size_t)(1 + k) * ns2, h->d_Bmax.p + (size_t)(1 + k) * ns2);
     rowmax_kernel<<<(int)((ns2 + 255) / 256), 256, 0, s>>>((int)ns2, nmat, h->d_B.p, h->d_Bmax.p);
     bounds_kernel<<<1 + nmat, 1024, 0, s>>>(ns, h->d_QS.p, h->d_B.p, h->d_Bmax.p, h->d_rwork.p, h->d_partial.p);
-    scales_kernel<<<1, 32, 0, s>>>(h->d_partial.p, nmat, h->qmax_cart, h->opt.threshold, h->density_threshold, h->d_scales.p);
+    scales_kernel<<<1, 32, 0, s>>>(h->d_partial.p, nmat, h->qmax_cart, h->opt.threshold, h->density_threshold,
+                                   (double)h->stats.shell_pairs_kept, h->opt.j_two_limb, tail);
     h->stats.n_launches_last += nmat + 3;
-    CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * 6 * n2c, s));
-    CUDA_TRY(cudaMemsetAsync(h->d_nq.p, 0, sizeof(unsigned long long) * CF_NQ_SLOTS, s));
+    CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * 9 * n2c, s));
+    CUDA_TRY(cudaMemsetAsync(h->d_cnt.p, 0, sizeof(unsigned long long) * h->d_cnt.n, s));
     CUDA_TRY(cudaEventRecord(h->ev[1], s));
     CUDA_TRY(cudaEventRecord(h->ev_fork, s));
     for (int i = 0; i < 3; i++) CUDA_TRY(cudaStreamWaitEvent(h->side[i], h->ev_fork, 0));
@@ -1422,7 +1622,8 @@ static int build_g_batch(cf_handle* h, int nmat, double exx) {
             qt.Dk[x] = h->d_Dcart[1 + x].p; qt.accK[x] = acc + (size_t)(3 + x) * n2c;
         }
         qt.Dtot = qt.Dj[0]; qt.accJ = qt.accJm[0];
-        qt.scales = h->d_scales.p; qt.nq_done = h->d_nq.p;
+        qt.jlo_off = (long long)(6 * n2c);
+        qt.scales = tail; qt.cnt = h->d_cnt.p + (size_t)t->index * CF_CNT_WORDS;
         qt.store = nullptr; qt.diag = 0; qt.prim_cut = 1e-22;
         fill_rys(qt, h);
         cudaStream_t ts = (it % 4 == 0) ? s : h->side[it % 4 - 1];
@@ -1434,11 +1635,11 @@ static int build_g_batch(cf_handle* h, int nmat, double exx) {
     CUDA_TRY(cudaEventRecord(h->ev[2], s));
     // G_k = J[2 D_k] - exx K[D_k] = 1/2 (rawJ + rawJ^T) - exx/8 (rawK + rawK^T)   (Int4C2E.cpp:726-728 with the J of D_k, not 2 D_k)
     for (int k = 0; k < nmat; k++) {
-        finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, acc + (size_t)k * n2c, h->d_scales.p, 0, 0.5, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
+        finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, acc + (size_t)k * n2c, acc + (size_t)(6 + k) * n2c, tail, 0, 0.5, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
                                              h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, nk ? h->d_out[3].p : h->d_out[k].p);
         h->stats.n_launches_last++;
         if (nk) {
-            finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, acc + (size_t)(3 + k) * n2c, h->d_scales.p, 1, 0.125 * exx, h->d_ctrans.p, h->d_ct_off.p,
+            finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, acc + (size_t)(3 + k) * n2c, nullptr, tail, 1, 0.125 * exx, h->d_ctrans.p, h->d_ct_off.p,
                                                  h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dpure[k].p);   // D_k is consumed: reuse its buffer
             sub_kernel<<<(int)((n2p + 255) / 256), 256, 0, s>>>(n2p, h->d_out[3].p, h->d_Dpure[k].p, h->d_out[k].p);
             h->stats.n_launches_last += 2;
@@ -1453,7 +1654,7 @@ static int build_g_batch(cf_handle* h, int nmat, double exx) {
 extern "C" int cf_build_g_multi(cf_handle* h, int nbf, int nmat, const double* Ds, double exx, double* Gs) {
     if (!h || !Ds || !Gs || nmat <= 0) return CF_ERR_BAD_ARGUMENT;
     if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const size_t n2 = (size_t)nbf * nbf, bytes = sizeof(double) * n2;
     for (int k0 = 0; k0 < nmat; k0 += 3) {
         const int nb = std::min(3, nmat - k0);
@@ -1461,8 +1662,8 @@ extern "C" int cf_build_g_multi(cf_handle* h, int nbf, int nmat, const double* D
         int rc = build_g_batch(h, nb, exx);
         if (rc != CF_OK) return rc;
         for (int k = 0; k < nb; k++) CUDA_TRY(cudaMemcpyAsync(Gs + (size_t)(k0 + k) * n2, h->d_out[k].p, bytes, cudaMemcpyDeviceToHost, 0));
-        CUDA_TRY(cudaMemcpyAsync(h->scales_host, h->d_scales.p, sizeof(h->scales_host), cudaMemcpyDeviceToHost, 0));
-        CUDA_TRY(cudaMemcpyAsync(h->nq_host, h->d_nq.p, sizeof(h->nq_host), cudaMemcpyDeviceToHost, 0));
+        rc = fetch_build_info(h, 0);
+        if (rc != CF_OK) return rc;
         CUDA_TRY(cudaStreamSynchronize(0));
         CUDA_TRY(cudaGetLastError());
         fetch_times(h);

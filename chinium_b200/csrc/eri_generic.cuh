@@ -114,6 +114,19 @@ __device__ __forceinline__ void fixed_add(long long* addr, double v, double scal
     const long long q = __double2ll_rn(v * scale);
     atomicAdd(reinterpret_cast<unsigned long long*>(addr), static_cast<unsigned long long>(q));
 }
+// J adds: high limb as above; with jlo != 0 the rounding residual (exact in FP64: |x| < 2^52 -> x - rn(x) is
+// representable, larger x are integers) is added, scaled by 2^31, to the low limb `jlo` words further on.
+// Partial sums may wrap around 2^64 in either limb: integer addition is exact modulo 2^64 and only the FINAL value has
+// to fit, which the scale guarantees (scales_kernel in engine.cu).
+__device__ __forceinline__ void fixed_add_j(long long* addr, long long jlo, double v, double scale) {
+    const double x = v * scale;
+    const long long q = __double2ll_rn(x);
+    atomicAdd(reinterpret_cast<unsigned long long*>(addr), static_cast<unsigned long long>(q));
+    if (jlo) {
+        const long long ql = __double2ll_rn((x - (double)q) * 0x1p31);
+        atomicAdd(reinterpret_cast<unsigned long long*>(addr + jlo), static_cast<unsigned long long>(ql));
+    }
+}
 
 template <int LA, int LB, int LC, int LD, int G, bool STORE>
 __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
@@ -126,6 +139,8 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
     extern __shared__ double smem[];
     const double scaleJ = STORE ? 1.0 : __ldg(t.scales), scaleK = STORE ? 1.0 : __ldg(t.scales + 1);
     const double thr = STORE ? t.thr : __ldg(t.scales + 4);   // effective Schwarz threshold of this build (scales_kernel)
+    const long long jlo = (!STORE && __ldg(t.scales + 6) != 0.0) ? t.jlo_off : 0;
+    unsigned cnt_q = 0, cnt_p = 0;          // evaluated shell quartets / executed primitive quartets (lane 0 counts)
     double* rw = smem;
     double* g = rw + 2 * NROOTS;
     double* V = g + NROOTS * 3 * GSZ;
@@ -180,7 +195,7 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
             const double Cx = t.ket.A[3 * ik], Cy = t.ket.A[3 * ik + 1], Cz = t.ket.A[3 * ik + 2];
             const double CDx = t.ket.AB[3 * ik], CDy = t.ket.AB[3 * ik + 1], CDz = t.ket.AB[3 * ik + 2];
             if (thr > 0.0 && !(t.bra.Q[ib] * t.ket.Q[ik] > thr)) continue;   // uniform across the CTA
-            if (!STORE && lane == 0 && t.nq_done) atomicAdd(t.nq_done + cf_nq_slot(), 1ull);
+            if (lane == 0) cnt_q++;
             const int pab0 = t.bra.pbase[ib], npab = t.bra.nprim[ib];
             const int pcd0 = t.ket.pbase[ik], npcd = t.ket.nprim[ik];
             double wgt = (sa == sb ? 1.0 : 2.0) * (sc == sd ? 1.0 : 2.0);
@@ -198,6 +213,7 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
                     const int scd = pcd0 + icd * CF_PSTRIDE;
                     const double ccd = t.ket.c[scd];
                     if (fabs(cab * ccd) < t.prim_cut) continue;   // uniform across the CTA
+                    if (lane == 0) cnt_p++;
                     const double qe = t.ket.p[scd];
                     const double Qx = t.ket.Px[scd], Qy = t.ket.Py[scd], Qz = t.ket.Pz[scd];
                     const double pq = p + qe;
@@ -275,11 +291,11 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
                 double s = 0.0;
                 if (e < NAB) {
                     for (int kl = 0; kl < NCD; kl++) s = fma(V[e * NCD + kl], Dcd[kl], s);
-                    fixed_add(t.accJ + (size_t)(cb + e % NB) * ld + ca + e / NB, s, scaleJ);
+                    fixed_add_j(t.accJ + (size_t)(cb + e % NB) * ld + ca + e / NB, jlo, s, scaleJ);
                 } else {
                     const int kl = e - NAB;
                     for (int ij = 0; ij < NAB; ij++) s = fma(V[ij * NCD + kl], Dab[ij], s);
-                    fixed_add(t.accJ + (size_t)(cdd + kl % ND) * ld + cc + kl / ND, s, scaleJ);
+                    fixed_add_j(t.accJ + (size_t)(cdd + kl % ND) * ld + cc + kl / ND, jlo, s, scaleJ);
                 }
             }
             for (int xj = 1; xj < t.nj; xj++) {   // further Coulomb densities of the multi-density build: D read from global memory
@@ -289,11 +305,11 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
                     double s = 0.0;
                     if (e < NAB) {
                         for (int kl = 0; kl < NCD; kl++) s = fma(V[e * NCD + kl], DJ[(size_t)(cdd + kl % ND) * ld + cc + kl / ND], s);
-                        fixed_add(aJ + (size_t)(cb + e % NB) * ld + ca + e / NB, s, scaleJ);
+                        fixed_add_j(aJ + (size_t)(cb + e % NB) * ld + ca + e / NB, jlo, s, scaleJ);
                     } else {
                         const int kl = e - NAB;
                         for (int ij = 0; ij < NAB; ij++) s = fma(V[ij * NCD + kl], DJ[(size_t)(cb + ij % NB) * ld + ca + ij / NB], s);
-                        fixed_add(aJ + (size_t)(cdd + kl % ND) * ld + cc + kl / ND, s, scaleJ);
+                        fixed_add_j(aJ + (size_t)(cdd + kl % ND) * ld + cc + kl / ND, jlo, s, scaleJ);
                     }
                 }
             }
@@ -332,6 +348,7 @@ __global__ void __launch_bounds__(G) eri_jk_generic(const QuartetTask t) {
             __syncthreads();   // V / D blocks are reused by the next quartet
         }
     }
+    if (!STORE && threadIdx.x < 32) cf_cnt_flush(t.cnt, cnt_q, cnt_p);
 }
 
 template <int LA, int LB, int LC, int LD>

@@ -164,6 +164,8 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
     extern __shared__ double smem[];
     const double scaleJ = __ldg(t.scales), scaleK = __ldg(t.scales + 1);
     const double thr = __ldg(t.scales + 4);   // effective Schwarz threshold of this build (scales_kernel)
+    const long long jlo = __ldg(t.scales + 6) != 0.0 ? t.jlo_off : 0;
+    unsigned cnt_q = 0, cnt_p = 0;            // this lane's evaluated shell quartets / executed primitive quartets
     double* tab = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* sbra = smem + TABLEN + warp * (TPQ_NBRA * MAXBP);   // this warp's [TPQ_NBRA][MAXBP]
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
         {   // warp-uniform: skip items whose quartets are all screened out; count the evaluated ones
             const unsigned amask = __ballot_sync(0xffffffffu, active);
             if (!amask) continue;
-            if (lane == 0 && t.nq_done) atomicAdd(t.nq_done + cf_nq_slot(), (unsigned long long)__popc(amask));
+            cnt_q += active ? 1u : 0u;
         }
 
         // bra pair: uniform across the warp
@@ -265,6 +267,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
                 for (int iab = 0; iab < nb; iab++) {
                     const double cc = sbra[5 * MAXBP + iab] * ccd;
                     if (fabs(cc) < t.prim_cut) continue;
+                    cnt_p++;
                     const double p = sbra[iab], hp = sbra[MAXBP + iab];
                     const double PQx = sbra[2 * MAXBP + iab] - Qx, PQy = sbra[3 * MAXBP + iab] - Qy,
                                  PQz = sbra[4 * MAXBP + iab] - Qz;
@@ -321,11 +324,11 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
                 }
                 // the bra pair is common to the warp's 32 quartets: one add per element and warp instead of 32
                 s = warp_sum_fixed(s);
-                if (lane == 0) fixed_add(aJ + off, s, scaleJ);
+                if (lane == 0) fixed_add_j(aJ + off, jlo, s, scaleJ);
             }
             if (active) {
 #pragma unroll
-                for (int kl = 0; kl < NCD; kl++) fixed_add(aJ + (cd0 + kl % ND) * ld + cc0 + kl / ND, jcd[kl], scaleJ);
+                for (int kl = 0; kl < NCD; kl++) fixed_add_j(aJ + (cd0 + kl % ND) * ld + cc0 + kl / ND, jlo, jcd[kl], scaleJ);
             }
         }
         if (!active) continue;
@@ -398,6 +401,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
             }
         }
     }
+    cf_cnt_flush(t.cnt, cnt_q, cnt_p);
 }
 
 // ================================================================================================
@@ -513,6 +517,8 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
     extern __shared__ double smem[];
     const double scaleJ = __ldg(t.scales), scaleK = __ldg(t.scales + 1);
     const double thr = __ldg(t.scales + 4);   // effective Schwarz threshold of this build (scales_kernel)
+    const long long jlo = __ldg(t.scales + 6) != 0.0 ? t.jlo_off : 0;
+    unsigned cnt_q = 0, cnt_p = 0;            // counted by slice 0 of every quartet
     double* tab = smem;
     double* sbra = smem + TABLEN;                   // [TPQ_NBRA][TPQ_MAXBP]
     double* part = sbra + TPQ_NBRA * TPQ_MAXBP;     // [VC][GS][NQ]
@@ -545,10 +551,7 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
         const int ik = it.y + q;
         bool active = q < it.z;
         if (active && thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > thr;
-        if (s == 0 && t.nq_done) {   // count the evaluated quartets (slice 0 of every quartet lives in the first warps)
-            const unsigned amask = __ballot_sync(0xffffffffu, active);
-            if ((threadIdx.x & 31) == 0 && amask) atomicAdd(t.nq_done + cf_nq_slot(), (unsigned long long)__popc(amask));
-        }
+        if (s == 0 && active) cnt_q++;   // slice 0 of every quartet counts
 
         const int sa = t.bra.sa[ib], sb = t.bra.sb[ib];
         const double Ax = t.bra.A[3 * ib], Ay = t.bra.A[3 * ib + 1], Az = t.bra.A[3 * ib + 2];
@@ -596,6 +599,7 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                 for (int iab = 0; iab < nb; iab++) {
                     const double cc = sbra[5 * TPQ_MAXBP + iab] * ccd;
                     if (fabs(cc) < t.prim_cut) continue;
+                    if (s == 0) cnt_p++;
                     const double p = sbra[iab], hp = sbra[TPQ_MAXBP + iab];
                     const double PQx = sbra[2 * TPQ_MAXBP + iab] - Qx, PQy = sbra[3 * TPQ_MAXBP + iab] - Qy,
                                  PQz = sbra[4 * TPQ_MAXBP + iab] - Qz;
@@ -642,7 +646,7 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
         const size_t ld = (size_t)t.ncart;
         const int ia0 = s * MA;
         // cross-slice sum of NV partial values through shared memory, chunk by chunk, then one fixed-point add each
-        auto reduce_add = [&](auto nv_tag, const double* pv, auto&& addr_of, long long* acc, double scale) {
+        auto reduce_add = [&](auto nv_tag, const double* pv, auto&& addr_of, long long* acc, double scale, long long lo) {
             constexpr int NV = decltype(nv_tag)::value;
 #pragma unroll
             for (int c0 = 0; c0 < NV; c0 += VC) {
@@ -658,7 +662,7 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                         double sum = 0.0;
 #pragma unroll
                         for (int s2 = 0; s2 < GS; s2++) sum += part[(v * GS + s2) * NQ + q];
-                        fixed_add(acc + addr_of(c0 + v), sum, scale);
+                        fixed_add_j(acc + addr_of(c0 + v), lo, sum, scale);
                     }
             }
         };
@@ -682,10 +686,10 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                     }
                     // the bra pair and the slice are warp-uniform: one add per element and warp
                     sum = warp_sum_fixed(sum);
-                    if ((threadIdx.x & 31) == 0) fixed_add(aJ + off, sum, scaleJ);
+                    if ((threadIdx.x & 31) == 0) fixed_add_j(aJ + off, jlo, sum, scaleJ);
                 }
             reduce_add(std::integral_constant<int, NCD>{}, jcd,
-                       [&](int kl) { return (size_t)(cd0 + kl % ND) * ld + cc0 + kl / ND; }, aJ, scaleJ);
+                       [&](int kl) { return (size_t)(cd0 + kl % ND) * ld + cc0 + kl / ND; }, aJ, scaleJ, jlo);
         }
         for (int x = 0; x < t.nk; x++) {
             const double* __restrict__ D = t.Dk[x];
@@ -751,7 +755,8 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                            if (e < NB * NC) return (size_t)(cb + e / NC) * ld + cc0 + e % NC;
                            const int f = e - NB * NC;
                            return (size_t)(cb + f / ND) * ld + cd0 + f % ND;
-                       }, acc, scaleK);
+                       }, acc, scaleK, 0LL);
         }
     }
+    cf_cnt_flush(t.cnt, cnt_q, cnt_p);
 }

@@ -65,6 +65,8 @@ eri_jk_tpqa(const QuartetTask t) {
     extern __shared__ double smem[];
     const double scaleJ = __ldg(t.scales), scaleK = __ldg(t.scales + 1);
     const double thr = __ldg(t.scales + 4);   // effective Schwarz threshold of this build (scales_kernel)
+    const long long jlo = __ldg(t.scales + 6) != 0.0 ? t.jlo_off : 0;
+    unsigned cnt_q = 0, cnt_p = 0;            // this lane's evaluated shell quartets / executed primitive quartets
     double* tab = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* sbra = smem + TABLEN + warp * (TPQ_NBRA * MAXBP);   // this warp's [TPQ_NBRA][MAXBP]
@@ -204,6 +206,7 @@ eri_jk_tpqa(const QuartetTask t) {
             const unsigned amask = __ballot_sync(0xffffffffu, act);
             if (!amask) { rotate(); continue; }
             nact += __popc(amask);
+            cnt_q += act ? 1u : 0u;
 
             const int sb = ri0.y & 0xffff, cb = ri0.z;
             const double ABx = rq0.y, ABy = rz0.x, ABz = rz0.y;
@@ -230,6 +233,7 @@ eri_jk_tpqa(const QuartetTask t) {
                     for (int iab = 0; iab < nb; iab++) {
                         const double cc = sbra[5 * MAXBP + iab] * ccd;
                         if (fabs(cc) < t.prim_cut) continue;
+                        cnt_p++;
                         const double p = sbra[iab], hp = sbra[MAXBP + iab];
                         const double PQx = sbra[2 * MAXBP + iab] - Qx, PQy = sbra[3 * MAXBP + iab] - Qy,
                                      PQz = sbra[4 * MAXBP + iab] - Qz;
@@ -281,7 +285,7 @@ eri_jk_tpqa(const QuartetTask t) {
                         jcd[xj * NCD + kl] = fma(gout[ij * NCD + kl], dab, jcd[xj * NCD + kl]);
                     }
                     s = warp_sum_fixed(s);
-                    if (lane == 0) fixed_add(aJ + off, s, scaleJ);
+                    if (lane == 0) fixed_add_j(aJ + off, jlo, s, scaleJ);
                 }
             }
             if (!act) continue;
@@ -367,13 +371,12 @@ eri_jk_tpqa(const QuartetTask t) {
 
         // ---- flush what accumulated over the chunk ---------------------------------------------------------------
         if (nact == 0) continue;   // warp-uniform: nothing was evaluated
-        if (lane == 0 && t.nq_done) atomicAdd(t.nq_done + cf_nq_slot(), (unsigned long long)nact);
         if (lane_ok) {
 #pragma unroll
             for (int xj = 0; xj < NJMAX; xj++) {
                 if (xj >= t.nj) break;
 #pragma unroll
-                for (int kl = 0; kl < NCD; kl++) fixed_add(t.accJm[xj] + (cd0 + kl % ND) * ld + cc0 + kl / ND, jcd[xj * NCD + kl], scaleJ);
+                for (int kl = 0; kl < NCD; kl++) fixed_add_j(t.accJm[xj] + (cd0 + kl % ND) * ld + cc0 + kl / ND, jlo, jcd[xj * NCD + kl], scaleJ);
             }
             if constexpr (ACCK) {
 #pragma unroll
@@ -388,4 +391,5 @@ eri_jk_tpqa(const QuartetTask t) {
             }
         }
     }
+    cf_cnt_flush(t.cnt, cnt_q, cnt_p);
 }

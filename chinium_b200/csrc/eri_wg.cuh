@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
     extern __shared__ double smem[];
     const double scaleJ = __ldg(t.scales), scaleK = __ldg(t.scales + 1);
     const double thr = __ldg(t.scales + 4);   // effective Schwarz threshold of this build (scales_kernel)
+    const long long jlo = __ldg(t.scales + 6) != 0.0 ? t.jlo_off : 0;
+    unsigned cnt_q = 0, cnt_p = 0;            // counted by lane g == 0 of every quartet group
     const double* tab = smem;
     const double* asym = smem;
     double* sbra = smem + C::TABLEN;
@@ -216,10 +218,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
         const int ik = it.y + warp * QW + qi;
         bool active = lane_ok && warp * QW + qi < it.z;
         if (active && thr > 0.0) active = t.bra.Q[ib] * t.ket.Q[ik] > thr;
-        if (t.nq_done) {   // count the evaluated quartets
-            const unsigned amask = __ballot_sync(FULL, active && g == 0);
-            if (lane == 0 && amask) atomicAdd(t.nq_done + cf_nq_slot(), (unsigned long long)__popc(amask));
-        }
+        if (active && g == 0) cnt_q++;
 
         const int sa = t.bra.sa[ib], sb = t.bra.sb[ib];
         const double Ax = t.bra.A[3 * ib], Ay = t.bra.A[3 * ib + 1], Az = t.bra.A[3 * ib + 2];
@@ -312,6 +311,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
                     const double cc = sbra[5 * TPQ_MAXBP + iab] * ccd;
                     const bool valid = vk && fabs(cc) >= t.prim_cut;
                     if (!__any_sync(FULL, valid)) continue;      // warp-uniform
+                    if constexpr (decltype(hp_tag)::value == 0) { if (valid && g == 0) cnt_p++; }   // counted once, not per H pass
                     const double p = sbra[iab], hp = sbra[TPQ_MAXBP + iab];
                     const double PQx = sbra[2 * TPQ_MAXBP + iab] - Qx, PQy = sbra[3 * TPQ_MAXBP + iab] - Qy,
                                  PQz = sbra[4 * TPQ_MAXBP + iab] - Qz;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
             }
 #pragma unroll
             for (int m = 0; m < MK; m++)
-                if (active && fok[m]) fixed_add(aJ + (cd0 + fid[m]) * ld + cc0 + fic[m], jcd[m], scaleJ);
+                if (active && fok[m]) fixed_add_j(aJ + (cd0 + fid[m]) * ld + cc0 + fic[m], jlo, jcd[m], scaleJ);
             __syncwarp();
             // J(a,b) is common to every quartet of the item: sum over ALL active quartets of the warp (fixed order) and
             // issue one add per element and warp; lanes map to consecutive rows i, i.e. consecutive addresses
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
 #pragma unroll
                             for (int g2 = 0; g2 < GS; g2++) s += wq[(size_t)q2 * C::SCR + e * GS + g2];
                         }
-                    if (amask) fixed_add(aJ + (cb + j) * ld + ca + IA0 + i, s, scaleJ);
+                    if (amask) fixed_add_j(aJ + (cb + j) * ld + ca + IA0 + i, jlo, s, scaleJ);
                 }
             }
             __syncwarp();
@@ -487,6 +487,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
         }
         });   // passes over the H components
     }
+    cf_cnt_flush(t.cnt, cnt_q, cnt_p);
 }
 
 // class-pair -> warp-group configuration: MK | (swap << 8) | (HS << 12) | (MINB << 16); 0 = not covered (HS field 0 means

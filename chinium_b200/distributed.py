@@ -52,8 +52,8 @@ class DistributedInt4C2E:
         acc = self._acc[: self.eng.acc_len(nk)]
         self.eng.accumulate_device(ptr(self._D[0], present[0]), ptr(self._D[1], present[1]), ptr(self._D[2], present[2]),
                                    acc.data_ptr(), stream)
-        if self.world > 1:
-            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+        if self.world > 1:   # integer sum of [J | K.. | J low limb]; the scale tail is identical on every rank and stays out
+            dist.all_reduce(acc[: self.eng.acc_reduce_len(nk)], op=dist.ReduceOp.SUM, group=self.group)
         self.eng.finalize_device(acc.data_ptr(), present, self._out[0].data_ptr(), ptr(self._out[1], present[0]),
                                  ptr(self._out[2], present[1]), ptr(self._out[3], present[2]), stream)
 

@@ -32,7 +32,7 @@ class _CfBasis(C.Structure):
 
 class _CfOptions(C.Structure):
     _fields_ = [("threshold", C.c_double), ("pair_cutoff", C.c_double), ("device", C.c_int), ("rank", C.c_int),
-                ("world_size", C.c_int), ("verbose", C.c_int), ("reserved", C.c_int * 8)]
+                ("world_size", C.c_int), ("verbose", C.c_int), ("j_two_limb", C.c_int), ("reserved", C.c_int * 7)]
 
 
 class CfStats(C.Structure):
@@ -43,7 +43,10 @@ class CfStats(C.Structure):
                 ("flops_alg_jk", C.c_double * 4), ("n_launches_last", C.c_int),
                 ("ms_device_last", C.c_double), ("ms_eri_last", C.c_double), ("fixedpoint_scale_log2", C.c_double * 2),
                 ("threshold_effective_last", C.c_double), ("quartets_evaluated_last", C.c_int64),
-                ("flops_alg_grad", C.c_double), ("ms_grad_last", C.c_double)]
+                ("flops_alg_grad", C.c_double), ("ms_grad_last", C.c_double),
+                ("primitive_quartets_executed_last", C.c_int64), ("flops_executed_last", C.c_double),
+                ("j_two_limb_last", C.c_int), ("j_rounding_estimate_last", C.c_double),
+                ("ref_repulsion_length", C.c_int64), ("ref_shell_quartet_length", C.c_int64)]
 
     def as_dict(self):
         d = {}
@@ -80,6 +83,8 @@ def load_library(path: str = LIB_PATH):
     L.cf_build_jk_device.argtypes = [vp, ip, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp]
     L.cf_acc_len.restype = C.c_size_t
     L.cf_acc_len.argtypes = [vp, ip]
+    L.cf_acc_reduce_len.restype = C.c_size_t
+    L.cf_acc_reduce_len.argtypes = [vp, ip]
     L.cf_accumulate_device.argtypes = [vp, ip, vp, vp, vp, C.c_double, vp, vp]
     L.cf_finalize_device.argtypes = [vp, ip, vp, C.c_double, ip, ip, ip, vp, vp, vp, vp, vp]
     L.cf_build_g_multi.argtypes = [vp, ip, ip, dp, C.c_double, dp]
@@ -111,11 +116,11 @@ class Int4C2E:
     """Drop-in mirror of the reference class; `basis` is a chinium_b200.inputs.FlatBasis (the Mwfn stand-in)."""
 
     def __init__(self, basis, exx: float = 1.0, threshold: float = -1.0, device: int = -1, rank: int = 0,
-                 world_size: int = 1, pair_cutoff: float = 0.0):
+                 world_size: int = 1, pair_cutoff: float = 0.0, j_two_limb: int = 0):
         self.MWFN = basis
         self.EXX = float(exx)            # read at contract time, like the reference (SelfConsistentField.cpp:48)
         self.Threshold = float(threshold)
-        self._opts = dict(device=device, rank=rank, world_size=world_size, pair_cutoff=pair_cutoff)
+        self._opts = dict(device=device, rank=rank, world_size=world_size, pair_cutoff=pair_cutoff, j_two_limb=j_two_limb)
         self._h = None
         self._lib = load_library()
         self.RepulsionDiags = None
@@ -143,6 +148,7 @@ class Int4C2E:
         o.rank = self._opts["rank"]
         o.world_size = self._opts["world_size"]
         o.verbose = int(output)
+        o.j_two_limb = int(self._opts["j_two_limb"])
         h = self._lib.cf_create(C.byref(b), C.byref(o))
         if not h:
             raise FockEngineError(self._lib.cf_last_error(None).decode())
@@ -187,8 +193,10 @@ class Int4C2E:
     def getRepulsionLength(self, output=0):
         assert self.RepulsionDiags is not None, "Diagonal elements of repulsion integrals are missing!"  # Int4C2E.cpp:514
         st = self.stats
-        self.RepulsionLength = st["unique_integrals"]
-        self.ShellQuartetLength = st["canonical_quartets"]
+        # the reference's own counts (its loop nest and uniqueness predicate, Int4C2E.cpp:79-128); the engine's work metric
+        # (canonical shell quartets it evaluates) is stats["canonical_quartets"]
+        self.RepulsionLength = st["ref_repulsion_length"]
+        self.ShellQuartetLength = st["ref_shell_quartet_length"]
         if output > 0:
             nb, nsh = st["nbf"], st["nshell"]
             print("Before screening: %d integrals and %d shell quartets" % (
@@ -213,17 +221,29 @@ class Int4C2E:
         self._stage = max(self._stage, 5)
 
     # ---- the hot call -------------------------------------------------------------------------------
-    def ContractInts(self, *args):
-        """ContractInts(Dd, Da, Db, nthreads=1, output=0) or ContractInts([D...], nthreads=1, output=0)."""
+    def ContractInts(self, *args, nthreads=1, output=0):
+        """ContractInts(Dd, Da, Db, nthreads=1, output=0) or ContractInts([D...], nthreads=1, output=0).
+        `nthreads` is accepted and ignored (the GPU partition is the handle's), `output` > 0 prints the reference's line."""
         if len(args) >= 1 and isinstance(args[0], (list, tuple)):
             return self._contract_multi(list(args[0]))
         Dd, Da, Db = (list(args) + [None, None, None])[:3]
         return self._contract(Dd, Da, Db)
 
-    def _contract(self, Dd, Da, Db):
+    def _contract(self, Dd, Da, Db, out=None):
+        """`out`: optional (J, Kd, Ka, Kb) of caller-owned F-ordered nbf x nbf arrays to write into (e.g. views of pinned
+        host memory); entries for absent densities may be None."""
         self._ensure()
         n = self.nbf
         Dd, Da, Db = _fmat(Dd, n), _fmat(Da, n), _fmat(Db, n)
+        if out is not None:
+            J = out[0]
+            Ks = [out[1 + k] if D is not None else None for k, D in enumerate((Dd, Da, Db))]
+            for a in [J] + [k for k in Ks if k is not None]:
+                if a.shape != (n, n) or a.dtype != np.float64 or not a.flags["F_CONTIGUOUS"]:
+                    raise FockEngineError("out matrices must be F-ordered float64 nbf x nbf")
+            self._check(self._lib.cf_build_jk(self._h, n, _dptr(Dd), _dptr(Da), _dptr(Db), self.EXX, _dptr(J),
+                                              _dptr(Ks[0]), _dptr(Ks[1]), _dptr(Ks[2])))
+            return J, Ks[0], Ks[1], Ks[2]
         J = np.zeros((n, n), order="F")
         Ks = [np.zeros((n, n), order="F") if D is not None else None for D in (Dd, Da, Db)]
         self._check(self._lib.cf_build_jk(self._h, n, _dptr(Dd), _dptr(Da), _dptr(Db), self.EXX, _dptr(J),
@@ -235,7 +255,12 @@ class Int4C2E:
     def _contract_multi(self, Ds):
         self._ensure()
         n = self.nbf
-        stack = np.ascontiguousarray(np.stack([np.asfortranarray(D, dtype=np.float64).T for D in Ds]))  # each block col-major
+        if len(Ds) == 0:
+            return []
+        Ds = [_fmat(D, n) for D in Ds]       # shape / dtype check: the C side reads nbf x nbf doubles per matrix
+        if any(D is None for D in Ds):
+            raise FockEngineError("ContractInts([D...]): every matrix must be nbf x nbf (None / 0x0 is not allowed here)")
+        stack = np.ascontiguousarray(np.stack([D.T for D in Ds]))  # each block col-major
         out = np.zeros_like(stack)
         self._check(self._lib.cf_build_g_multi(self._h, n, len(Ds), _dptr(stack), self.EXX, _dptr(out)))
         return [np.asfortranarray(out[k].T) for k in range(len(Ds))]
@@ -257,8 +282,14 @@ class Int4C2E:
 
     # ---- device-resident / multi-GPU building blocks (plain pointers: e.g. torch tensors' data_ptr()) ---
     def acc_len(self, nk):
+        """int64 words to allocate for an accumulator: [J | K.. | J low limb | scale tail]"""
         self._ensure()
         return int(self._lib.cf_acc_len(self._h, nk))
+
+    def acc_reduce_len(self, nk):
+        """leading words that a multi-GPU caller all-reduces (everything but the scale tail)"""
+        self._ensure()
+        return int(self._lib.cf_acc_reduce_len(self._h, nk))
 
     def accumulate_device(self, Dd_ptr, Da_ptr, Db_ptr, acc_ptr, stream=None):
         self._ensure()
@@ -277,12 +308,12 @@ class Int4C2E:
     def profile_tasks(self, Dd_ptr, Da_ptr, Db_ptr):
         """-> list of dicts (bra, ket class names, quartets, ms, flops_alg, group): every class-pair kernel timed alone."""
         self._ensure()
-        rows = np.zeros((64, 6))
+        rows = np.zeros((64, 8))
         n = C.c_int(0)
         self._check(self._lib.cf_profile_tasks(self._h, self.nbf, Dd_ptr, Da_ptr, Db_ptr, self.EXX, _dptr(rows), 64, C.byref(n)))
         names = ["ss", "ps", "pp", "ds", "dp", "dd", "fs", "fp", "fd", "ff"]
         return [dict(bra=names[int(r[0])], ket=names[int(r[1])], quartets=int(r[2]), ms=float(r[3]), flops_alg=float(r[4]),
-                     group=int(r[5])) for r in rows[:n.value]]
+                     group=int(r[5]), prim_executed=int(r[6]), flops_executed=float(r[7])) for r in rows[:n.value]]
 
     def sync_stats(self):
         self._check(self._lib.cf_sync_stats(self._h))   # also the deferred fixed-point range check of that build

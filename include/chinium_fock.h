@@ -61,12 +61,16 @@ typedef struct cf_options {
     double threshold;   /* Cauchy-Schwarz threshold on sqrt((ab|ab)(cd|cd)) as in Int4C2E.cpp:108-113.
                            <= 0 (the reference passes -1): no Schwarz screening; only shell pairs whose
                            largest primitive overlap prefactor is < pair_cutoff are dropped.          */
-    double pair_cutoff; /* 0 -> default 1e-18 (drops nothing that can change J/K at the 1e-12 level)  */
+    double pair_cutoff; /* primitive pairs whose overlap prefactor is below this are dropped at setup; 0 -> default
+                           1e-20 (cannot change J/K at the 1e-12 level).  Shell pairs left without primitives are
+                           not evaluated; the reference-style counts (ref_*) are NOT affected by it                */
     int device;         /* CUDA device ordinal; -1 -> current device                                  */
     int rank;           /* this handle computes partition `rank` of `world_size` (static, cost-       */
     int world_size;     /*  balanced split of the quartet work; 0/0 or 0/1 = everything)              */
     int verbose;        /* >0: print the reference's "... Done in %f s" lines (Int4C2E.cpp:500-587)   */
-    int reserved[8];
+    int j_two_limb;     /* J accumulator low limb: 0 = automatic (switched on per build when the estimated rounding
+                           noise of ~1e6 fixed-point adds per element exceeds 1e-11), 1 = always, -1 = never */
+    int reserved[7];
 } cf_options;
 
 typedef struct cf_handle cf_handle;
@@ -89,6 +93,14 @@ typedef struct cf_stats {
     int64_t quartets_evaluated_last;   /* shell quartets this partition actually evaluated in the last build            */
     double  flops_alg_grad;            /* F_alg of one cf_contract_grads call (DESIGN.md model), this partition          */
     double  ms_grad_last;              /* CUDA-event time of the gradient kernels of the last cf_contract_grads call     */
+    int64_t primitive_quartets_executed_last; /* primitive quartets the last build really ran (device counters): the ones
+                                                 that survive pair_cutoff at setup AND the in-kernel primitive cutoff   */
+    double  flops_executed_last;       /* SURVEY 8d model on EXECUTED work: sum over class pairs of executed primitive
+                                          quartets x per-primitive flops + digestion term of the evaluated quartets     */
+    int     j_two_limb_last;           /* 1: the last build accumulated J in two limbs                                   */
+    double  j_rounding_estimate_last;  /* the estimate the automatic choice was based on (absolute, J units)            */
+    int64_t ref_repulsion_length;      /* the reference's RepulsionLength / ShellQuartetLength (Int4C2E.cpp:79-128):     */
+    int64_t ref_shell_quartet_length;  /*   its own loop nest and uniqueness predicate, independent of pair_cutoff        */
 } cf_stats;
 
 /* cf_create: pair build + Schwarz bounds + class sort + task lists, all on the device.
@@ -134,8 +146,15 @@ int cf_build_jk_device(cf_handle* h, int nbf,
  * fixed point, so the cross-rank sum is an INTEGER all-reduce (ncclInt64/ncclSum) and the result is
  * bit-identical for any world_size.
  *   cf_accumulate_device : this rank's partition -> acc (device, int64[cf_acc_len(h,nk)]), zeroed first
- *   (caller all-reduces acc)
- *   cf_finalize_device   : acc -> J, K (device, col-major nbf x nbf)                                */
+ *   (caller all-reduces the first cf_acc_reduce_len(h,nk) words of acc)
+ *   cf_finalize_device   : acc -> J, K (device, col-major nbf x nbf)
+ * Accumulator layout: [J | K_0..K_{nk-1} | J low limb | tail]; the tail (8 words) holds the fixed-point scales of the
+ * build that filled THIS accumulator (every rank derives bit-identical scales from the same densities, so the tail is
+ * not part of the all-reduce).  Scales therefore travel with their accumulator: accumulate(A), accumulate(B),
+ * finalize(A) is well defined.  The densities' Cartesian work space is per handle: calls on one handle must be issued
+ * on ONE stream (or be ordered by the caller); a handle is not re-entrant, like the reference's class.
+ * The integer sums are taken modulo 2^64: partial sums (per rank, per limb) may wrap around, the final value fits. */
+size_t cf_acc_reduce_len(const cf_handle* h, int nk);
 size_t cf_acc_len(const cf_handle* h, int nk);
 int cf_accumulate_device(cf_handle* h, int nbf,
                          const double* Dd, const double* Da, const double* Db, double exx,
@@ -162,7 +181,8 @@ int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const double* D2,
  * astronomically large density is reported here; cf_build_jk reports it itself). */
 int cf_sync_stats(cf_handle* h);
 /* Developer/benchmark aid: run every (bra class, ket class) kernel alone and time it with CUDA events.
- * DEVICE density pointers. rows: 6 doubles each = bra class, ket class, quartets, ms, F_alg, threads per quartet. */
+ * DEVICE density pointers. rows: 8 doubles each = bra class, ket class, quartets, ms, F_alg at nominal contraction depth,
+ * threads per quartet, primitive quartets executed by the launch, model flops of the executed work. */
 int cf_profile_tasks(cf_handle* h, int nbf, const double* Dd, const double* Da, const double* Db, double exx,
                      double* rows, int max_rows, int* nrows);
 

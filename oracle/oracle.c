@@ -154,15 +154,30 @@ static void hermite_E(int la, int lb, double p, double PA, double PB, ecoef* E) 
     }
 }
 
+/* per-thread scratch that grows on demand and is reused: no allocation inside the primitive / shell-quartet loops
+ * (a CPU baseline that mallocs per primitive quartet would be a strawman) */
+#define TLS_SLOTS 6
+static __thread double* tls_buf[TLS_SLOTS];
+static __thread size_t tls_cap[TLS_SLOTS];
+static double* tls_get(int slot, size_t n) {
+    if (tls_cap[slot] < n) {
+        free(tls_buf[slot]);
+        tls_buf[slot] = (double*)malloc(sizeof(double) * n);
+        tls_cap[slot] = n;
+    }
+    return tls_buf[slot];
+}
+
 /* Hermite Coulomb integrals R_{tuv} = R^0_{tuv}(alpha, PQ), t+u+v <= L. out[t][u][v], dim L+1 each */
 static void hermite_R(int L, double alpha, const double* PQ, double* out /* (L+1)^3 */) {
     double F[L4MAX + 1];
     double T = alpha * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
     boys(L, T, F);
     int d = L + 1;
-    /* work[n][t][u][v] built downward in n; keep two layers via full array for clarity */
+    /* work[n][t][u][v] built downward in n (every entry read below has been written: level n holds t+u+v <= L-n) */
     size_t sz = (size_t)d * d * d;
-    double* w = (double*)calloc(sz * (L + 1), sizeof(double));
+    double* w = tls_get(0, sz * (L + 1));
+    memset(w, 0, sz * sizeof(double));      /* level 0 is copied out whole; entries with t+u+v > L stay 0 */
 #define RW(n, t, u, v) w[(size_t)(n) * sz + ((size_t)(t) * d + (u)) * d + (v)]
     double f = 1.0;
     for (int n = 0; n <= L; n++) { RW(n, 0, 0, 0) = f * F[n]; f *= -2.0 * alpha; }
@@ -188,7 +203,6 @@ static void hermite_R(int L, double alpha, const double* PQ, double* out /* (L+1
     }
     memcpy(out, w, sz * sizeof(double));
 #undef RW
-    free(w);
 }
 
 /* ---------------------------------------------------------------- primitive-pair data of a shell pair */
@@ -239,9 +253,9 @@ static void eri_cart(const pairdata* ab, const pairdata* cd, double* out) {
     cart_components(la, ca); cart_components(lb, cb); cart_components(lc, cc); cart_components(ld, cdd);
     size_t ntot = (size_t)nca * ncb * ncc * ncd;
     memset(out, 0, sizeof(double) * ntot);
-    double* R = (double*)malloc(sizeof(double) * d * d * d);
+    double* R = tls_get(1, (size_t)d * d * d);
     int dab = Lab + 1;
-    double* G = (double*)malloc(sizeof(double) * dab * dab * dab);
+    double* G = tls_get(2, (size_t)dab * dab * dab);
     for (int i = 0; i < ab->npp; i++)
         for (int j = 0; j < cd->npp; j++) {
             double p = ab->p[i], q = cd->p[j];
@@ -288,7 +302,6 @@ static void eri_cart(const pairdata* ab, const pairdata* cd, double* out) {
                         }
                 }
         }
-    free(R); free(G);
 }
 
 /* transform index `which` (0..3) of a 4-index tensor with dims n[4] by matrix C [nnew][n[which]] */
@@ -316,8 +329,8 @@ static void eri_shell_quartet_pd(const cf_basis* b, const pairdata* ab, const pa
     int n[4];
     for (int i = 0; i < 4; i++) n[i] = NCART(sh_l(b, sh[i]));
     size_t ntot = (size_t)n[0] * n[1] * n[2] * n[3];
-    double* t1 = (double*)malloc(sizeof(double) * ntot);
-    double* t2 = (double*)malloc(sizeof(double) * ntot);
+    double* t1 = tls_get(3, ntot);
+    double* t2 = tls_get(4, ntot);
     eri_cart(ab, cd, t1);
     double C[(2 * LMAX + 1) * NCMAX];
     for (int i = 0; i < 4; i++) {
@@ -327,7 +340,6 @@ static void eri_shell_quartet_pd(const cf_basis* b, const pairdata* ab, const pa
         double* tmp = t1; t1 = t2; t2 = tmp;
     }
     memcpy(buf, t1, sizeof(double) * (size_t)n[0] * n[1] * n[2] * n[3]);
-    free(t1); free(t2);
 }
 void oracle_eri_shell_quartet(const cf_basis* b, int s1, int s2, int s3, int s4, double* buf) {
     pairdata ab, cd;
@@ -357,6 +369,7 @@ static void one_electron(const cf_basis* b, int natom, const double* Z, const do
     int nbf = oracle_nbf(b), ns = b->nshell;
     int* s2bf = (int*)malloc(sizeof(int) * ns);
     shell2bf(b, s2bf);
+#pragma omp parallel for schedule(dynamic, 1)   /* every (sa, sb) writes its own block of S, T, V */
     for (int sa = 0; sa < ns; sa++)
         for (int sb = 0; sb < ns; sb++) {
             int la = sh_l(b, sa), lb = sh_l(b, sb);
@@ -993,6 +1006,16 @@ void ref_store_contract(const ref_store* st, const double* Dd, const double* Da,
     ref_Gunified(st->bf, st->bf + n, st->bf + 2 * n, st->bf + 3 * n, st->ints, n, st->nbf, Dd, Da, Db, exx, nthreads, J, Kd, Ka, Kb);
 }
 void ref_store_free(ref_store* st) { free(st->bf); free(st->ints); free(st); }
+/* set the OpenMP thread count explicitly (launchers such as torchrun export OMP_NUM_THREADS=1); n <= 0: all online cores */
+int oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n <= 0) n = omp_get_num_procs();
+    omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 int oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -51,7 +51,14 @@ class Oracle:
         L.ref_store_len.restype = C.c_long
         L.ref_store_len.argtypes = [C.c_void_p]
         L.ref_store_free.argtypes = [C.c_void_p]
+        L.oracle_set_threads.restype = C.c_int
         self.nthreads = L.oracle_max_threads()
+
+    def set_threads(self, n=0):
+        """OpenMP threads of every later call; n <= 0 = all online cores, whatever OMP_NUM_THREADS a launcher exported
+        (torchrun sets it to 1)."""
+        self.nthreads = int(self.lib.oracle_set_threads(C.c_int(n)))
+        return self.nthreads
 
     def boys(self, mmax, T):
         F = np.zeros(mmax + 1)

@@ -101,7 +101,10 @@ def rhf_incremental(S, Hcore, nocc, jk, e_nuc=0.0, max_iter=100, tol=1e-8, diis_
     raise RuntimeError("Convergence failed!")
 
 
-def uhf(S, Hcore, na, nb, jk, e_nuc=0.0, D0=None, max_iter=200, tol=1e-8, diis_space=12, verbose=False, level_shift=0.0):
+def uhf(S, Hcore, na, nb, jk, e_nuc=0.0, D0=None, max_iter=200, tol=1e-8, diis_space=12, verbose=False, level_shift=0.0,
+        trace=None, raise_on_fail=True):
+    """`trace`: list that receives the energy of every iteration; raise_on_fail=False returns the last iterate after
+    max_iter instead of raising (parity of two runs that take the same steps does not need convergence)."""
     w, U = np.linalg.eigh(S)
     X = U @ np.diag(w ** -0.5) @ U.T
     def density(F, n):
@@ -120,9 +123,11 @@ def uhf(S, Hcore, na, nb, jk, e_nuc=0.0, D0=None, max_iter=200, tol=1e-8, diis_s
         Ra = Fa @ Da @ S - S @ Da @ Fa
         Rb = Fb @ Db @ S - S @ Db @ Fb
         err = max(np.abs(Ra).max(), np.abs(Rb).max())
+        if trace is not None:
+            trace.append(E)
         if verbose:
             print("  it %2d  E = %.10f  |R| = %.2e" % (it, E, err))
-        if err < tol:
+        if err < tol or (not raise_on_fail and it == max_iter - 1):
             return E, (Da, Db), (Fa, Fb), it
         Fs.append(np.stack([Fa, Fb])); Rs.append(np.stack([X.T @ Ra @ X, X.T @ Rb @ X]))
         Fs, Rs = Fs[-diis_space:], Rs[-diis_space:]
