@@ -75,6 +75,14 @@ class Int4C2E_T {
     Int4C2E_T() {}
     Int4C2E_T(const FlatBasis& basis, double exx, double threshold, int device = -1, int rank = 0, int world_size = 1)
         : Threshold(threshold), EXX(exx), basis_(std::make_shared<FlatBasis>(basis)), device_(device), rank_(rank), world_(world_size) {}
+    // all-in-one-process multi-GPU: `ndevices` GPUs of the box (<= 0: all of them) behind the same ContractInts call;
+    // partial J/K are summed with an integer NCCL all-reduce inside the library (cf_create_multi)
+    static Int4C2E_T MultiDevice(const FlatBasis& basis, double exx, double threshold, int ndevices) {
+        Int4C2E_T x(basis, exx, threshold);
+        x.ndevices_ = ndevices <= 0 ? -1 : ndevices;
+        return x;
+    }
+    int NumDevices() { ensure(0); return cf_num_devices(h_.get()); }
 
     // ---- the five setup stages, same order and same assertions as the reference (Int4C2E.cpp:500-587)
     void getRepulsionDiag(int output) {
@@ -183,6 +191,7 @@ class Int4C2E_T {
     std::shared_ptr<FlatBasis> basis_;
     std::shared_ptr<cf_handle> h_;
     int device_ = -1, rank_ = 0, world_ = 1, stage_ = 0;
+    int ndevices_ = 0;      // 0: single-device handle (cf_create); -1: all GPUs; n > 0: n GPUs (cf_create_multi)
 
     static void fill_zero(Matrix& m) { double* p = m.data(); for (long i = 0; i < (long)m.size(); i++) p[i] = 0.0; }
     void ensure(int output) {
@@ -191,7 +200,7 @@ class Int4C2E_T {
         cf_options o{};
         o.threshold = Threshold; o.device = device_; o.rank = rank_; o.world_size = world_; o.verbose = output;
         cf_basis b = basis_->view();
-        cf_handle* h = cf_create(&b, &o);
+        cf_handle* h = ndevices_ == 0 ? cf_create(&b, &o) : cf_create_multi(&b, &o, ndevices_ < 0 ? 0 : ndevices_, nullptr);
         if (!h) throw std::runtime_error(std::string("chinium_fock: ") + cf_last_error(nullptr));
         h_ = std::shared_ptr<cf_handle>(h, cf_destroy);
     }

@@ -14,6 +14,12 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <dlfcn.h>
+#include <nccl.h>              // types and prototypes only: libnccl.so.2 is bound with dlopen when a multi-device handle is created
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -273,12 +279,21 @@ struct cf_handle {
     long long ref_counts[2] = {0, 0};        // the reference's RepulsionLength / ShellQuartetLength
     std::string err;
     bool diag_ready = false;
+    struct MultiCtx* multi = nullptr;        // != nullptr: this handle fronts one partition handle per device (cf_create_multi)
 };
 
 static void set_error(cf_handle* h, const std::string& s) {
     if (h) h->err = s;
     g_last_error = s;
 }
+
+static int multi_build_jk(cf_handle* h, int nbf, const double* Dd, const double* Da, const double* Db, double exx,
+                          double* J, double* Kd, double* Ka, double* Kb);
+static int multi_build_g(cf_handle* h, int nbf, int nmat, const double* Ds, double exx, double* Gs);
+static int multi_contract_grads(cf_handle* h, int nbf, const double* D1, const double* D2, double exx, int natom, double* grad);
+static void multi_destroy(cf_handle* h);
+static cf_handle* multi_part0(const cf_handle* h);
+static void multi_set_density_threshold(cf_handle* h, double dthr);
 
 // every entry point works on the handle's device and leaves the caller's current device as it found it
 struct DeviceGuard {
@@ -778,6 +793,7 @@ extern "C" int cf_measure_fp64_peak(int device, double* tflops) {
 
 extern "C" void cf_destroy(cf_handle* h) {
     if (!h) return;
+    if (h->multi) { multi_destroy(h); delete h; return; }
     DeviceGuard guard(h->device);
     for (auto& c : h->cls) c.release();
     for (auto* t : h->tasks) { t->d_qoff.release(); t->d_items.release(); delete t; }
@@ -1205,6 +1221,7 @@ extern "C" int cf_nbf(const cf_handle* h) { return h ? h->nbf : -1; }
 extern "C" int cf_set_density_threshold(cf_handle* h, double dthr) {
     if (!h) return CF_ERR_BAD_ARGUMENT;
     h->density_threshold = dthr > 0.0 ? dthr : 0.0;
+    if (h->multi) multi_set_density_threshold(h, h->density_threshold);
     return CF_OK;
 }
 
@@ -1213,9 +1230,16 @@ extern "C" int cf_get_stats(const cf_handle* h, cf_stats* out) {
     *out = h->stats;
     return CF_OK;
 }
+static int multi_only_host_calls(cf_handle* h) {
+    set_error(h, "this is a multi-device handle (cf_create_multi): use the host calls cf_build_jk / cf_build_g_multi / "
+                 "cf_contract_grads; the *_device entry points work on single-device handles");
+    return CF_ERR_BAD_ARGUMENT;
+}
+
 
 extern "C" int cf_get_repulsion_diag(cf_handle* h, double* diag1212) {
     if (!h || !diag1212) return CF_ERR_BAD_ARGUMENT;
+    if (h->multi) return cf_get_repulsion_diag(multi_part0(h), diag1212);
     if (!h->diag_ready) { set_error(h, "Diagonal elements of repulsion integrals are missing!"); return CF_ERR_STATE; }
     DeviceGuard guard(h->device);
     CUDA_TRY(cudaMemcpy(diag1212, h->d_diag.p, sizeof(double) * (size_t)h->nbf * h->nbf, cudaMemcpyDeviceToHost));
@@ -1249,6 +1273,7 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
     if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
     if (!Dd && !Da && !Db) { set_error(h, "at least one density is required"); return CF_ERR_BAD_ARGUMENT; }
     if (!acc) { set_error(h, "null accumulator"); return CF_ERR_BAD_ARGUMENT; }
+    if (h->multi) return multi_only_host_calls(h);
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     const double* dk[3]; int slot[3];
@@ -1310,6 +1335,7 @@ extern "C" int cf_finalize_device(cf_handle* h, int nbf, const int64_t* acc, dou
                                   double* J, double* Kd, double* Ka, double* Kb, void* stream) {
     if (!h || !acc || !J) return CF_ERR_BAD_ARGUMENT;
     if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
+    if (h->multi) return multi_only_host_calls(h);
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     const int ns = h->nshell, ncart = h->ncart;
@@ -1345,6 +1371,7 @@ extern "C" int cf_finalize_device(cf_handle* h, int nbf, const int64_t* acc, dou
 extern "C" int cf_build_jk_device(cf_handle* h, int nbf, const double* Dd, const double* Da, const double* Db, double exx,
                                   double* J, double* Kd, double* Ka, double* Kb, void* stream) {
     if (!h) return CF_ERR_BAD_ARGUMENT;
+    if (h->multi) return multi_only_host_calls(h);
     DeviceGuard guard(h->device);
     int rc = cf_accumulate_device(h, nbf, Dd, Da, Db, exx, (int64_t*)h->d_acc.p, stream);
     if (rc != CF_OK) return rc;
@@ -1401,6 +1428,7 @@ static int fetch_build_info(cf_handle* h, cudaStream_t s) {
 
 extern "C" int cf_sync_stats(cf_handle* h) {   // after a *_device call has been synchronised by the caller
     if (!h) return CF_ERR_BAD_ARGUMENT;
+    if (h->multi) return CF_OK;                // the host calls of a multi-device handle refresh the statistics themselves
     DeviceGuard guard(h->device);
     fetch_times(h);
     int rc = fetch_build_info(h, 0);
@@ -1416,6 +1444,7 @@ extern "C" int cf_build_jk(cf_handle* h, int nbf, const double* Dd, const double
     if (!J) { set_error(h, "J output is required"); return CF_ERR_BAD_ARGUMENT; }
     if (!Dd && !Da && !Db) { set_error(h, "at least one density is required"); return CF_ERR_BAD_ARGUMENT; }
     if ((Dd && !Kd) || (Da && !Ka) || (Db && !Kb)) { set_error(h, "K output missing for a density that was given"); return CF_ERR_BAD_ARGUMENT; }
+    if (h->multi) return multi_build_jk(h, nbf, Dd, Da, Db, exx, J, Kd, Ka, Kb);
     DeviceGuard guard(h->device);
     const double t0 = now_s();
     if (h->opt.verbose > 0) std::printf("Contracting 4c-2e repulsion integrals with 1 matrix ... ");
@@ -1446,6 +1475,7 @@ extern "C" int cf_build_jk(cf_handle* h, int nbf, const double* Dd, const double
 extern "C" int cf_profile_tasks(cf_handle* h, int nbf, const double* Dd_dev, const double* Da_dev, const double* Db_dev, double exx,
                                 double* rows, int max_rows, int* nrows) {
     if (!h || !rows || !nrows) return CF_ERR_BAD_ARGUMENT;
+    if (h->multi) return multi_only_host_calls(h);
     DeviceGuard guard(h->device);
     int rc = cf_accumulate_device(h, nbf, Dd_dev, Da_dev, Db_dev, exx, (int64_t*)h->d_acc.p, nullptr);   // sets densities + scales
     if (rc != CF_OK) return rc;
@@ -1505,6 +1535,7 @@ __global__ void grad_reduce_kernel(const double* __restrict__ gpart, int nrow, i
 extern "C" int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const double* D2, double exx, int natom, double* grad) {
     if (!h || !D1 || !D2 || !grad || natom <= 0) return CF_ERR_BAD_ARGUMENT;
     if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
+    if (h->multi) return multi_contract_grads(h, nbf, D1, D2, exx, natom, grad);
     if (h->shell2atom.empty()) { set_error(h, "cf_contract_grads needs cf_basis.shell2atom"); return CF_ERR_BAD_ARGUMENT; }
     for (int a : h->shell2atom) if (a < 0 || a >= natom) { set_error(h, "shell2atom entry outside [0, natom)"); return CF_ERR_BAD_ARGUMENT; }
     DeviceGuard guard(h->device);
@@ -1587,11 +1618,11 @@ __global__ void sub_kernel(size_t n, const double* __restrict__ a, const double*
 
 // One batch (<= 3 densities, already in d_Dpure[0..nmat-1]) of the multi-density build: ONE pass over the integrals digests
 // J[D_k] and K[D_k] of every member (QuartetTask::nj / nk), accumulators [J_0..J_2 | K_0..K_2]; G_k -> d_out[k].
-static int build_g_batch(cf_handle* h, int nmat, double exx) {
+// first half: this partition's raw accumulators; a multi-GPU caller all-reduces the 9 n2c payload words in between
+static int build_g_accumulate(cf_handle* h, int nmat, double exx, cudaStream_t s) {
     const int ns = h->nshell, nbf = h->nbf, ncart = h->ncart;
-    const size_t n2c = (size_t)ncart * ncart, ns2 = (size_t)ns * ns, n2p = (size_t)nbf * nbf;
+    const size_t n2c = (size_t)ncart * ncart, ns2 = (size_t)ns * ns;
     const int nk = exx > 0.0 ? nmat : 0;
-    cudaStream_t s = 0;
     long long* acc = h->d_acc.p;                 // [J_0..J_2 | K_0..K_2 | Jlo_0..Jlo_2 | tail]
     double* tail = reinterpret_cast<double*>(acc + 9 * n2c);
     h->last_tail = (const long long*)tail; h->last_nk = nk;
@@ -1633,6 +1664,16 @@ static int build_g_batch(cf_handle* h, int nmat, double exx) {
     }
     for (int i = 0; i < 3; i++) { CUDA_TRY(cudaEventRecord(h->ev_join[i], h->side[i])); CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join[i], 0)); }
     CUDA_TRY(cudaEventRecord(h->ev[2], s));
+    return CF_OK;
+}
+// second half: G_k -> d_out[k]
+static int build_g_finalize(cf_handle* h, int nmat, double exx, cudaStream_t s) {
+    const int ns = h->nshell, nbf = h->nbf, ncart = h->ncart;
+    const size_t n2c = (size_t)ncart * ncart, n2p = (size_t)nbf * nbf;
+    const int nk = exx > 0.0 ? nmat : 0;
+    long long* acc = h->d_acc.p;
+    const double* tail = reinterpret_cast<const double*>(acc + 9 * n2c);
+    dim3 grid2(ns, ns);
     // G_k = J[2 D_k] - exx K[D_k] = 1/2 (rawJ + rawJ^T) - exx/8 (rawK + rawK^T)   (Int4C2E.cpp:726-728 with the J of D_k, not 2 D_k)
     for (int k = 0; k < nmat; k++) {
         finalize_kernel<<<grid2, 64, 0, s>>>(nbf, ncart, acc + (size_t)k * n2c, acc + (size_t)(6 + k) * n2c, tail, 0, 0.5, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
@@ -1649,11 +1690,16 @@ static int build_g_batch(cf_handle* h, int nmat, double exx) {
     CUDA_TRY(cudaEventRecord(h->ev[3], s));
     return CF_OK;
 }
+static int build_g_batch(cf_handle* h, int nmat, double exx) {
+    int rc = build_g_accumulate(h, nmat, exx, 0);
+    return rc != CF_OK ? rc : build_g_finalize(h, nmat, exx, 0);
+}
 
 // G_k = J[2 D_k] - exx K[D_k]  (GhfMultiple, Int4C2E.cpp:685-745): batches of three densities share one pass over the integrals
 extern "C" int cf_build_g_multi(cf_handle* h, int nbf, int nmat, const double* Ds, double exx, double* Gs) {
     if (!h || !Ds || !Gs || nmat <= 0) return CF_ERR_BAD_ARGUMENT;
     if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
+    if (h->multi) return multi_build_g(h, nbf, nmat, Ds, exx, Gs);
     DeviceGuard guard(h->device);
     const size_t n2 = (size_t)nbf * nbf, bytes = sizeof(double) * n2;
     for (int k0 = 0; k0 < nmat; k0 += 3) {
@@ -1670,5 +1716,281 @@ extern "C" int cf_build_g_multi(cf_handle* h, int nbf, int nmat, const double* D
         rc = check_scales(h);
         if (rc != CF_OK) return rc;
     }
+    return CF_OK;
+}
+
+// ================================================================================================
+// Multi-device handle (SURVEY 8b "Threading", 8e): ONE process, one worker thread + one stream per GPU.
+// The reference is a single C++ process (src/main.cpp:14-63) whose Int4C2E spawns OpenMP workers inside
+// ContractInts (Int4C2E.cpp:617-621); here the same call fans out over the GPUs of the box:
+//   host D (pinned staging) -> H2D on every device -> each device accumulates ITS static partition of the quartet work
+//   -> ncclAllReduce(int64, sum) of the fixed-point accumulators over NVLink -> device 0 finalises -> D2H.
+// The integer all-reduce makes the result bit-identical to the single-GPU result for any number of devices.
+// NCCL is bound at run time (dlopen of libnccl.so.2: inside a PyTorch process this resolves to the copy torch loaded).
+// ================================================================================================
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (lib) break; }
+        if (!lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+        CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!CommInitAll || !CommDestroy || !AllReduce || !GetErrorString) { err = "libnccl.so.2 lacks the expected symbols"; return false; }
+        return true;
+    }
+};
+
+struct MultiCtx {
+    int ndev = 0;
+    std::vector<int> devices;
+    std::vector<cf_handle*> parts;
+    std::vector<cudaStream_t> streams;
+    std::vector<ncclComm_t> comms;
+    NcclApi nccl;
+    double* pin = nullptr;             // pinned host staging: [3 inputs | 4 outputs] x nbf^2
+    size_t n2 = 0;
+    // worker pool: thread i owns device i
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    long epoch = 0;
+    int done = 0;
+    bool quit = false;
+    std::function<int(int)> job;
+    std::vector<int> rc;
+    std::vector<std::string> errs;
+
+    void worker(int i) {
+        long seen = 0;
+        for (;;) {
+            std::function<int(int)> f;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_go.wait(lk, [&] { return quit || epoch != seen; });
+                if (quit) return;
+                seen = epoch;
+                f = job;
+            }
+            const int r = f(i);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                rc[i] = r;
+                done++;
+            }
+            cv_done.notify_one();
+        }
+    }
+    void start() {
+        rc.assign(ndev, 0); errs.assign(ndev, "");
+        for (int i = 0; i < ndev; i++) th.emplace_back([this, i] { worker(i); });
+    }
+    // run f(i) on every worker, return the first non-zero code
+    int run(const std::function<int(int)>& f) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job = f; done = 0; epoch++;
+        }
+        cv_go.notify_all();
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return done == ndev; });
+        for (int i = 0; i < ndev; i++) if (rc[i] != CF_OK) return rc[i];
+        return CF_OK;
+    }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv_go.notify_all();
+        for (auto& t : th) if (t.joinable()) t.join();
+        th.clear();
+    }
+};
+
+static cf_handle* multi_part0(const cf_handle* h) { return h->multi->parts[0]; }
+
+static void multi_set_density_threshold(cf_handle* h, double dthr) {
+    for (cf_handle* p : h->multi->parts) p->density_threshold = dthr;
+}
+
+static void multi_destroy(cf_handle* h) {
+    MultiCtx* M = h->multi;
+    if (!M) return;
+    M->stop();
+    for (int i = 0; i < (int)M->comms.size(); i++) if (M->comms[i] && M->nccl.CommDestroy) M->nccl.CommDestroy(M->comms[i]);
+    for (int i = 0; i < (int)M->streams.size(); i++) if (M->streams[i]) { DeviceGuard g(M->devices[i]); cudaStreamDestroy(M->streams[i]); }
+    for (cf_handle* p : M->parts) if (p) cf_destroy(p);
+    if (M->pin) cudaFreeHost(M->pin);
+    delete M;
+    h->multi = nullptr;
+}
+
+// statistics of the whole job from the partitions (setup counts are identical on every partition)
+static void multi_refresh_stats(cf_handle* h) {
+    MultiCtx* M = h->multi;
+    cf_stats st = M->parts[0]->stats;
+    st.canonical_quartets_local = st.canonical_quartets;
+    for (int k = 0; k < 4; k++) st.flops_alg_jk[k] = 0;
+    st.flops_alg_grad = 0; st.quartets_evaluated_last = 0; st.primitive_quartets_executed_last = 0; st.flops_executed_last = 0;
+    st.n_launches_last = 0; st.ms_device_last = 0; st.ms_eri_last = 0; st.ms_grad_last = 0;
+    for (cf_handle* p : M->parts) {
+        for (int k = 0; k < 4; k++) st.flops_alg_jk[k] += p->stats.flops_alg_jk[k];
+        st.flops_alg_grad += p->stats.flops_alg_grad;
+        st.quartets_evaluated_last += p->stats.quartets_evaluated_last;
+        st.primitive_quartets_executed_last += p->stats.primitive_quartets_executed_last;
+        st.flops_executed_last += p->stats.flops_executed_last;
+        st.n_launches_last += p->stats.n_launches_last;
+        st.ms_device_last = std::max(st.ms_device_last, p->stats.ms_device_last);      // the build takes as long as its slowest device
+        st.ms_eri_last = std::max(st.ms_eri_last, p->stats.ms_eri_last);
+        st.ms_grad_last = std::max(st.ms_grad_last, p->stats.ms_grad_last);
+    }
+    h->stats = st;
+}
+
+extern "C" cf_handle* cf_create_multi(const cf_basis* basis, const cf_options* opts, int ndev, const int* devices) {
+    int navail = 0;
+    if (cudaGetDeviceCount(&navail) != cudaSuccess || navail == 0) { set_error(nullptr, "no CUDA device (this engine has no CPU fallback)"); return nullptr; }
+    if (ndev <= 0) ndev = navail;                       // all GPUs of the box
+    if (ndev > navail) { set_error(nullptr, "cf_create_multi: more devices requested than present"); return nullptr; }
+    if (ndev == 1 && !devices) return cf_create(basis, opts);
+    cf_handle* h = new cf_handle();
+    MultiCtx* M = new MultiCtx();
+    h->multi = M;
+    M->ndev = ndev;
+    for (int i = 0; i < ndev; i++) M->devices.push_back(devices ? devices[i] : i);
+    M->parts.assign(ndev, nullptr); M->streams.assign(ndev, nullptr); M->comms.assign(ndev, nullptr);
+    auto fail = [&](const std::string& s) -> cf_handle* { set_error(nullptr, s); multi_destroy(h); delete h; return nullptr; };
+    std::string err;
+    if (!M->nccl.load(err)) return fail("cf_create_multi: " + err);
+    M->start();
+    cf_options o{};
+    if (opts) o = *opts;
+    // every partition runs the whole setup on its own device, concurrently
+    int rc = M->run([&](int i) {
+        cf_options oi = o;
+        oi.device = M->devices[i]; oi.rank = i; oi.world_size = ndev; oi.verbose = (i == 0) ? o.verbose : 0;
+        cf_handle* p = cf_create(basis, &oi);
+        if (!p) { M->errs[i] = g_last_error; return CF_ERR_CUDA; }
+        M->parts[i] = p;
+        DeviceGuard g(p->device);
+        if (cudaStreamCreateWithFlags(&M->streams[i], cudaStreamNonBlocking) != cudaSuccess) { M->errs[i] = "cudaStreamCreate failed"; return CF_ERR_CUDA; }
+        return CF_OK;
+    });
+    if (rc != CF_OK) { for (auto& e : M->errs) if (!e.empty()) return fail("cf_create_multi: " + e); return fail("cf_create_multi: partition setup failed"); }
+    ncclResult_t nr = M->nccl.CommInitAll(M->comms.data(), ndev, M->devices.data());
+    if (nr != ncclSuccess) return fail(std::string("ncclCommInitAll: ") + M->nccl.GetErrorString(nr));
+    h->device = M->devices[0];
+    h->opt = o; h->opt.world_size = 1; h->opt.rank = 0;
+    h->nshell = M->parts[0]->nshell; h->nbf = M->parts[0]->nbf; h->ncart = M->parts[0]->ncart;
+    h->diag_ready = true;
+    M->n2 = (size_t)h->nbf * h->nbf;
+    if (cudaMallocHost(&M->pin, sizeof(double) * 7 * M->n2) != cudaSuccess) return fail("cf_create_multi: cudaMallocHost failed");
+    multi_refresh_stats(h);
+    return h;
+}
+
+extern "C" int cf_num_devices(const cf_handle* h) { return !h ? 0 : h->multi ? h->multi->ndev : 1; }
+
+static int multi_fail(cf_handle* h, int rc) {
+    for (int i = 0; i < h->multi->ndev; i++)
+        if (h->multi->rc[i] != CF_OK) { set_error(h, "device " + std::to_string(h->multi->devices[i]) + ": " + h->multi->parts[i]->err + h->multi->errs[i]); break; }
+    return rc;
+}
+
+static int multi_build_jk(cf_handle* h, int nbf, const double* Dd, const double* Da, const double* Db, double exx,
+                          double* J, double* Kd, double* Ka, double* Kb) {
+    MultiCtx* M = h->multi;
+    const size_t n2 = M->n2, bytes = sizeof(double) * n2;
+    const double t0 = now_s();
+    if (h->opt.verbose > 0) std::printf("Contracting 4c-2e repulsion integrals with 1 matrix ... ");
+    const double* src[3] = {Dd, Da, Db};
+    double* outs[4] = {J, Kd, Ka, Kb};
+    for (int k = 0; k < 3; k++) if (src[k]) std::memcpy(M->pin + k * n2, src[k], bytes);
+    const double* dk[3]; int slot[3];
+    const int nk = exchange_list(Dd, Da, Db, exx, dk, slot);
+    int rc = M->run([&](int i) -> int {
+        cf_handle* p = M->parts[i];
+        DeviceGuard g(p->device);
+        cudaStream_t s = M->streams[i];
+        M->errs[i].clear();
+        auto cu = [&](cudaError_t e, const char* what) { if (e != cudaSuccess) { M->errs[i] = std::string(what) + ": " + cudaGetErrorString(e); return false; } return true; };
+        const double* dev[3] = {nullptr, nullptr, nullptr};
+        for (int k = 0; k < 3; k++)
+            if (src[k]) { if (!cu(cudaMemcpyAsync(p->d_Dpure[k].p, M->pin + k * n2, bytes, cudaMemcpyHostToDevice, s), "H2D")) return CF_ERR_CUDA; dev[k] = p->d_Dpure[k].p; }
+        int r = cf_accumulate_device(p, nbf, dev[0], dev[1], dev[2], exx, (int64_t*)p->d_acc.p, s);
+        if (r != CF_OK) return r;
+        ncclResult_t nr = M->nccl.AllReduce(p->d_acc.p, p->d_acc.p, cf_acc_reduce_len(p, nk), ncclInt64, ncclSum, M->comms[i], s);
+        if (nr != ncclSuccess) { M->errs[i] = std::string("ncclAllReduce: ") + M->nccl.GetErrorString(nr); return CF_ERR_CUDA; }
+        if (i == 0) {   // every device holds the summed accumulators; device 0 turns them into J/K for the host
+            r = cf_finalize_device(p, nbf, (const int64_t*)p->d_acc.p, exx, Dd != nullptr, Da != nullptr, Db != nullptr,
+                                   p->d_out[0].p, p->d_out[1].p, p->d_out[2].p, p->d_out[3].p, s);
+            if (r != CF_OK) return r;
+            if (!cu(cudaMemcpyAsync(M->pin + 3 * n2, p->d_out[0].p, bytes, cudaMemcpyDeviceToHost, s), "D2H")) return CF_ERR_CUDA;
+            for (int k = 0; k < 3; k++)
+                if (src[k] && !cu(cudaMemcpyAsync(M->pin + (4 + k) * n2, p->d_out[1 + k].p, bytes, cudaMemcpyDeviceToHost, s), "D2H")) return CF_ERR_CUDA;
+        } else {
+            if (!cu(cudaEventRecord(p->ev[3], s), "event")) return CF_ERR_CUDA;
+        }
+        r = fetch_build_info(p, s);
+        if (r != CF_OK) return r;
+        if (!cu(cudaStreamSynchronize(s), "synchronize")) return CF_ERR_CUDA;
+        fetch_times(p);
+        return check_scales(p);
+    });
+    if (rc != CF_OK) return multi_fail(h, rc);
+    std::memcpy(J, M->pin + 3 * n2, bytes);
+    for (int k = 0; k < 3; k++) if (src[k]) std::memcpy(outs[1 + k], M->pin + (4 + k) * n2, bytes);
+    multi_refresh_stats(h);
+    if (h->opt.verbose > 0) std::printf("Done in %f s\n", now_s() - t0);
+    return CF_OK;
+}
+
+static int multi_build_g(cf_handle* h, int nbf, int nmat, const double* Ds, double exx, double* Gs) {
+    MultiCtx* M = h->multi;
+    const size_t n2 = M->n2, bytes = sizeof(double) * n2;
+    for (int k0 = 0; k0 < nmat; k0 += 3) {
+        const int nb = std::min(3, nmat - k0);
+        for (int k = 0; k < nb; k++) std::memcpy(M->pin + k * n2, Ds + (size_t)(k0 + k) * n2, bytes);
+        int rc = M->run([&](int i) -> int {
+            cf_handle* p = M->parts[i];
+            DeviceGuard g(p->device);
+            cudaStream_t s = M->streams[i];
+            M->errs[i].clear();
+            auto cu = [&](cudaError_t e, const char* what) { if (e != cudaSuccess) { M->errs[i] = std::string(what) + ": " + cudaGetErrorString(e); return false; } return true; };
+            for (int k = 0; k < nb; k++) if (!cu(cudaMemcpyAsync(p->d_Dpure[k].p, M->pin + k * n2, bytes, cudaMemcpyHostToDevice, s), "H2D")) return CF_ERR_CUDA;
+            int r = build_g_accumulate(p, nb, exx, s);
+            if (r != CF_OK) return r;
+            ncclResult_t nr = M->nccl.AllReduce(p->d_acc.p, p->d_acc.p, 9 * (size_t)p->ncart * p->ncart, ncclInt64, ncclSum, M->comms[i], s);
+            if (nr != ncclSuccess) { M->errs[i] = std::string("ncclAllReduce: ") + M->nccl.GetErrorString(nr); return CF_ERR_CUDA; }
+            if (i == 0) {
+                r = build_g_finalize(p, nb, exx, s);
+                if (r != CF_OK) return r;
+                for (int k = 0; k < nb; k++) if (!cu(cudaMemcpyAsync(M->pin + (3 + k) * n2, p->d_out[k].p, bytes, cudaMemcpyDeviceToHost, s), "D2H")) return CF_ERR_CUDA;
+            } else if (!cu(cudaEventRecord(p->ev[3], s), "event")) return CF_ERR_CUDA;
+            r = fetch_build_info(p, s);
+            if (r != CF_OK) return r;
+            if (!cu(cudaStreamSynchronize(s), "synchronize")) return CF_ERR_CUDA;
+            fetch_times(p);
+            return check_scales(p);
+        });
+        if (rc != CF_OK) return multi_fail(h, rc);
+        for (int k = 0; k < nb; k++) std::memcpy(Gs + (size_t)(k0 + k) * n2, M->pin + (3 + k) * n2, bytes);
+    }
+    multi_refresh_stats(h);
+    return CF_OK;
+}
+
+// every partition contracts its share of the quartets; the 3*natom partial vectors are added in device order (fixed)
+static int multi_contract_grads(cf_handle* h, int nbf, const double* D1, const double* D2, double exx, int natom, double* grad) {
+    MultiCtx* M = h->multi;
+    std::vector<std::vector<double>> part(M->ndev, std::vector<double>(3 * (size_t)natom, 0.0));
+    int rc = M->run([&](int i) -> int { return cf_contract_grads(M->parts[i], nbf, D1, D2, exx, natom, part[i].data()); });
+    if (rc != CF_OK) return multi_fail(h, rc);
+    for (int j = 0; j < 3 * natom; j++) { double s = 0.0; for (int i = 0; i < M->ndev; i++) s += part[i][j]; grad[j] = s; }
+    multi_refresh_stats(h);
     return CF_OK;
 }

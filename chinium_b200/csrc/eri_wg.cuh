@@ -27,13 +27,6 @@
 __device__ __forceinline__ void cf_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #endif
 
-// 8-byte asynchronous copy global -> shared (LDGSTS): no register staging, completion awaited with wg_cp_async_wait()
-__device__ __forceinline__ void wg_cp_async8(double* smem_dst, const double* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void wg_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 template <int B, int E, class F>
 __device__ __forceinline__ void wg_static_for(F&& f) {
     if constexpr (B < E) { f(std::integral_constant<int, B>{}); wg_static_for<B + 1, E>(f); }
@@ -58,17 +51,7 @@ struct WgCfg {
     static constexpr int NAP = NA / HS;                             // components of shell a handled per pass
     static constexpr int NE = NAP * NB;                             // register accumulators per owned S component
     static constexpr int R1 = NE * GS, R2 = (NAP + NB) * NCD;
-    // Digestion staging: the density elements a quartet's digestion reads -- D(c,d) of the Coulomb density and the
-    // (NAP+NB) x (NC+ND) block D(a|b rows, c|d columns) of the exchange density -- are fetched by the lanes of the group
-    // with cp.async into the END of the quartet's scratch in ONE batch right after the primitive loop, so the digestion
-    // sees a single L2 round trip instead of ~8 dependent batches of scattered loads (2 warps per scheduler cannot hide
-    // those; r02p: 15 % of the kernel in long-scoreboard stalls inside the digestion).  The partial sums of the J phase
-    // (R1) and of the K phase (R2) live at the start of the scratch and never reach the staged blocks.
-    static constexpr int DBLK = (NAP + NB) * (NC + ND);
-    static constexpr int RJ = R1 + NCD + DBLK, RK = R2 + DBLK;
-    static constexpr int wg_max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
-    static constexpr int SCR = wg_pad(wg_max3(TQ, RJ, RK));   // doubles per quartet
-    static constexpr int OFF_DK = SCR - DBLK, OFF_DCD = SCR - DBLK - NCD;
+    static constexpr int SCR = wg_pad(TQ > R1 ? (TQ > R2 ? TQ : R2) : (R1 > R2 ? R1 : R2));   // doubles per quartet
     // GTAB: when the staged Chebyshev root tables (18-64 KB) would keep the MINB-th CTA off the SM (or leave the L1 cache
     // next to nothing of the 256 KB), they are read through L1 from global memory instead.  Measured (profiles r02f):
     // ff|fd 3.17 -> 1.74 ms, ff|ps 2.03 -> 1.44 ms on c18; classes that fit anyway are 2-3 % faster with staged tables.
@@ -391,39 +374,15 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
         }
 
         // ---- digestion (warp-synchronous; the quartet's scratch is free now) -----------------------------------
-        // round r digests Coulomb density r and exchange density r (RHF: one round); their density elements are staged
-        // together by the lanes of the group -> one L2 round trip per round
-        const int nrounds = t.nj > t.nk ? t.nj : t.nk;
-        for (int rd = 0; rd < nrounds; rd++) {
-        const bool doJ = rd < t.nj, doK = rd < t.nk;
-        if (active) {
-            if (doJ) {
-                const double* __restrict__ DJ = t.Dj[rd];
-                for (int idx = g; idx < NCD; idx += GS)
-                    wg_cp_async8(myq + C::OFF_DCD + idx, DJ + (cd0 + idx % ND) * ld + cc0 + idx / ND);
-            }
-            if (doK) {
-                const double* __restrict__ D = t.Dk[rd];
-                for (int idx = g; idx < C::DBLK; idx += GS) {
-                    const int rr = idx / (NC + ND), k = idx - rr * (NC + ND);
-                    const int row = rr < NAP ? ca + IA0 + rr : cb + (rr - NAP);
-                    const int col = k < NC ? cc0 + k : cd0 + (k - NC);
-                    wg_cp_async8(myq + C::OFF_DK + idx, D + row * ld + col);
-                }
-            }
-        }
-        wg_cp_async_wait();
-        __syncwarp();
-        if (doJ) {   // J(c,d) complete per lane; J(a,b) partial over the lanes of the group
-            const int xj = rd;
+        for (int xj = 0; xj < t.nj; xj++) {   // J(c,d) complete per lane; J(a,b) partial over the lanes of the group
             const double* __restrict__ DJ = t.Dj[xj];
             long long* aJ = t.accJm[xj];
             double dcd[MK], jcd[MK];
 #pragma unroll
-            for (int m = 0; m < MK; m++) { dcd[m] = (active && fok[m]) ? myq[C::OFF_DCD + g * MK + m] : 0.0; jcd[m] = 0.0; }
+            for (int m = 0; m < MK; m++) { dcd[m] = (active && fok[m]) ? DJ[(cd0 + fid[m]) * ld + cc0 + fic[m]] : 0.0; jcd[m] = 0.0; }
 #pragma unroll
             for (int e = 0; e < NE; e++) {
-                const double dab = DJ[(cb + e % NB) * ld + ca + IA0 + e / NB];     // warp-uniform address: one broadcast sector
+                const double dab = DJ[(cb + e % NB) * ld + ca + IA0 + e / NB];
                 double pab = 0.0;
 #pragma unroll
                 for (int m = 0; m < MK; m++) { pab = fma(acc[m][e], dcd[m], pab); jcd[m] = fma(acc[m][e], dab, jcd[m]); }
@@ -452,9 +411,8 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
             }
             __syncwarp();
         }
-        if (doK) {
-            const int x = rd;
-            const double* blk = myq + C::OFF_DK;       // [(NAP a-rows | NB b-rows)][(NC c-columns | ND d-columns)]
+        for (int x = 0; x < t.nk; x++) {
+            const double* __restrict__ D = t.Dk[x];
             long long* accK = t.accK[x];
             // half 1: K(a,c) += sum_bd V D(b,d) ; K(b,c) += sum_ad V D(a,d)   -> slots [.., ic, id], summed over id
             if (active) {
@@ -463,9 +421,9 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
                     if (!fok[m]) continue;
                     double dbd[NB], dad[NAP];
 #pragma unroll
-                    for (int j = 0; j < NB; j++) dbd[j] = blk[(NAP + j) * (NC + ND) + NC + fid[m]];
+                    for (int j = 0; j < NB; j++) dbd[j] = D[(cb + j) * ld + cd0 + fid[m]];
 #pragma unroll
-                    for (int i = 0; i < NAP; i++) dad[i] = blk[i * (NC + ND) + NC + fid[m]];
+                    for (int i = 0; i < NAP; i++) dad[i] = D[(ca + IA0 + i) * ld + cd0 + fid[m]];
                     double kbc[NB];
 #pragma unroll
                     for (int j = 0; j < NB; j++) kbc[j] = 0.0;
@@ -498,9 +456,9 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
                     if (!fok[m]) continue;
                     double dbc[NB], dac[NAP];
 #pragma unroll
-                    for (int j = 0; j < NB; j++) dbc[j] = blk[(NAP + j) * (NC + ND) + fic[m]];
+                    for (int j = 0; j < NB; j++) dbc[j] = D[(cb + j) * ld + cc0 + fic[m]];
 #pragma unroll
-                    for (int i = 0; i < NAP; i++) dac[i] = blk[i * (NC + ND) + fic[m]];
+                    for (int i = 0; i < NAP; i++) dac[i] = D[(ca + IA0 + i) * ld + cc0 + fic[m]];
                     double kbd[NB];
 #pragma unroll
                     for (int j = 0; j < NB; j++) kbd[j] = 0.0;
@@ -527,7 +485,6 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
                 }
             __syncwarp();
         }
-        }   // rounds
         });   // passes over the H components
     }
     cf_cnt_flush(t.cnt, cnt_q, cnt_p);

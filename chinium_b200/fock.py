@@ -72,6 +72,9 @@ def load_library(path: str = LIB_PATH):
     vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.c_int
     L.cf_create.restype = vp
     L.cf_create.argtypes = [C.POINTER(_CfBasis), C.POINTER(_CfOptions)]
+    L.cf_create_multi.restype = vp
+    L.cf_create_multi.argtypes = [C.POINTER(_CfBasis), C.POINTER(_CfOptions), ip, C.POINTER(C.c_int)]
+    L.cf_num_devices.argtypes = [vp]
     L.cf_destroy.argtypes = [vp]
     L.cf_last_error.restype = C.c_char_p
     L.cf_last_error.argtypes = [vp]
@@ -116,11 +119,14 @@ class Int4C2E:
     """Drop-in mirror of the reference class; `basis` is a chinium_b200.inputs.FlatBasis (the Mwfn stand-in)."""
 
     def __init__(self, basis, exx: float = 1.0, threshold: float = -1.0, device: int = -1, rank: int = 0,
-                 world_size: int = 1, pair_cutoff: float = 0.0, j_two_limb: int = 0):
+                 world_size: int = 1, pair_cutoff: float = 0.0, j_two_limb: int = 0, ndevices: int = 0):
+        """ndevices: 0 = single-device handle (cf_create); n > 0 = n GPUs of the box driven by this ONE process, -1 = all of
+        them (cf_create_multi: worker thread + stream per device, NCCL int64 all-reduce inside the library)."""
         self.MWFN = basis
         self.EXX = float(exx)            # read at contract time, like the reference (SelfConsistentField.cpp:48)
         self.Threshold = float(threshold)
-        self._opts = dict(device=device, rank=rank, world_size=world_size, pair_cutoff=pair_cutoff, j_two_limb=j_two_limb)
+        self._opts = dict(device=device, rank=rank, world_size=world_size, pair_cutoff=pair_cutoff, j_two_limb=j_two_limb,
+                          ndevices=ndevices)
         self._h = None
         self._lib = load_library()
         self.RepulsionDiags = None
@@ -149,7 +155,8 @@ class Int4C2E:
         o.world_size = self._opts["world_size"]
         o.verbose = int(output)
         o.j_two_limb = int(self._opts["j_two_limb"])
-        h = self._lib.cf_create(C.byref(b), C.byref(o))
+        nd = int(self._opts["ndevices"])
+        h = self._lib.cf_create(C.byref(b), C.byref(o)) if nd == 0 else self._lib.cf_create_multi(C.byref(b), C.byref(o), max(nd, 0), None)
         if not h:
             raise FockEngineError(self._lib.cf_last_error(None).decode())
         self._h = h

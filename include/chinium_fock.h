@@ -109,6 +109,17 @@ typedef struct cf_stats {
  * available from cf_last_error(NULL). */
 cf_handle* cf_create(const cf_basis* basis, const cf_options* opts);
 void cf_destroy(cf_handle* h);
+
+/* Multi-GPU handle: ONE process drives `ndev` GPUs of the box (devices[i], or 0..ndev-1 when devices == NULL; ndev <= 0 =
+ * all GPUs).  The reference is a single C++ process whose ContractInts spawns its workers internally (Int4C2E.cpp:617-621,
+ * SURVEY 8b "Threading"); here one worker thread + one stream per device do the same: every device evaluates its static
+ * partition of the quartet work, the fixed-point accumulators are summed with ncclAllReduce(ncclInt64, ncclSum) over
+ * NVLink, device 0 finalises.  Results are bit-identical to the single-GPU handle.  The HOST calls (cf_build_jk,
+ * cf_build_g_multi, cf_contract_grads, cf_get_repulsion_diag, cf_get_stats, cf_set_density_threshold) accept such a
+ * handle; the *_device calls do not (they return CF_ERR_BAD_ARGUMENT).  libnccl.so.2 is bound at run time (dlopen);
+ * if it cannot be loaded the call fails (NULL) -- there is no fallback path.  opts->rank / world_size are ignored. */
+cf_handle* cf_create_multi(const cf_basis* basis, const cf_options* opts, int ndev, const int* devices);
+int cf_num_devices(const cf_handle* h);
 const char* cf_last_error(const cf_handle* h);
 int cf_get_stats(const cf_handle* h, cf_stats* out);
 int cf_nbf(const cf_handle* h);
@@ -124,10 +135,11 @@ int cf_set_density_threshold(cf_handle* h, double dthr);
  * (the reference's Diag1212, Int4C2E.cpp:19-77). */
 int cf_get_repulsion_diag(cf_handle* h, double* diag1212);
 
-/* NOTE on partitions: a handle created with world_size > 1 evaluates ITS share of the quartets only.  The host calls
- * below (cf_build_jk, cf_build_g_multi, cf_contract_grads) then return partial results; the multi-GPU route is
- * cf_accumulate_device -> integer all-reduce of the accumulator -> cf_finalize_device (chinium_b200/distributed.py),
- * respectively a sum of the partial gradient vectors. */
+/* NOTE on partitions: a handle created by cf_create with world_size > 1 evaluates ITS share of the quartets only (one
+ * process per GPU, the caller owns the communication): the host calls below then return partial results, and the route
+ * is cf_accumulate_device -> integer all-reduce of the accumulator -> cf_finalize_device (chinium_b200/distributed.py),
+ * respectively a sum of the partial gradient vectors.  A C++ host that simply wants all GPUs of the box uses
+ * cf_create_multi instead and calls cf_build_jk as usual. */
 
 /* The hot call; replaces Int4C2E::ContractInts(Dd,Da,Db,nthreads,output) (Int4C2E.cpp:673-683).
  * HOST pointers. Dd/Da/Db: nullable (absent = the reference's 0x0 matrix). J is always written;

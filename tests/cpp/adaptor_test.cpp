@@ -2,7 +2,10 @@
 // Int4C2E (src/HartreeFockKohnSham/SelfConsistentField.cpp:47-53, Restricted/SP.cpp:47, Restricted/Grad.cpp:66), with a column-major
 // matrix shim standing in for Eigen::MatrixXd.  Input: a flat text dump of the basis and a density written by
 // tests/test_gpu.py; output: J and K as text.  Exit code 3 = "no GPU" (the loud failure the CPU test checks).
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -61,6 +64,20 @@ int main(int argc, char** argv) {
         const std::vector<double> grads = copy.ContractGrads(D, D, 1);     // Restricted/Grad.cpp:66
         out << grads.size() << "\n";
         for (double x : grads) out << x << "\n";
+        if (argc > 3) {   // the same calls through ONE process driving several GPUs (cf_create_multi): must be bit-identical
+            const int nd = std::atoi(argv[3]);
+            Int4C2E multi = Int4C2E::MultiDevice(fb, 1, -1, nd);
+            multi.EXX = 0.5;
+            multi.getRepulsionDiag(0); multi.getRepulsionLength(0); multi.getRepulsionIndices(0); multi.getThreadPointers(4, 0);
+            multi.CalculateIntegrals(0, 0);
+            auto [J2, Kd2, Ka2, Kb2] = multi.ContractInts(D, Mat(0, 0), Mat(0, 0), 4, 1);
+            auto Gs2 = multi.ContractInts(Ds, 4, 1);
+            const std::vector<double> grads2 = multi.ContractGrads(D, D, 0);
+            bool same = J2.v == J.v && Kd2.v == Kd.v && Gs2[1].v == Gs[1].v && multi.RepulsionLength == int4c2e.RepulsionLength;
+            double dg = 0; for (size_t i = 0; i < grads.size(); i++) dg = std::max(dg, std::fabs(grads[i] - grads2[i]));
+            std::printf("multi-device handle: %d GPUs, J/K/G bit-identical to one GPU: %s, max|dgrad| %.3e\n", multi.NumDevices(), same ? "yes" : "NO", dg);
+            out << "MULTI " << multi.NumDevices() << " " << (same ? 1 : 0) << " " << dg << "\n";
+        }
     } catch (const std::exception& e) {
         std::fprintf(stderr, "adaptor_test: %s\n", e.what());
         return std::strstr(e.what(), "no CUDA device") || std::strstr(e.what(), "no CPU fallback") ? 3 : 1;
