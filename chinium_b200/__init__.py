@@ -5,4 +5,4 @@ chinium_b200/csrc (CUDA, sm_100a).  This package is the thin Python mirror of th
 `Int4C2E` interface used by the tests and the benchmark; it loads the library and FAILS LOUDLY if
 it is missing -- there is no CPU fallback anywhere in the product path.
 """
-from .fock import Int4C2E, FockEngineError, load_library, LIB_PATH  # noqa: F401
+from .fock import Int4C2E, Int2C1E, FockEngineError, load_library, LIB_PATH  # noqa: F401

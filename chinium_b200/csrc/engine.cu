@@ -19,6 +19,7 @@
 #include <mutex>
 #include <thread>
 #include <dlfcn.h>
+#include <cub/cub.cuh>         // device radix sort / scan of the setup (pair order, bra-role order)
 #include <nccl.h>              // types and prototypes only: libnccl.so.2 is bound with dlopen when a multi-device handle is created
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +33,7 @@
 #include "eri_generic.cuh"     // rys_tmax/rys_off (host constexpr) -- no kernels instantiated here
 #include "eri_tpq.cuh"         // TPQ_THREADS
 #include "eri_grad.cuh"        // GradTask (kernels are instantiated in eri_inst.cu)
+#include "oneint.cuh"          // one-electron integrals S, T, V
 #include "rys_tables_data.h"
 
 #ifndef CF_BRALOOP_MAXK
@@ -61,30 +63,171 @@ static bra_launch_fn g_bra_launch[CF_NCLS] = {cf_launch_bra0, cf_launch_bra1, cf
 
 static std::string g_last_error;
 
+// Device buffer.  Setup allocates a few hundred arrays (per class, per task): they come from the device's stream-ordered
+// memory pool (cudaMallocAsync on the default stream; the pool keeps freed blocks, so repeated handles cost microseconds
+// per allocation instead of a cudaMalloc each).  `pooled = false` (plain cudaMalloc) is used for the accumulators that
+// NCCL reads and writes over NVLink.
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool pooled = true;
     cudaError_t alloc(size_t count) {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc(&p, count * sizeof(T));
+        if (!pooled) return cudaMalloc(&p, count * sizeof(T));
+        cudaError_t e = cudaMallocAsync(&p, count * sizeof(T), 0);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); pooled = false; e = cudaMalloc(&p, count * sizeof(T)); }
+        return e;
     }
     cudaError_t upload(const std::vector<T>& v) {
         cudaError_t e = alloc(v.size());
         if (e != cudaSuccess || v.empty()) return e;
         return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() {
+        if (p) { if (pooled) cudaFreeAsync(p, 0); else cudaFree(p); }
+        p = nullptr; n = 0;
+    }
 };
+
+// basis arrays on the device (pair build and primitive screening run there, cf_create)
+struct BasisDev {
+    const int* l; const int* nprim; const int* prim_off; const int* cao_off;
+    const double* exps; const double* coefs; const double* xyz;
+};
+
+// One thread per canonical shell pair e = s1 (s1+1)/2 + s2, s2 <= s1 (replaces the reference's pair loops,
+// Int4C2E.cpp:79-231, and round 1's host loop): angular class and number of primitive pairs whose prefactor
+// ca cb exp(-ab/p |AB|^2) sqrt(2) pi^(5/4) / p survives the cutoff.  cls 255 = no primitive left (pair dropped).
+__global__ void pair_classify_kernel(int ns, long long npairs, BasisDev b, double cutoff, unsigned char* __restrict__ cls, int* __restrict__ kept) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= npairs) return;
+    long long s1 = (long long)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+    while (s1 * (s1 + 1) / 2 > e) s1--;
+    while ((s1 + 1) * (s1 + 2) / 2 <= e) s1++;
+    int a = (int)s1, c = (int)(e - s1 * (s1 + 1) / 2);
+    if (b.l[c] > b.l[a]) { const int t = a; a = c; c = t; }
+    const double dx = b.xyz[3 * a] - b.xyz[3 * c], dy = b.xyz[3 * a + 1] - b.xyz[3 * c + 1], dz = b.xyz[3 * a + 2] - b.xyz[3 * c + 2];
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const double pref = 5.9149671727956128778;   // sqrt(2) pi^(5/4)
+    int n = 0;
+    for (int i = 0; i < b.nprim[a]; i++)
+        for (int j = 0; j < b.nprim[c]; j++) {
+            const double ea = b.exps[b.prim_off[a] + i], eb = b.exps[b.prim_off[c] + j], p = ea + eb;
+            const double cc = b.coefs[b.prim_off[a] + i] * b.coefs[b.prim_off[c] + j] * exp(-ea * eb / p * r2) * pref / p;
+            if (fabs(cc) >= cutoff) n++;
+        }
+    kept[e] = n;
+    cls[e] = n ? (unsigned char)cf_pair_class(b.l[a], b.l[c]) : (unsigned char)255;
+}
+
+// Primitive-pair data of one class in device order: one thread per pair writes its SoA entries and its surviving primitives
+// into the interleaved slots pbase[i] + k * CF_PSTRIDE (padding slots were pre-filled with p = 1, c = 0).
+__global__ void pair_fill_kernel(int np, const int* __restrict__ sa, const int* __restrict__ sb, const int* __restrict__ pbase,
+                                 const int* __restrict__ nkeep, BasisDev b,
+                                 double cutoff, int* __restrict__ cao_a, int* __restrict__ cao_b, double* __restrict__ A, double* __restrict__ AB,
+                                 double* __restrict__ p_, double* __restrict__ hp, double* __restrict__ Px, double* __restrict__ Py,
+                                 double* __restrict__ Pz, double* __restrict__ c_, double* __restrict__ aexp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const int a = sa[i], c = sb[i];
+    const double ax = b.xyz[3 * a], ay = b.xyz[3 * a + 1], az = b.xyz[3 * a + 2];
+    const double bx = b.xyz[3 * c], by = b.xyz[3 * c + 1], bz = b.xyz[3 * c + 2];
+    const double dx = ax - bx, dy = ay - by, dz = az - bz, r2 = dx * dx + dy * dy + dz * dz;
+    cao_a[i] = b.cao_off[a]; cao_b[i] = b.cao_off[c];
+    A[3 * (size_t)i] = ax; A[3 * (size_t)i + 1] = ay; A[3 * (size_t)i + 2] = az;
+    AB[3 * (size_t)i] = dx; AB[3 * (size_t)i + 1] = dy; AB[3 * (size_t)i + 2] = dz;
+    const double pref = 5.9149671727956128778;
+    size_t slot = (size_t)pbase[i];
+    int left = nkeep[i];       // the slots were sized by pair_classify_kernel's count: never write more (same arithmetic, same answer)
+    for (int ia = 0; ia < b.nprim[a]; ia++)
+        for (int jb = 0; jb < b.nprim[c]; jb++) {
+            const double ea = b.exps[b.prim_off[a] + ia], eb = b.exps[b.prim_off[c] + jb], p = ea + eb;
+            const double cc = b.coefs[b.prim_off[a] + ia] * b.coefs[b.prim_off[c] + jb] * exp(-ea * eb / p * r2) * pref / p;
+            if (fabs(cc) < cutoff || left <= 0) continue;
+            left--;
+            p_[slot] = p; hp[slot] = 0.5 / p; c_[slot] = cc; aexp[slot] = ea;
+            Px[slot] = (ea * ax + eb * bx) / p; Py[slot] = (ea * ay + eb * by) / p; Pz[slot] = (ea * az + eb * bz) / p;
+            slot += CF_PSTRIDE;
+        }
+}
+__global__ void fill_value_kernel(size_t n, double v, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+// sort keys: pair order inside a class = (primitive count descending, Schwarz bound descending); bra-role order = (shell a
+// ascending, Schwarz bound descending).  Q >= 0, so the bit pattern of the double orders like the value; its top bits
+// are complemented for "descending".  Radix sort is stable and deterministic: ties keep creation order on every rank.
+__global__ void pair_sort_key_kernel(int np, const int* __restrict__ nprim, const double* __restrict__ Q, unsigned long long* __restrict__ key, int* __restrict__ val) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const unsigned long long qb = (unsigned long long)__double_as_longlong(fmax(Q[i], 0.0));
+    const unsigned long long npk = (unsigned long long)(4095 - min(nprim[i], 4095));
+    key[i] = (npk << 52) | ((~qb >> 12) & ((1ull << 52) - 1));
+    val[i] = i;
+}
+__global__ void role_sort_key_kernel(int np, const int* __restrict__ sa, const double* __restrict__ Q, unsigned long long* __restrict__ key, int* __restrict__ val) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const unsigned long long qb = (unsigned long long)__double_as_longlong(fmax(Q[i], 0.0));
+    key[i] = ((unsigned long long)sa[i] << 48) | ((~qb >> 16) & ((1ull << 48) - 1));
+    val[i] = i;
+}
+__global__ void desc_key_kernel(int np, const double* __restrict__ Q, unsigned long long* __restrict__ key, int* __restrict__ val) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    key[i] = ~(unsigned long long)__double_as_longlong(fmax(Q[i], 0.0));
+    val[i] = i;
+}
+template <class T>
+__global__ void gather_kernel(int n, const int* __restrict__ idx, const T* __restrict__ in, T* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[idx[i]];
+}
+// bra-role copy of a class (eri_tpqa.cuh): records + CONTIGUOUS primitives in `border` order, gathered from the slot arrays
+__global__ void role_fill_kernel(int np, const int* __restrict__ border, const int* __restrict__ off, long long tot, const int* __restrict__ sb,
+                                 const int* __restrict__ cao_b, const int* __restrict__ nprim, const int* __restrict__ pbase,
+                                 const double* __restrict__ Q, const double* __restrict__ AB, const double* __restrict__ p,
+                                 const double* __restrict__ hp, const double* __restrict__ Px, const double* __restrict__ Py,
+                                 const double* __restrict__ Pz, const double* __restrict__ c, int4* __restrict__ ri, double* __restrict__ rd,
+                                 double* __restrict__ bp) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= np) return;
+    const int pos = border[e], n = nprim[pos], o = off[e];
+    ri[e] = make_int4(pos, sb[pos] | (n << 16), cao_b[pos], o);
+    rd[4 * (size_t)e] = Q[pos];
+    for (int x = 0; x < 3; x++) rd[4 * (size_t)e + 1 + x] = AB[3 * (size_t)pos + x];
+    for (int k = 0; k < n; k++) {
+        const size_t src = (size_t)pbase[pos] + (size_t)k * CF_PSTRIDE;
+        bp[o + k] = p[src]; bp[tot + o + k] = hp[src]; bp[2 * tot + o + k] = Px[src]; bp[3 * tot + o + k] = Py[src];
+        bp[4 * tot + o + k] = Pz[src]; bp[5 * tot + o + k] = c[src];
+    }
+}
+
+// stable device radix sort of (key, value) pairs; returns the sorted values in `vals` (keys are scratch)
+static cudaError_t device_sort_pairs(int n, unsigned long long* keys, int* vals) {
+    if (n <= 1) return cudaSuccess;
+    unsigned long long* k2 = nullptr; int* v2 = nullptr; void* tmp = nullptr; size_t bytes = 0;
+    cudaError_t e;
+    if ((e = cudaMalloc(&k2, sizeof(unsigned long long) * n)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&v2, sizeof(int) * n)) != cudaSuccess) { cudaFree(k2); return e; }
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, k2, vals, v2, n);
+    if ((e = cudaMalloc(&tmp, bytes)) == cudaSuccess) {
+        e = cub::DeviceRadixSort::SortPairs(tmp, bytes, keys, k2, vals, v2, n);
+        if (e == cudaSuccess) e = cudaMemcpy(vals, v2, sizeof(int) * n, cudaMemcpyDeviceToDevice);
+    }
+    cudaFree(tmp); cudaFree(k2); cudaFree(v2);
+    return e;
+}
 
 struct PairClassHost {
     int la = 0, lb = 0;
-    // canonical host storage: pairs in creation order, primitives contiguous per pair (prim_off / nprim)
-    std::vector<int> sa, sb, cao_a, cao_b, prim_off, nprim, nprim_full;
-    std::vector<double> A, AB, Q, Qpure, p, P, c, aexp /* exponent of shell a per primitive pair (derivatives) */;
-    std::vector<int> order;          // device position -> canonical pair index
+    // host copies in DEVICE order (pairs sorted by (primitive count desc, Schwarz bound desc) once the bounds exist)
+    std::vector<int> sa, sb, nprim, nprim_full;
+    std::vector<double> Q, Qpure;    // Cartesian / pure-function Schwarz bounds
+    std::vector<int> order;          // identity (kept for the position -> pair indirection of the host helpers)
     std::vector<int> seg;            // device positions where the primitive count changes (+ npair): Q descends inside a segment
     DevBuf<int> d_sa, d_sb, d_cao_a, d_cao_b, d_pbase, d_nprim, d_seg;
     DevBuf<double> d_A, d_AB, d_Q, d_Qcart, d_p, d_hp, d_Px, d_Py, d_Pz, d_c, d_aexp;
@@ -105,98 +248,100 @@ struct PairClassHost {
         d.p = d_p.p; d.hp = d_hp.p; d.Px = d_Px.p; d.Py = d_Py.p; d.Pz = d_Pz.p; d.c = d_c.p;
         return d;
     }
-    // device layout for the pair order `order`: blocks of CF_PSTRIDE pairs with interleaved primitives
-    cudaError_t upload() {
+    // device layout for the current host order: blocks of CF_PSTRIDE pairs with interleaved primitives.  The host only
+    // lays out the slot bases (a prefix sum over blocks); every primitive is generated by pair_fill_kernel on the device.
+    cudaError_t layout_and_fill(const BasisDev& b, double cutoff) {
         const int np = npair();
-        if ((int)order.size() != np) { order.resize(np); std::iota(order.begin(), order.end(), 0); }
-        std::vector<int> o_sa(np), o_sb(np), o_ca(np), o_cb(np), o_pbase(np), o_np(np);
-        std::vector<double> o_A(3 * (size_t)np), o_AB(3 * (size_t)np), o_Q(np);
+        order.resize(np); std::iota(order.begin(), order.end(), 0);
+        std::vector<int> pbase(np);
         size_t nslot = 0;
         for (int b0 = 0; b0 < np; b0 += CF_PSTRIDE) {
             int mx = 0;
-            for (int i = b0; i < std::min(np, b0 + CF_PSTRIDE); i++) mx = std::max(mx, nprim[order[i]]);
-            for (int i = b0; i < std::min(np, b0 + CF_PSTRIDE); i++) o_pbase[i] = (int)(nslot + (i - b0));
+            for (int i = b0; i < std::min(np, b0 + CF_PSTRIDE); i++) mx = std::max(mx, nprim[i]);
+            for (int i = b0; i < std::min(np, b0 + CF_PSTRIDE); i++) pbase[i] = (int)(nslot + (i - b0));
             nslot += (size_t)mx * CF_PSTRIDE;
         }
         if (nslot > 0x7fffffffull) return cudaErrorInvalidValue;
-        std::vector<double> o_p(nslot, 1.0), o_hp(nslot, 0.5), o_Px(nslot, 0.0), o_Py(nslot, 0.0), o_Pz(nslot, 0.0), o_c(nslot, 0.0), o_ae(nslot, 0.5);
-        for (int i = 0; i < np; i++) {
-            const int s = order[i];
-            o_sa[i] = sa[s]; o_sb[i] = sb[s]; o_ca[i] = cao_a[s]; o_cb[i] = cao_b[s]; o_np[i] = nprim[s]; o_Q[i] = Qpure[s];
-            for (int x = 0; x < 3; x++) { o_A[3 * (size_t)i + x] = A[3 * (size_t)s + x]; o_AB[3 * (size_t)i + x] = AB[3 * (size_t)s + x]; }
-            for (int k = 0; k < nprim[s]; k++) {
-                const size_t slot = (size_t)o_pbase[i] + (size_t)k * CF_PSTRIDE, src = (size_t)prim_off[s] + k;
-                o_p[slot] = p[src]; o_hp[slot] = 0.5 / p[src]; o_c[slot] = c[src]; o_ae[slot] = aexp[src];
-                o_Px[slot] = P[3 * src]; o_Py[slot] = P[3 * src + 1]; o_Pz[slot] = P[3 * src + 2];
-            }
-        }
         cudaError_t e;
-        if ((e = d_sa.upload(o_sa)) != cudaSuccess) return e;
-        if ((e = d_sb.upload(o_sb)) != cudaSuccess) return e;
-        if ((e = d_cao_a.upload(o_ca)) != cudaSuccess) return e;
-        if ((e = d_cao_b.upload(o_cb)) != cudaSuccess) return e;
-        if ((e = d_pbase.upload(o_pbase)) != cudaSuccess) return e;
-        if ((e = d_nprim.upload(o_np)) != cudaSuccess) return e;
-        if ((e = d_A.upload(o_A)) != cudaSuccess) return e;
-        if ((e = d_AB.upload(o_AB)) != cudaSuccess) return e;
-        if ((e = d_Q.upload(o_Q)) != cudaSuccess) return e;
-        if ((e = d_p.upload(o_p)) != cudaSuccess) return e;
-        if ((e = d_hp.upload(o_hp)) != cudaSuccess) return e;
-        if ((e = d_Px.upload(o_Px)) != cudaSuccess) return e;
-        if ((e = d_Py.upload(o_Py)) != cudaSuccess) return e;
-        if ((e = d_Pz.upload(o_Pz)) != cudaSuccess) return e;
-        if ((e = d_aexp.upload(o_ae)) != cudaSuccess) return e;
+        if ((e = d_sa.upload(sa)) != cudaSuccess) return e;
+        if ((e = d_sb.upload(sb)) != cudaSuccess) return e;
+        if ((e = d_pbase.upload(pbase)) != cudaSuccess) return e;
+        if ((e = d_nprim.upload(nprim)) != cudaSuccess) return e;
+        if ((e = d_cao_a.alloc(np)) != cudaSuccess || (e = d_cao_b.alloc(np)) != cudaSuccess) return e;
+        if ((e = d_A.alloc(3 * (size_t)np)) != cudaSuccess || (e = d_AB.alloc(3 * (size_t)np)) != cudaSuccess) return e;
+        if (d_Q.n != (size_t)np && (e = d_Q.alloc(np)) != cudaSuccess) return e;
+        DevBuf<double>* slots[7] = {&d_p, &d_hp, &d_Px, &d_Py, &d_Pz, &d_c, &d_aexp};
+        const double fillv[7] = {1.0, 0.5, 0.0, 0.0, 0.0, 0.0, 0.5};
+        for (int k = 0; k < 7; k++) {
+            if ((e = slots[k]->alloc(nslot)) != cudaSuccess) return e;
+            if (nslot) fill_value_kernel<<<(unsigned)((nslot + 255) / 256), 256>>>(nslot, fillv[k], slots[k]->p);
+        }
         seg.clear();
-        for (int i = 0; i < np; i++) if (i == 0 || o_np[i] != o_np[i - 1]) seg.push_back(i);
+        for (int i = 0; i < np; i++) if (i == 0 || nprim[i] != nprim[i - 1]) seg.push_back(i);
         seg.push_back(np);
         if ((e = d_seg.upload(seg)) != cudaSuccess) return e;
-        return d_c.upload(o_c);
+        if (np) pair_fill_kernel<<<(np + 127) / 128, 128>>>(np, d_sa.p, d_sb.p, d_pbase.p, d_nprim.p, b, cutoff, d_cao_a.p, d_cao_b.p, d_A.p, d_AB.p,
+                                                             d_p.p, d_hp.p, d_Px.p, d_Py.p, d_Pz.p, d_c.p, d_aexp.p);
+        return cudaGetLastError();
     }
-    double qpos(int pos) const { return Qpure[order[pos]]; }
-    // needs `order` (device position -> canonical pair) and Qpure
+    // after the Schwarz kernels: order = device radix sort by (primitive count desc, pure Schwarz bound desc); the host
+    // copies and the device bounds are permuted accordingly, then the class is laid out again in that order
+    cudaError_t sort_by_bounds(const BasisDev& b, double cutoff, const double* d_qpure) {
+        const int np = npair();
+        if (np == 0) return cudaSuccess;
+        DevBuf<unsigned long long> key; DevBuf<int> val; DevBuf<double> q2;
+        cudaError_t e;
+        if ((e = key.alloc(np)) != cudaSuccess || (e = val.alloc(np)) != cudaSuccess || (e = q2.alloc(np)) != cudaSuccess) return e;
+        pair_sort_key_kernel<<<(np + 255) / 256, 256>>>(np, d_nprim.p, d_qpure, key.p, val.p);
+        if ((e = device_sort_pairs(np, key.p, val.p)) != cudaSuccess) return e;
+        std::vector<int> perm(np);
+        std::vector<double> qc(np), qp(np);
+        gather_kernel<double><<<(np + 255) / 256, 256>>>(np, val.p, d_Qcart.p, q2.p);
+        if ((e = cudaMemcpy(qc.data(), q2.p, sizeof(double) * np, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+        gather_kernel<double><<<(np + 255) / 256, 256>>>(np, val.p, d_qpure, q2.p);
+        if ((e = cudaMemcpy(qp.data(), q2.p, sizeof(double) * np, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+        if ((e = cudaMemcpy(perm.data(), val.p, sizeof(int) * np, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+        auto permute = [&](std::vector<int>& v) { std::vector<int> t(np); for (int i = 0; i < np; i++) t[i] = v[perm[i]]; v.swap(t); };
+        permute(sa); permute(sb); permute(nprim); permute(nprim_full);
+        Q = qc; Qpure = qp;
+        if ((e = layout_and_fill(b, cutoff)) != cudaSuccess) return e;
+        if ((e = d_Qcart.upload(Q)) != cudaSuccess) return e;
+        e = d_Q.upload(Qpure);
+        key.release(); val.release(); q2.release();
+        return e;
+    }
+    double qpos(int pos) const { return Qpure[pos]; }
+    // bra / ket roles of the bra-loop kernels; needs the sorted layout and Qpure
     cudaError_t build_roles() {
         const int np = npair();
         nblk = (np + 31) / 32;
         border.resize(np); group.clear();
         if (np == 0) return cudaSuccess;
-        std::iota(border.begin(), border.end(), 0);
-        std::stable_sort(border.begin(), border.end(), [&](int x, int y) {
-            const int ax = sa[order[x]], ay = sa[order[y]];
-            if (ax != ay) return ax < ay;
-            return qpos(x) > qpos(y);
-        });
-        for (int i = 0; i < np; i++) if (i == 0 || sa[order[border[i]]] != sa[order[border[i - 1]]]) group.push_back(i);
+        DevBuf<unsigned long long> key; DevBuf<int> val, d_off;
+        cudaError_t e;
+        if ((e = key.alloc(np)) != cudaSuccess || (e = val.alloc(np)) != cudaSuccess) return e;
+        role_sort_key_kernel<<<(np + 255) / 256, 256>>>(np, d_sa.p, d_Q.p, key.p, val.p);
+        if ((e = device_sort_pairs(np, key.p, val.p)) != cudaSuccess) return e;
+        if ((e = cudaMemcpy(border.data(), val.p, sizeof(int) * np, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+        for (int i = 0; i < np; i++) if (i == 0 || sa[border[i]] != sa[border[i - 1]]) group.push_back(i);
         group.push_back(np);
         std::vector<double> bq(nblk, 0.0);
         for (int i = 0; i < np; i++) bq[i / 32] = std::max(bq[i / 32], qpos(i));
-        // bra-role copy in border order: records + contiguous primitives
-        std::vector<int4> ri(np);
-        std::vector<double> rd(4 * (size_t)np);
+        std::vector<int> off(np);
         size_t tot = 0;
-        for (int e = 0; e < np; e++) tot += nprim[order[border[e]]];
-        bprim_stride = (long long)tot;
-        std::vector<double> bp(6 * tot);
-        size_t off = 0;
-        for (int e = 0; e < np; e++) {
-            const int s = order[border[e]];
-            if (nprim[s] >= 32768 || off > 0x7fffffffull) return cudaErrorInvalidValue;
-            ri[e] = make_int4(border[e], sb[s] | (nprim[s] << 16), cao_b[s], (int)off);
-            rd[4 * (size_t)e] = Qpure[s];
-            for (int x = 0; x < 3; x++) rd[4 * (size_t)e + 1 + x] = AB[3 * (size_t)s + x];
-            for (int k = 0; k < nprim[s]; k++) {
-                const size_t src = (size_t)prim_off[s] + k;
-                bp[off + k] = p[src]; bp[tot + off + k] = 0.5 / p[src];
-                bp[2 * tot + off + k] = P[3 * src]; bp[3 * tot + off + k] = P[3 * src + 1]; bp[4 * tot + off + k] = P[3 * src + 2];
-                bp[5 * tot + off + k] = c[src];
-            }
-            off += nprim[s];
+        for (int i = 0; i < np; i++) {
+            if (nprim[border[i]] >= 32768 || tot > 0x7fffffffull) return cudaErrorInvalidValue;
+            off[i] = (int)tot; tot += nprim[border[i]];
         }
-        cudaError_t e;
-        if ((e = d_border.upload(border)) != cudaSuccess) return e;
-        if ((e = d_brec_i.upload(ri)) != cudaSuccess) return e;
-        if ((e = d_brec_d.upload(rd)) != cudaSuccess) return e;
-        if ((e = d_bprim.upload(bp)) != cudaSuccess) return e;
-        return d_blkQ.upload(bq);
+        bprim_stride = (long long)tot;
+        if ((e = d_border.upload(border)) != cudaSuccess || (e = d_off.upload(off)) != cudaSuccess) return e;
+        if ((e = d_brec_i.alloc(np)) != cudaSuccess || (e = d_brec_d.alloc(4 * (size_t)np)) != cudaSuccess || (e = d_bprim.alloc(6 * tot)) != cudaSuccess) return e;
+        role_fill_kernel<<<(np + 127) / 128, 128>>>(np, d_border.p, d_off.p, (long long)tot, d_sb.p, d_cao_b.p, d_nprim.p, d_pbase.p, d_Q.p, d_AB.p,
+                                                     d_p.p, d_hp.p, d_Px.p, d_Py.p, d_Pz.p, d_c.p, d_brec_i.p, d_brec_d.p, d_bprim.p);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        e = d_blkQ.upload(bq);
+        key.release(); val.release(); d_off.release();
+        return e;
     }
     // chunks of consecutive entries of `border` inside one a-group: at most lch pairs and (after the first pair) at most
     // pcap primitive pairs, so that the cost of a work item is bounded; heaviest chunks first (static schedule, short tail)
@@ -207,7 +352,7 @@ struct PairClassHost {
             for (int c0 = group[g]; c0 < group[g + 1];) {
                 int n = 0, mx = 0; double cost = 0;
                 while (c0 + n < group[g + 1] && n < lch) {
-                    const double np1 = nprim[order[border[c0 + n]]];
+                    const double np1 = nprim[border[c0 + n]];
                     if (n > 0 && cost + np1 > pcap) break;
                     cost += np1; mx = std::max(mx, border[c0 + n]); n++;
                 }
@@ -251,7 +396,8 @@ struct cf_handle {
     std::vector<int> type, l, nprim, prim_off, bf_off, cao_off, nfun;
     std::vector<double> exps, coefs, xyz;
     std::vector<int> shell2atom;           // empty when the caller gave none (gradients then refuse)
-    DevBuf<int> d_shell2atom;
+    DevBuf<int> d_shell2atom, d_l, d_nprim_sh, d_prim_off_sh;
+    DevBuf<double> d_exps, d_coefs, d_xyz, d_atomZ, d_atomxyz;
     DevBuf<double> d_gpart, d_grad;
     // per-shell transformation (function x cartesian), pooled by type
     std::vector<double> ctrans;            // pool
@@ -601,23 +747,32 @@ __global__ void ref_count_special_kernel(int ns, int nbf, const int* __restrict_
         const int s2 = (int)(e / (s1 + 1)), s4 = (int)(e % (s1 + 1));
         if (!(P[(size_t)s1 * ns + s2] * P[(size_t)s1 * ns + s4] > thr)) continue;
         const int n2 = nfun[s2], o2 = bf_off[s2], n4 = nfun[s4], o4 = bf_off[s4];
-        int uniq = 0; bool keep = false;
-        for (int f1 = 0; f1 < n1; f1++) {
+        bool keep = false;
+        for (int f1 = 0; f1 < n1 && !keep; f1++) {
             const int bf1 = o1 + f1;
-            for (int f2 = 0; f2 < n2; f2++) {
+            for (int f2 = 0; f2 < n2 && !keep; f2++) {
                 const int bf2 = o2 + f2;
                 if (bf2 > bf1) break;
                 const double d12 = diag[(size_t)bf2 * nbf + bf1];
-                for (int f3 = 0; f3 <= f1; f3++) {
+                for (int f3 = 0; f3 <= f1 && !keep; f3++) {
                     const int bf3 = o1 + f3;
                     const int lim = (bf1 == bf3) ? bf2 : bf3;
                     for (int f4 = 0; f4 < n4; f4++) {
                         const int bf4 = o4 + f4;
                         if (bf4 > lim) break;
-                        uniq++;
-                        if (sqrt(fabs(d12 * diag[(size_t)bf4 * nbf + bf3])) > thr) keep = true;
+                        if (sqrt(fabs(d12 * diag[(size_t)bf4 * nbf + bf3])) > thr) { keep = true; break; }
                     }
                 }
+            }
+        }
+        int uniq = 0;
+        if (keep) {   // number of unique function quartets: a count over (f1, f3 <= f1) with closed forms for f2 and f4
+            for (int f1 = 0; f1 < n1; f1++) {
+                const int c2 = s2 < s1 ? n2 : f1 + 1;                       // f2 with bf2 <= bf1
+                for (int f3 = 0; f3 < f1; f3++) uniq += c2 * (s4 < s1 ? n4 : f3 + 1);      // bf4 <= bf3
+                // f3 == f1: bf4 <= bf2
+                if (s4 < s2) uniq += c2 * n4;
+                else if (s4 == s2) uniq += c2 * (c2 + 1) / 2;               // sum over f2 < c2 of (f2 + 1)
             }
         }
         if (keep) { nq++; ni += (unsigned long long)uniq; }
@@ -688,6 +843,11 @@ static int check_device(cf_handle* h, int device) {
     if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { set_error(h, "cudaGetDeviceProperties failed"); return CF_ERR_NO_DEVICE; }
     if (p.major != 10) { set_error(h, "device is not sm_100 (kernels are built for sm_100a only)"); return CF_ERR_NO_DEVICE; }
     if (cudaSetDevice(device) != cudaSuccess) { set_error(h, "cudaSetDevice failed"); return CF_ERR_NO_DEVICE; }
+    {   // the default memory pool keeps what setup frees (DevBuf): later allocations are served from it
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { unsigned long long keep = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+        (void)cudaGetLastError();
+    }
     if (h) h->device = device;
     return CF_OK;
 }
@@ -805,6 +965,8 @@ extern "C" void cf_destroy(cf_handle* h) {
     h->d_partial.release(); h->d_diag.release(); h->d_acc.release(); h->d_cnt.release();
     h->d_QS.release(); h->d_B.release(); h->d_Bmax.release(); h->d_rwork.release();
     h->d_shell2atom.release(); h->d_gpart.release(); h->d_grad.release();
+    h->d_atomZ.release(); h->d_atomxyz.release();
+    h->d_l.release(); h->d_nprim_sh.release(); h->d_prim_off_sh.release(); h->d_exps.release(); h->d_coefs.release(); h->d_xyz.release();
     for (auto& e : h->ev) cudaEventDestroy(e);
     for (int i = 0; i < 3; i++) { cudaStreamDestroy(h->side[i]); cudaEventDestroy(h->ev_join[i]); }
     cudaEventDestroy(h->ev_fork);
@@ -832,6 +994,15 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     if (h->opt.pair_cutoff <= 0) h->opt.pair_cutoff = 1e-20;
     if (check_device(h, h->opt.device) != CF_OK) { g_last_error = h->err; delete h; return nullptr; }
     const double t_start = now_s();
+    const bool timing = h->opt.verbose >= 2 || getenv("CF_SETUP_TIMING") != nullptr;
+    double t_mark = t_start;
+    auto mark = [&](const char* what) {
+        if (!timing) return;
+        cudaDeviceSynchronize();
+        const double t = now_s();
+        std::fprintf(stderr, "  [cf_create] %-28s %8.3f ms\n", what, (t - t_mark) * 1e3);
+        t_mark = t;
+    };
     auto fail = [&](const std::string& s) -> cf_handle* { set_error(nullptr, s); cf_destroy(h); return nullptr; };
     for (auto& e : h->ev) cudaEventCreate(&e);
     for (int i = 0; i < 3; i++) { cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming); }
@@ -889,47 +1060,51 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
         UP(h->d_boys, boys);
     }
 
-    // ---- shell pairs by class
-    const double pref = std::sqrt(2.0) * std::pow(M_PI, 1.25);
+    mark("shells + tables");
+    // ---- shell pairs: built, primitive-screened, Schwarz-bounded and sorted ON THE DEVICE (north_star; replaces the
+    // reference's serial pair loops, Int4C2E.cpp:19-231).  The host only buckets pair ids by class and lays out slot bases.
     for (int la = 0; la <= CF_LMAX_DEV; la++)
         for (int lb = 0; lb <= la; lb++) { auto& c = h->cls[cf_pair_class(la, lb)]; c.la = la; c.lb = lb; }
+    UP(h->d_l, h->l); UP(h->d_nprim_sh, h->nprim); UP(h->d_prim_off_sh, h->prim_off); UP(h->d_exps, h->exps); UP(h->d_coefs, h->coefs); UP(h->d_xyz, h->xyz);
+    BasisDev bd;
+    bd.l = h->d_l.p; bd.nprim = h->d_nprim_sh.p; bd.prim_off = h->d_prim_off_sh.p; bd.cao_off = h->d_cao_off.p;
+    bd.exps = h->d_exps.p; bd.coefs = h->d_coefs.p; bd.xyz = h->d_xyz.p;
+    const double cutoff = h->opt.pair_cutoff;
     long long pairs_kept = 0;
-    for (int s1 = 0; s1 < ns; s1++)
-        for (int s2 = 0; s2 <= s1; s2++) {
-            int a = s1, b = s2;
-            if (h->l[b] > h->l[a]) std::swap(a, b);
-            PairClassHost& c = h->cls[cf_pair_class(h->l[a], h->l[b])];
-            const double* A = &h->xyz[3 * a];
-            const double* B = &h->xyz[3 * b];
-            const double ab[3] = {A[0] - B[0], A[1] - B[1], A[2] - B[2]};
-            const double r2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
-            const int p0 = (int)c.p.size();
-            int kept = 0;
-            for (int i = 0; i < h->nprim[a]; i++)
-                for (int j = 0; j < h->nprim[b]; j++) {
-                    const double ea = h->exps[h->prim_off[a] + i], eb = h->exps[h->prim_off[b] + j];
-                    const double p = ea + eb;
-                    const double cc = h->coefs[h->prim_off[a] + i] * h->coefs[h->prim_off[b] + j] * std::exp(-ea * eb / p * r2) * pref / p;
-                    if (std::fabs(cc) < h->opt.pair_cutoff) continue;
-                    c.p.push_back(p);
-                    for (int x = 0; x < 3; x++) c.P.push_back((ea * A[x] + eb * B[x]) / p);
-                    c.c.push_back(cc);
-                    c.aexp.push_back(ea);
-                    kept++;
-                }
-            if (kept == 0) continue;
-            c.sa.push_back(a); c.sb.push_back(b);
-            c.cao_a.push_back(h->cao_off[a]); c.cao_b.push_back(h->cao_off[b]);
-            c.prim_off.push_back(p0); c.nprim.push_back(kept); c.nprim_full.push_back(h->nprim[a] * h->nprim[b]);
-            for (int x = 0; x < 3; x++) { c.A.push_back(A[x]); c.AB.push_back(ab[x]); }
-            c.Q.push_back(0.0); c.Qpure.push_back(0.0);
-            pairs_kept++;
-        }
-    for (auto& c : h->cls) if (c.upload() != cudaSuccess) return fail("pair upload failed");
+    {
+        const long long npairs_tot = (long long)ns * (ns + 1) / 2;
+        DevBuf<unsigned char> d_cls; DevBuf<int> d_kept;
+        if (d_cls.alloc(npairs_tot) != cudaSuccess || d_kept.alloc(npairs_tot) != cudaSuccess) return fail("cudaMalloc failed (pair classification)");
+        pair_classify_kernel<<<(unsigned)((npairs_tot + 127) / 128), 128>>>(ns, npairs_tot, bd, cutoff, d_cls.p, d_kept.p);
+        std::vector<unsigned char> cls_h(npairs_tot); std::vector<int> kept_h(npairs_tot);
+        if (cudaMemcpy(cls_h.data(), d_cls.p, npairs_tot, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(kept_h.data(), d_kept.p, sizeof(int) * npairs_tot, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(std::string("pair classification kernel failed: ") + cudaGetErrorString(cudaGetLastError()));
+        d_cls.release(); d_kept.release();
+        long long e = 0;
+        for (int s1 = 0; s1 < ns; s1++)
+            for (int s2 = 0; s2 <= s1; s2++, e++) {
+                if (cls_h[e] == 255) continue;
+                int a = s1, b = s2;
+                if (h->l[b] > h->l[a]) std::swap(a, b);
+                PairClassHost& c = h->cls[cls_h[e]];
+                c.sa.push_back(a); c.sb.push_back(b);
+                c.nprim.push_back(kept_h[e]); c.nprim_full.push_back(h->nprim[a] * h->nprim[b]);
+                c.Q.push_back(0.0); c.Qpure.push_back(0.0);
+                pairs_kept++;
+            }
+    }
+    mark("pair classify + bucket");
+    for (auto& c : h->cls) if (c.layout_and_fill(bd, cutoff) != cudaSuccess) return fail("pair layout failed");
+    mark("pair fill (device)");
 
-    // ---- Schwarz bounds: (ab|ab) Cartesian blocks from the quartet kernel in STORE/diag mode
+    // ---- Schwarz bounds: (ab|ab) Cartesian blocks from the quartet kernel in STORE/diag mode; then the class is sorted
+    // by (primitive count desc, pure-function Schwarz bound desc) with a device radix sort and laid out in that order.
+    // Equal primitive counts inside a warp keep the per-thread primitive loops of the thread-per-quartet kernels
+    // convergent; heavy pairs first gives the static schedule a short tail.
     if (h->d_diag.alloc((size_t)nbf * nbf) != cudaSuccess) return fail("cudaMalloc failed (diag)");
     cudaMemset(h->d_diag.p, 0, sizeof(double) * (size_t)nbf * nbf);
+    h->qmax_cart = 0;
     for (int ci = 0; ci < CF_NCLS; ci++) {
         PairClassHost& c = h->cls[ci];
         const int np = c.npair();
@@ -954,30 +1129,15 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
             schwarz_kernel<<<cnt, 128>>>(cnt, nca, ncb, blocks.p, c.d_sa.p + p0, c.d_sb.p + p0, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
                                          h->d_nfun.p, nbf, c.d_Qcart.p + p0, qpure.p + p0, h->d_diag.p);
         }
-        if (cudaMemcpy(c.Q.data(), c.d_Qcart.p, sizeof(double) * np, cudaMemcpyDeviceToHost) != cudaSuccess ||
-            cudaMemcpy(c.Qpure.data(), qpure.p, sizeof(double) * np, cudaMemcpyDeviceToHost) != cudaSuccess)
-            return fail(std::string("Schwarz kernels failed: ") + cudaGetErrorString(cudaGetLastError()));
-        blocks.release(); qpure.release();
+        blocks.release();
+        if (c.sort_by_bounds(bd, cutoff, qpure.p) != cudaSuccess)
+            return fail(std::string("Schwarz kernels / class sort failed: ") + cudaGetErrorString(cudaGetLastError()));
+        qpure.release();
+        for (double q : c.Q) h->qmax_cart = std::max(h->qmax_cart, q);
+        if (c.build_roles() != cudaSuccess) return fail("bra/ket role build failed");
     }
     h->diag_ready = true;
-
-    // ---- sort each class by (primitive count desc, pure-function Schwarz bound desc); re-upload in that order.
-    // Equal primitive counts inside a warp keep the per-thread primitive loops of the thread-per-quartet kernels
-    // convergent; heavy pairs first gives the static schedule a short tail.
-    h->qmax_cart = 0;
-    for (auto& c : h->cls) {
-        const int np = c.npair();
-        if (np == 0) continue;
-        c.order.resize(np);
-        std::iota(c.order.begin(), c.order.end(), 0);
-        std::stable_sort(c.order.begin(), c.order.end(), [&](int x, int y) {
-            if (c.nprim[x] != c.nprim[y]) return c.nprim[x] > c.nprim[y];
-            return c.Qpure[x] > c.Qpure[y];
-        });
-        for (double q : c.Q) h->qmax_cart = std::max(h->qmax_cart, q);
-        if (c.upload() != cudaSuccess) return fail("pair re-upload failed");
-        if (c.build_roles() != cudaSuccess) return fail("bra/ket role upload failed");
-    }
+    mark("Schwarz + device sort + roles");
     {   // dense Cartesian Schwarz matrix over shell pairs (0 for pairs dropped by the primitive cutoff)
         std::vector<double> QS((size_t)ns * ns, 0.0);
         for (auto& c : h->cls)
@@ -1045,6 +1205,7 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
         }
         h->ref_counts[0] = ni_ref; h->ref_counts[1] = nq_ref;
     }
+    mark("QS matrix + reference counts");
 
     // ---- class-pair tasks.  Quartet (ib, ik) of a task is canonical iff ik <= ib when bra class == ket class.
     // Schwarz screening (threshold > 0, Int4C2E.cpp:108-113) is a per-quartet test Q_b * Q_k > thr inside the kernels;
@@ -1056,6 +1217,8 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     st.ref_repulsion_length = h->ref_counts[0]; st.ref_shell_quartet_length = h->ref_counts[1];
     st.shell_pairs_total = (long long)ns * (ns + 1) / 2;
     st.shell_pairs_kept = pairs_kept;
+    struct KetByQ { std::vector<double> qs, pre_prim, pre_primfull, pre_uniq; };
+    std::vector<KetByQ> ketq(CF_NCLS);
     for (int cb = 0; cb < CF_NCLS; cb++)
         for (int ck = 0; ck <= cb; ck++) {
             const PairClassHost& B = h->cls[cb];
@@ -1066,25 +1229,36 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
             const int nb = B.npair(), nk = K.npair();
             const bool same = (cb == ck);
             const int nfa = h->nfun[B.sa[0]], nfb = h->nfun[B.sb[0]], nfc = h->nfun[K.sa[0]], nfd = h->nfun[K.sb[0]];
-            // kets by descending Q with prefix sums of the per-pair weights
-            std::vector<int> kq(nk);
-            std::iota(kq.begin(), kq.end(), 0);
-            std::sort(kq.begin(), kq.end(), [&](int x, int y) { return K.Qpure[x] > K.Qpure[y]; });
-            std::vector<double> qs(nk), pre_prim(nk + 1, 0.0), pre_primfull(nk + 1, 0.0), pre_uniq(nk + 1, 0.0);
+            // kets by descending Q with prefix sums of the per-pair weights: a property of the ket class, built once per class
             auto nfun_pair = [](bool diag, int n1, int n2) { return diag ? n1 * (n1 + 1) / 2.0 : (double)n1 * n2; };
-            for (int k = 0; k < nk; k++) {
-                const int s = kq[k];
-                qs[k] = K.Qpure[s];
-                pre_prim[k + 1] = pre_prim[k] + K.nprim[s];
-                pre_primfull[k + 1] = pre_primfull[k] + K.nprim_full[s];
-                pre_uniq[k + 1] = pre_uniq[k] + nfun_pair(K.sa[s] == K.sb[s], nfc, nfd);
+            KetByQ& kb = ketq[ck];
+            if (kb.qs.empty()) {
+                std::vector<int> kq(nk);
+                {   // order by descending Q: device radix sort on the class's bound array (ties in creation order)
+                    DevBuf<unsigned long long> key; DevBuf<int> val;
+                    if (key.alloc(nk) != cudaSuccess || val.alloc(nk) != cudaSuccess) { delete t; return fail("cudaMalloc failed (ket order)"); }
+                    desc_key_kernel<<<(nk + 255) / 256, 256>>>(nk, K.d_Q.p, key.p, val.p);
+                    if (device_sort_pairs(nk, key.p, val.p) != cudaSuccess ||
+                        cudaMemcpy(kq.data(), val.p, sizeof(int) * nk, cudaMemcpyDeviceToHost) != cudaSuccess) { delete t; return fail("ket order sort failed"); }
+                    key.release(); val.release();
+                }
+                kb.qs.resize(nk); kb.pre_prim.assign(nk + 1, 0.0); kb.pre_primfull.assign(nk + 1, 0.0); kb.pre_uniq.assign(nk + 1, 0.0);
+                for (int k = 0; k < nk; k++) {
+                    const int s = kq[k];
+                    kb.qs[k] = K.Qpure[s];
+                    kb.pre_prim[k + 1] = kb.pre_prim[k] + K.nprim[s];
+                    kb.pre_primfull[k + 1] = kb.pre_primfull[k] + K.nprim_full[s];
+                    kb.pre_uniq[k + 1] = kb.pre_uniq[k] + nfun_pair(K.sa[s] == K.sb[s], nfc, nfd);
+                }
             }
+            const std::vector<double>&qs = kb.qs, &pre_prim = kb.pre_prim, &pre_primfull = kb.pre_primfull, &pre_uniq = kb.pre_uniq;
             const int L = B.la + B.lb + K.la + K.lb, nr = L / 2 + 1;
             const double per_prim = nr * (40.0 + 12.0 * (B.la + B.lb + 1) * (K.la + K.lb + 1) +
                                           3.0 * cf_ncart(B.la) * cf_ncart(B.lb) * cf_ncart(K.la) * cf_ncart(K.lb));
             double nq = 0, uniq = 0, primq = 0, primq_full = 0;        // over ordered (bra, ket) combinations
             double dq = 0, duniq = 0, dprimq = 0, dprimq_full = 0;     // diagonal (i, i) part, same class only
             double uniq_fix = 0;
+#pragma omp parallel for reduction(+ : nq, uniq, primq, primq_full, dq, duniq, dprimq, dprimq_full, uniq_fix) schedule(static)
             for (int i = 0; i < nb; i++) {
                 int cnt = nk;
                 if (thr > 0) {
@@ -1190,6 +1364,7 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
             }
             h->tasks.push_back(t);
         }
+    mark("tasks: stats + item lists");
     st.canonical_quartets_local = st.canonical_quartets / h->opt.world_size;
     if (h->opt.world_size > 1) { for (int k = 0; k < 4; k++) st.flops_alg_jk[k] /= h->opt.world_size; st.flops_alg_grad /= h->opt.world_size; }
     // heavy tasks first so the tail of the build is made of small kernels
@@ -1204,6 +1379,7 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     for (auto& b : h->d_Dcart) ok = ok && b.alloc(n2c) == cudaSuccess;
     for (auto& b : h->d_out) ok = ok && b.alloc(n2p) == cudaSuccess;
     // accumulator of the host calls: up to [J_0..J_2 | K_0..K_2 | Jlo_0..Jlo_2 | tail] (multi-density build)
+    h->d_acc.pooled = false;      // NCCL works on it (cf_create_multi)
     ok = ok && h->d_acc.alloc(9 * n2c + CF_ACC_TAIL) == cudaSuccess && h->d_partial.alloc(4 * 256) == cudaSuccess &&
          h->d_cnt.alloc(std::max<size_t>(1, h->tasks.size()) * CF_CNT_WORDS) == cudaSuccess;
     if (!ok) return fail("cudaMalloc failed (work space)");
@@ -1716,6 +1892,50 @@ extern "C" int cf_build_g_multi(cf_handle* h, int nbf, int nmat, const double* D
         rc = check_scales(h);
         if (rc != CF_OK) return rc;
     }
+    return CF_OK;
+}
+
+// ================================================================================================
+// One-electron integrals: Int2C1E::CalculateIntegrals(0, ...) for Overlap / Kinetic / Nuclear
+// (src/Integral/Int2C1E.cpp:18-67, :313-333) on the device.  S, T, V: DEVICE pointers, nbf x nbf col-major.
+// ================================================================================================
+extern "C" int cf_one_electron_device(cf_handle* h, int natom, const double* Z, const double* xyz, double* S, double* T, double* V, void* stream) {
+    if (!h || natom <= 0 || !Z || !xyz || !S || !T || !V) return CF_ERR_BAD_ARGUMENT;
+    if (h->multi) h = multi_part0(h);
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->d_atomZ.n < (size_t)natom && (h->d_atomZ.alloc(natom) != cudaSuccess || h->d_atomxyz.alloc(3 * (size_t)natom) != cudaSuccess)) {
+        set_error(h, "cudaMalloc failed (atoms)"); return CF_ERR_CUDA;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_atomZ.p, Z, sizeof(double) * natom, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_atomxyz.p, xyz, sizeof(double) * 3 * natom, cudaMemcpyHostToDevice, s));
+    OneIntTask t{};
+    t.ns = h->nshell; t.nbf = h->nbf; t.natom = natom;
+    t.l = h->d_l.p; t.nprim = h->d_nprim_sh.p; t.prim_off = h->d_prim_off_sh.p;
+    t.exps = h->d_exps.p; t.coefs = h->d_coefs.p; t.xyz = h->d_xyz.p;
+    t.Z = h->d_atomZ.p; t.atom_xyz = h->d_atomxyz.p;
+    t.ctrans = h->d_ctrans.p; t.ct_off = h->d_ct_off.p; t.bf_off = h->d_bf_off.p; t.nfun = h->d_nfun.p;
+    fill_rys_tables(t.rys, h);
+    t.S = S; t.T = T; t.V = V;
+    const long long npairs = (long long)h->nshell * (h->nshell + 1) / 2;
+    oneint_kernel<<<(unsigned)npairs, ONEINT_THREADS, 0, s>>>(t);
+    CUDA_TRY(cudaGetLastError());
+    return CF_OK;
+}
+
+// HOST pointers out (what Int2C1E stores in Overlap / Kinetic / Nuclear)
+extern "C" int cf_one_electron(cf_handle* h, int natom, const double* Z, const double* xyz, double* S, double* T, double* V) {
+    if (!h || !S || !T || !V) return CF_ERR_BAD_ARGUMENT;
+    cf_handle* p = h->multi ? multi_part0(h) : h;
+    DeviceGuard guard(p->device);
+    const size_t bytes = sizeof(double) * (size_t)p->nbf * p->nbf;
+    int rc = cf_one_electron_device(p, natom, Z, xyz, p->d_out[0].p, p->d_out[1].p, p->d_out[2].p, nullptr);
+    if (rc != CF_OK) { if (p != h) h->err = p->err; return rc; }
+    h = p;
+    CUDA_TRY(cudaMemcpyAsync(S, p->d_out[0].p, bytes, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpyAsync(T, p->d_out[1].p, bytes, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpyAsync(V, p->d_out[2].p, bytes, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
     return CF_OK;
 }
 

@@ -237,15 +237,7 @@ __global__ void __launch_bounds__(GRAD_TPQ_THREADS) eri_grad_tpq(const GradTask 
     double* rows = smem + TABLEN;                             // [warps][ngrad]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* myrow = rows + (size_t)warp * t.ngrad;
-    if constexpr (NR <= 2) {
-        constexpr int M = 2 * NR - 1;
-        for (int e = threadIdx.x; e < BOYS_NROW * 8; e += GRAD_TPQ_THREADS) tab[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
-    } else {
-        constexpr int NT = (rys_tmax(NR) / 2) * 2 * NR * RYS_NC;
-        const double* src = t.rys.table + rys_off(NR);
-        for (int e = threadIdx.x; e < NT; e += GRAD_TPQ_THREADS) tab[e] = src[e];
-        if (threadIdx.x < 2 * NR) tab[NT + threadIdx.x] = t.rys.asym[rys_asym_off(NR) + threadIdx.x];
-    }
+    tpq_stage_tables<NR>(tab, t.rys, threadIdx.x, GRAD_TPQ_THREADS);
     for (int e = threadIdx.x; e < (GRAD_TPQ_THREADS / 32) * t.ngrad; e += GRAD_TPQ_THREADS) rows[e] = 0.0;
     __syncthreads();
     const size_t ld = (size_t)t.ncart;

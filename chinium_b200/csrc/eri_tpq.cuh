@@ -32,8 +32,15 @@
 __host__ __device__ constexpr bool tpq_ok(int la, int lb, int lc, int ld) {
     return cf_ncart(la) * cf_ncart(lb) * cf_ncart(lc) * cf_ncart(ld) <= TPQ_MAX_NOUT;
 }
+// one-root classes (L <= 1) read F_0 and F_1 from their own Taylor rows F_0..F_9 (no exp, no downward recursion);
+// -DCF_BOYS1_EXP restores the F_1-row + exp(-T) + recursion path for A/B measurements
+#ifdef CF_BOYS1_EXP
+#define BOYS1_COLS 8
+#else
+#define BOYS1_COLS 10
+#endif
 __host__ __device__ constexpr int tpq_table_len(int nroots) {
-    return nroots <= 2 ? BOYS_NROW * 8 : (rys_tmax(nroots) / 2) * 2 * nroots * RYS_NC + 2 * nroots;
+    return nroots == 1 ? BOYS_NROW * BOYS1_COLS : nroots == 2 ? BOYS_NROW * 8 : (rys_tmax(nroots) / 2) * 2 * nroots * RYS_NC + 2 * nroots;
 }
 #define TPQ_WBP 32        // bra primitive pairs staged per pass and per warp by the thread-per-quartet kernel
 __host__ __device__ constexpr size_t tpq_smem(int nroots) {
@@ -86,10 +93,54 @@ __device__ __forceinline__ void boys_large(double T, double* __restrict__ F) {  
     for (int m = 0; m < M; m++) F[m + 1] = fma((double)(2 * m + 1), F[m], -e) * i2t;
 }
 
+// F_0(T), F_1(T) for T < BOYS_TMAX from the staged rows F_0..F_9 at T_i = i/8: two 8-term Taylor sums sharing the powers
+__device__ __forceinline__ void boys01_small(const double* __restrict__ tab, double T, double& F0, double& F1) {
+    const int i = (int)fma(T, 8.0, 0.5);
+    const double mh = fma((double)i, 0.125, -T);   // -(T - T_i), |mh| <= 1/16
+    const double2* row = reinterpret_cast<const double2*>(tab + i * 10);
+    const double2 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3], r4 = row[4];     // F_0..F_9
+    const double h7 = mh * (1.0 / 7.0), h6 = mh * (1.0 / 6.0), h5 = mh * (1.0 / 5.0), h4 = mh * 0.25, h3 = mh * (1.0 / 3.0), h2 = mh * 0.5;
+    double s0 = r3.y, s1 = r4.x;
+    s0 = fma(s0, h7, r3.x); s1 = fma(s1, h7, r3.y);
+    s0 = fma(s0, h6, r2.y); s1 = fma(s1, h6, r3.x);
+    s0 = fma(s0, h5, r2.x); s1 = fma(s1, h5, r2.y);
+    s0 = fma(s0, h4, r1.y); s1 = fma(s1, h4, r2.x);
+    s0 = fma(s0, h3, r1.x); s1 = fma(s1, h3, r1.y);
+    s0 = fma(s0, h2, r0.y); s1 = fma(s1, h2, r1.x);
+    F0 = fma(s0, mh, r0.x); F1 = fma(s1, mh, r0.y);
+}
+
+// stage the root tables of a kernel with NT threads (once per CTA): Boys Taylor rows for 1 and 2 roots, Chebyshev
+// coefficient tables + asymptotic constants for 3 and more
+template <int NROOTS>
+__device__ __forceinline__ void tpq_stage_tables(double* __restrict__ tab, const RysTablesDev& rys, int tid, int nt) {
+    if constexpr (NROOTS == 1 && BOYS1_COLS == 10) {
+        for (int e = tid; e < BOYS_NROW * 10; e += nt) tab[e] = rys.boys[(e / 10) * BOYS_NCOL + (e % 10)];
+    } else if constexpr (NROOTS <= 2) {
+        constexpr int M = 2 * NROOTS - 1;
+        for (int e = tid; e < BOYS_NROW * 8; e += nt) tab[e] = rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
+    } else {
+        constexpr int NTAB = (rys_tmax(NROOTS) / 2) * 2 * NROOTS * RYS_NC;
+        const double* src = rys.table + rys_off(NROOTS);
+        for (int e = tid; e < NTAB; e += nt) tab[e] = src[e];
+        if (tid < 2 * NROOTS) tab[NTAB + tid] = rys.asym[rys_asym_off(NROOTS) + tid];
+    }
+}
+
 // Rys roots x_r (= t^2) and weights (sum_r w_r x_r^k = F_k(T)) of one primitive quartet, all in registers
 template <int NROOTS>
 __device__ __forceinline__ void tpq_roots(const double* __restrict__ tab, double T, double* __restrict__ x, double* __restrict__ w) {
-    if constexpr (NROOTS <= 2) {
+    if constexpr (NROOTS == 1 && BOYS1_COLS == 10) {
+        double F0, F1;
+        if (T < BOYS_TMAX) boys01_small(tab, T, F0, F1);
+        else {   // erfc(sqrt T) < 2e-17: F_0 = sqrt(pi/4T); F_1 = (F_0 - e^-T) / 2T with e^-T / F_0 < 2e-15 dropped (root only)
+            const double r = rsqrt(T);
+            F0 = 0.88622692545275801365 * r;
+            F1 = F0 * (0.5 * r * r);
+        }
+        w[0] = F0;
+        x[0] = F1 * fast_rcp(F0);
+    } else if constexpr (NROOTS <= 2) {
         constexpr int M = 2 * NROOTS - 1;
         double F[M + 1];
         if (T < BOYS_TMAX) boys_small<M>(tab, T, F); else boys_large<M>(T, F);
@@ -171,15 +222,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
     double* sbra = smem + TABLEN + warp * (TPQ_NBRA * MAXBP);   // this warp's [TPQ_NBRA][MAXBP]
 
     // ---- stage the root tables (once per CTA) ----------------------------------------------------
-    if constexpr (NROOTS <= 2) {
-        constexpr int M = 2 * NROOTS - 1;
-        for (int e = threadIdx.x; e < BOYS_NROW * 8; e += TPQ_THREADS) tab[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
-    } else {
-        constexpr int NT = (rys_tmax(NROOTS) / 2) * 2 * NROOTS * RYS_NC;
-        const double* src = t.rys.table + rys_off(NROOTS);
-        for (int e = threadIdx.x; e < NT; e += TPQ_THREADS) tab[e] = src[e];
-        if (threadIdx.x < 2 * NROOTS) tab[NT + threadIdx.x] = t.rys.asym[rys_asym_off(NROOTS) + threadIdx.x];
-    }
+    tpq_stage_tables<NROOTS>(tab, t.rys, threadIdx.x, TPQ_THREADS);
     __syncthreads();
 
     // ---- work items are WARP-private: (one bra pair) x (<= 32 consecutive ket pairs); no CTA barrier below -------
@@ -523,15 +566,7 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
     double* sbra = smem + TABLEN;                   // [TPQ_NBRA][TPQ_MAXBP]
     double* part = sbra + TPQ_NBRA * TPQ_MAXBP;     // [VC][GS][NQ]
 
-    if constexpr (NROOTS <= 2) {
-        constexpr int M = 2 * NROOTS - 1;
-        for (int e = threadIdx.x; e < BOYS_NROW * 8; e += NT) tab[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
-    } else {
-        constexpr int NTAB = (rys_tmax(NROOTS) / 2) * 2 * NROOTS * RYS_NC;
-        const double* src = t.rys.table + rys_off(NROOTS);
-        for (int e = threadIdx.x; e < NTAB; e += NT) tab[e] = src[e];
-        if (threadIdx.x < 2 * NROOTS) tab[NTAB + threadIdx.x] = t.rys.asym[rys_asym_off(NROOTS) + threadIdx.x];
-    }
+    tpq_stage_tables<NROOTS>(tab, t.rys, threadIdx.x, NT);
 
     const int q = threadIdx.x % NQ, s = threadIdx.x / NQ;   // s is warp-uniform
     int eax[MA], eay[MA], eaz[MA];

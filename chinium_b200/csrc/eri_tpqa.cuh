@@ -38,6 +38,8 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 // resident CTAs per SM the register allocation is held to: the light classes are latency-bound and want warps
+// Measured (profiles/r2e_*): holding the smallest classes to 80-96 registers for 5-6 resident CTAs makes them SLOWER on
+// (H2O)64 (ps|ps +18 %, pp|ss +8 %, ss|ss +3 %: the extra warps do not pay for the spills), so round 1's rule stays.
 __host__ __device__ constexpr int tpqa_minb(int nout, int nkmax) {
 #ifdef TPQA_MINB
     return TPQA_MINB;
@@ -71,15 +73,7 @@ eri_jk_tpqa(const QuartetTask t) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* sbra = smem + TABLEN + warp * (TPQ_NBRA * MAXBP);   // this warp's [TPQ_NBRA][MAXBP]
 
-    if constexpr (NROOTS <= 2) {
-        constexpr int M = 2 * NROOTS - 1;
-        for (int e = threadIdx.x; e < BOYS_NROW * 8; e += TPQ_THREADS) tab[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
-    } else {
-        constexpr int NT = (rys_tmax(NROOTS) / 2) * 2 * NROOTS * RYS_NC;
-        const double* src = t.rys.table + rys_off(NROOTS);
-        for (int e = threadIdx.x; e < NT; e += TPQ_THREADS) tab[e] = src[e];
-        if (threadIdx.x < 2 * NROOTS) tab[NT + threadIdx.x] = t.rys.asym[rys_asym_off(NROOTS) + threadIdx.x];
-    }
+    tpq_stage_tables<NROOTS>(tab, t.rys, threadIdx.x, TPQ_THREADS);
     __syncthreads();
 
     const size_t ld = (size_t)t.ncart;

@@ -179,8 +179,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS, MINB) eri_jk_wg(const QuartetTa
 
     // ---- stage the root tables ------------------------------------------------------------------
     if constexpr (NROOTS <= 2) {
-        constexpr int M = 2 * NROOTS - 1;
-        for (int e = threadIdx.x; e < BOYS_NROW * 8; e += 32 * WG_WARPS) smem[e] = t.rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
+        tpq_stage_tables<NROOTS>(smem, t.rys, threadIdx.x, 32 * WG_WARPS);
     } else {
         constexpr int NTAB = (rys_tmax(NROOTS) / 2) * 2 * NROOTS * RYS_NC;
         if constexpr (C::GTAB) {

@@ -95,6 +95,8 @@ def load_library(path: str = LIB_PATH):
     L.cf_device_info.argtypes = [ip, C.c_char_p, ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]
     L.cf_measure_fp64_peak.argtypes = [ip, dp]
     L.cf_sync_stats.argtypes = [vp]
+    L.cf_one_electron.argtypes = [vp, ip, dp, dp, dp, dp, dp]
+    L.cf_one_electron_device.argtypes = [vp, ip, dp, dp, vp, vp, vp, vp]
     L.cf_profile_tasks.argtypes = [vp, ip, vp, vp, vp, C.c_double, dp, ip, C.POINTER(ip)]
     _lib = L
     return L
@@ -312,6 +314,24 @@ class Int4C2E:
         self._check(self._lib.cf_build_jk_device(self._h, self.nbf, Dd_ptr, Da_ptr, Db_ptr, self.EXX, J_ptr, Kd_ptr, Ka_ptr,
                                                  Kb_ptr, stream))
 
+    # ---- one-electron integrals (Int2C1E.cpp:18-67, :313-333) -----------------------------------
+    def one_electron(self, Z, xyz_bohr):
+        """-> (S, T, V) host matrices: overlap, kinetic energy, nuclear attraction of the point charges Z at xyz_bohr."""
+        self._ensure()
+        n = self.nbf
+        Zd = np.ascontiguousarray(Z, np.float64)
+        R = np.ascontiguousarray(xyz_bohr, np.float64).reshape(-1)
+        S, T, V = (np.zeros((n, n), order="F") for _ in range(3))
+        self._check(self._lib.cf_one_electron(self._h, len(Zd), _dptr(Zd), _dptr(R), _dptr(S), _dptr(T), _dptr(V)))
+        return S, T, V
+
+    def one_electron_device(self, Z, xyz_bohr, S_ptr, T_ptr, V_ptr, stream=None):
+        """Same into DEVICE matrices (plain pointers); enqueued on `stream`, not synchronised."""
+        self._ensure()
+        Zd = np.ascontiguousarray(Z, np.float64)
+        R = np.ascontiguousarray(xyz_bohr, np.float64).reshape(-1)
+        self._check(self._lib.cf_one_electron_device(self._h, len(Zd), _dptr(Zd), _dptr(R), S_ptr, T_ptr, V_ptr, stream))
+
     def profile_tasks(self, Dd_ptr, Da_ptr, Db_ptr):
         """-> list of dicts (bra, ket class names, quartets, ms, flops_alg, group): every class-pair kernel timed alone."""
         self._ensure()
@@ -325,6 +345,31 @@ class Int4C2E:
     def sync_stats(self):
         self._check(self._lib.cf_sync_stats(self._h))   # also the deferred fixed-point range check of that build
         return self.stats
+
+
+class Int2C1E:
+    """Mirror of the reference's `class Int2C1E` (src/Integral/Int2C1E.h:10-57) for the zeroth-order matrices the SCF needs:
+    CalculateIntegrals(0, output) fills Overlap, Kinetic, Nuclear (Int2C1E.cpp:313-333) on the GPU.  Multipole matrices,
+    ECP terms and the derivative orders are outside this engine's scope.  `engine`: an Int4C2E on the same basis whose
+    device handle is shared (otherwise one is created)."""
+
+    def __init__(self, basis, Z, xyz_bohr, engine=None, device: int = -1):
+        self.MWFN = basis
+        self._Z = np.ascontiguousarray(Z, np.float64)
+        self._xyz = np.ascontiguousarray(xyz_bohr, np.float64)
+        self._eng = engine if engine is not None else Int4C2E(basis, 1.0, -1.0, device=device)
+        self.Overlap = self.Kinetic = self.Nuclear = None
+
+    def CalculateIntegrals(self, order=0, output=0):
+        if order != 0:
+            raise FockEngineError("one-electron derivative integrals (order %d) are outside this engine's scope" % order)
+        import time
+        t = time.perf_counter()
+        if output > 0:
+            print("Calculating 2c-1e integrals ... ", end="")
+        self.Overlap, self.Kinetic, self.Nuclear = self._eng.one_electron(self._Z, self._xyz)
+        if output > 0:
+            print("Done in %f s" % (time.perf_counter() - t))
 
 
 def measure_fp64_peak(device=-1) -> float:

@@ -188,6 +188,14 @@ int cf_build_g_multi(cf_handle* h, int nbf, int nmat, const double* Ds, double e
  * list.  A handle with world_size > 1 returns ITS PARTITION's share: sum the vectors over the ranks. */
 int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const double* D2, double exx, int natom, double* grad);
 
+/* One-electron integrals: overlap, kinetic energy and nuclear attraction of `natom` point charges Z at
+ * xyz (bohr, [3*natom]); replaces Int2C1E::CalculateIntegrals(0, ...) for Overlap / Kinetic / Nuclear
+ * (src/Integral/Int2C1E.cpp:18-67, :313-333; multipoles and ECP terms are outside this engine).  nbf x nbf col-major,
+ * exactly symmetric.  Z / xyz are HOST pointers in both forms; S, T, V are host pointers (cf_one_electron) or device
+ * pointers on the handle's device (cf_one_electron_device, enqueued on `stream`, not synchronised). */
+int cf_one_electron(cf_handle* h, int natom, const double* Z, const double* xyz, double* S, double* T, double* V);
+int cf_one_electron_device(cf_handle* h, int natom, const double* Z, const double* xyz, double* S, double* T, double* V, void* stream);
+
 /* After the caller has synchronised the stream of a *_device call: refresh ms_device_last / ms_eri_last and run the
  * fixed-point range check of that build (the *_device calls never synchronise, so CF_ERR_RANGE for a non-finite or
  * astronomically large density is reported here; cf_build_jk reports it itself). */

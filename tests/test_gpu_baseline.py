@@ -345,3 +345,46 @@ def test_multi_density_rejects_bad_shapes(Int4C2E):
     Gs = eng.ContractInts([np.eye(n)], nthreads=4, output=0)
     assert len(Gs) == 1 and Gs[0].shape == (n, n)
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# one-electron integrals on the device and a device-resident RHF iteration
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["h2o", "hf_tz", "bo3h3", "fe4s4"])
+def test_one_electron_integrals(Int4C2E, oracle, name):
+    """S, T, V from the device kernels (oneint.cuh; Int2C1E.cpp:18-67, :313-333) against the oracle's McMurchie-Davidson
+    one-electron integrals: s..f shells, contracted and uncontracted, 2 to 8 nuclei."""
+    from chinium_b200 import Int2C1E
+    mol, fb = load_fixture_molecule(name)
+    eng = Int4C2E(fb, 1.0, -1.0)
+    i1 = Int2C1E(fb, mol.Z, mol.xyz_bohr, engine=eng)
+    i1.CalculateIntegrals(0, 0)
+    S, T, V = oracle.one_electron(fb, mol.Z, mol.xyz_bohr)
+    assert np.abs(i1.Overlap - S).max() < 1e-12
+    assert np.abs(i1.Kinetic - T).max() < 1e-10 * max(1.0, np.abs(T).max() / 100)
+    assert np.abs(i1.Nuclear - V).max() < 1e-10 * max(1.0, np.abs(V).max() / 100)
+    for M in (i1.Overlap, i1.Kinetic, i1.Nuclear):
+        assert np.abs(M - M.T).max() == 0.0
+    assert np.abs(np.diag(i1.Overlap) - 1.0).max() < 1e-12
+    eng.close()
+
+
+def test_device_resident_scf(Int4C2E, oracle):
+    """RHF with D, J, K, F, S, H resident on the device (tests/scf_device.py): the energies of examples/h2o.inp and of the
+    CH3ClF- golden case equal the oracle's / Chinium's to 1e-8 Eh."""
+    import scf_device
+    for name, golden in (("h2o", None), ("sn2", -598.514802895)):
+        mol, fb = load_fixture_molecule(name)
+        enuc = H.nuclear_repulsion(mol.Z, mol.xyz_bohr)
+        nocc = mol.nelec // 2
+        eng = Int4C2E(fb, 1.0, -1.0)
+        E_dev, D_dev, it = scf_device.rhf_device(eng, mol.Z, mol.xyz_bohr, nocc, enuc)
+        eng.close()
+        S, T, V = oracle.one_electron(fb, mol.Z, mol.xyz_bohr)
+        h = oracle.store_build(fb)
+        E_cpu, D_cpu, _, it_cpu = H.rhf(S, T + V, nocc, lambda d, a, b: oracle.store_contract(h, fb.nbf, d, a, b), enuc)
+        oracle.store_free(h)
+        assert abs(E_dev - E_cpu) < 1e-8, (name, E_dev, E_cpu)
+        assert np.abs(D_dev.cpu().numpy() - D_cpu).max() < 1e-6
+        if golden is not None:
+            assert abs(E_dev - golden) < 1e-7
