@@ -875,6 +875,16 @@ static int launch_task(cf_handle* h, ClassPairTask* t, QuartetTask& qt, int stor
         if (nlocal <= 0) return CF_OK;
         if (t->kind == 1) nlocal = (nlocal + TPQ_THREADS / 32 - 1) / (TPQ_THREADS / 32);   // warp-private items
         grid = (int)std::min<long long>(nlocal, 148LL * 16);
+        // Every CTA stages its root tables (18-64 KB) before the first item: when a partition leaves only a few items
+        // per CTA (many GPUs, small class pairs) that fixed cost and the ragged tail dominate (round 1: 0.83 efficiency
+        // at 8 GPUs on c18).  Fewer, longer-running CTAs then: at least CF_MIN_ITEMS items per CTA as long as every SM
+        // keeps 4 CTAs.  Launch geometry only -- the set of fixed-point adds, hence the result, is unchanged.
+        {
+            static int min_items = -1;
+            if (min_items < 0) { const char* e = getenv("CF_MIN_ITEMS"); min_items = e ? atoi(e) : 8; }
+            const long long want = std::max<long long>(148LL * 4, (nlocal + min_items - 1) / std::max(1, min_items));
+            grid = (int)std::min<long long>(grid, std::max<long long>(1, std::min<long long>(nlocal, want)));
+        }
     } else {
         // chunk: enough chunks to fill the machine ~8x over, at most 64 quartets each
         long long chunk = nq / (148LL * 32 * std::max(1, qt.world));
@@ -1105,6 +1115,18 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     if (h->d_diag.alloc((size_t)nbf * nbf) != cudaSuccess) return fail("cudaMalloc failed (diag)");
     cudaMemset(h->d_diag.p, 0, sizeof(double) * (size_t)nbf * nbf);
     h->qmax_cart = 0;
+    DevBuf<double> blocks;          // (ab|ab) store buffer, one allocation shared by all classes (slabs of at most ~1 GiB)
+    blocks.pooled = false;
+    {
+        size_t need = 0;
+        for (int ci = 0; ci < CF_NCLS; ci++) {
+            const PairClassHost& c = h->cls[ci];
+            if (c.npair() == 0) continue;
+            const size_t nout = (size_t)cf_ncart(c.la) * cf_ncart(c.lb) * cf_ncart(c.la) * cf_ncart(c.lb);
+            need = std::max(need, nout * std::max<size_t>(1, std::min<size_t>(c.npair(), (1ull << 27) / nout)));
+        }
+        if (blocks.alloc(need) != cudaSuccess) return fail("cudaMalloc failed (Schwarz store buffer)");
+    }
     for (int ci = 0; ci < CF_NCLS; ci++) {
         PairClassHost& c = h->cls[ci];
         const int np = c.npair();
@@ -1113,8 +1135,8 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
         const size_t nout = (size_t)nca * ncb * nca * ncb;
         // in slabs so the store buffer stays below ~1 GiB
         const int slab = (int)std::max<size_t>(1, std::min<size_t>(np, (1ull << 27) / nout));
-        DevBuf<double> blocks, qpure;
-        if (blocks.alloc(nout * slab) != cudaSuccess || qpure.alloc(np) != cudaSuccess || c.d_Qcart.alloc(np) != cudaSuccess) return fail("cudaMalloc failed (Schwarz)");
+        DevBuf<double> qpure;
+        if (qpure.alloc(np) != cudaSuccess || c.d_Qcart.alloc(np) != cudaSuccess) return fail("cudaMalloc failed (Schwarz)");
         for (int p0 = 0; p0 < np; p0 += slab) {
             const int cnt = std::min(slab, np - p0);
             QuartetTask qt{};
@@ -1129,13 +1151,13 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
             schwarz_kernel<<<cnt, 128>>>(cnt, nca, ncb, blocks.p, c.d_sa.p + p0, c.d_sb.p + p0, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p,
                                          h->d_nfun.p, nbf, c.d_Qcart.p + p0, qpure.p + p0, h->d_diag.p);
         }
-        blocks.release();
         if (c.sort_by_bounds(bd, cutoff, qpure.p) != cudaSuccess)
             return fail(std::string("Schwarz kernels / class sort failed: ") + cudaGetErrorString(cudaGetLastError()));
         qpure.release();
         for (double q : c.Q) h->qmax_cart = std::max(h->qmax_cart, q);
         if (c.build_roles() != cudaSuccess) return fail("bra/ket role build failed");
     }
+    blocks.release();
     h->diag_ready = true;
     mark("Schwarz + device sort + roles");
     {   // dense Cartesian Schwarz matrix over shell pairs (0 for pairs dropped by the primitive cutoff)

@@ -62,6 +62,9 @@ class DistributedInt4C2E:
         No transposes: the engine symmetrises D on the device ((D + D^T)/2, the reference's precondition) and J/K come
         back exactly symmetric, so the row-major torch view and the column-major reference layout hold the same bytes."""
         n = self.nbf
+        if isinstance(Dd, (list, tuple)):
+            raise FockEngineError("DistributedInt4C2E.ContractInts([D...]): the multi-density build across processes is not wired up; "
+                                  "use Int4C2E(..., ndevices=N) (one process, cf_create_multi), which supports it")
         present = [D is not None and np.size(D) > 0 for D in (Dd, Da, Db)]
         for k, D in enumerate((Dd, Da, Db)):
             if present[k]:
