@@ -13,6 +13,7 @@
 // is held by a std::shared_ptr.  No CPU fallback: without a usable sm_100 GPU every call throws.
 #pragma once
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <memory>
 #include <stdexcept>
@@ -179,6 +180,53 @@ class Int4C2E_T {
         check(cf_contract_grads(h_.get(), n, D1.data(), D2.data(), EXX, natom, g.data()));
         if (output > 0) std::printf("Done in %f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
         return g;
+    }
+
+    // matrix form (Int4C2E.cpp:766-790; consumer Restricted/Hess.cpp:72): 3*natoms matrices G^(atom,xyz)[D], kept in
+    // GradCache and looked up by value like the reference does (:769-772)
+    std::vector<std::tuple<Matrix, double, std::vector<Matrix>>> GradCache;
+    std::vector<Matrix> ContractGrads(Matrix D, int output) {
+        ensure(0);
+        const int n = cf_nbf(h_.get());
+        if (D.rows() != n || D.cols() != n) throw std::runtime_error("ContractGrads: matrix is not nbf x nbf");
+        auto t0 = std::chrono::steady_clock::now();
+        if (output > 0) std::printf("Contracting 4c-2e repulsion integral nuclear gradient with 1 matrix ... ");
+        const size_t n2 = (size_t)n * n;
+        for (auto& entry : GradCache) {
+            Matrix& key = std::get<0>(entry);
+            bool same = std::get<1>(entry) == EXX;
+            for (size_t i = 0; same && i < n2; i++) same = std::fabs(key.data()[i] - D.data()[i]) <= 1e-12 * std::fabs(D.data()[i]);
+            if (same) {
+                if (output > 0) std::printf("Found in cache -> Done in %f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+                return std::get<2>(entry);
+            }
+        }
+        int natom = 0;
+        for (int a : basis_->shell2atom) natom = a + 1 > natom ? a + 1 : natom;
+        std::vector<double> buf(3 * (size_t)natom * n2);
+        check(cf_contract_grads_matrices(h_.get(), n, D.data(), EXX, natom, buf.data()));
+        std::vector<Matrix> Gs;
+        for (int j = 0; j < 3 * natom; j++) {
+            Matrix G(n, n);
+            std::copy(buf.begin() + (size_t)j * n2, buf.begin() + (size_t)(j + 1) * n2, G.data());
+            Gs.push_back(G);
+        }
+        GradCache.push_back(std::make_tuple(D, EXX, Gs));
+        if (output > 0) std::printf("Done in %f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        return Gs;
+    }
+    // several left matrices against one right matrix (Int4C2E.cpp:752-764): D1s[i] o ContractGrads(D2)[j]
+    std::vector<std::vector<double>> ContractGrads(std::vector<Matrix>& D1s, Matrix D2, int output) {
+        const std::vector<Matrix> GD2 = ContractGrads(D2, output);
+        const size_t n2 = (size_t)D2.rows() * D2.cols();
+        std::vector<std::vector<double>> out(D1s.size(), std::vector<double>(GD2.size(), 0.0));
+        for (size_t i = 0; i < D1s.size(); i++)
+            for (size_t j = 0; j < GD2.size(); j++) {
+                double s = 0.0;
+                for (size_t k = 0; k < n2; k++) s += D1s[i].data()[k] * GD2[j].data()[k];
+                out[i][j] = s;
+            }
+        return out;
     }
 
     // extension for direct SCF (no counterpart in the stored-ERI reference): density-weighted screening for incremental

@@ -56,6 +56,10 @@ typedef cudaError_t (*bra_launch_fn)(int, const QuartetTask&, int, int, cudaStre
 #define DECL_GRAD(n) cudaError_t cf_launch_grad_bra##n(int, const GradTask&, int, cudaStream_t, int*, size_t*);
 DECL_GRAD(0) DECL_GRAD(1) DECL_GRAD(2) DECL_GRAD(3) DECL_GRAD(4) DECL_GRAD(5) DECL_GRAD(6) DECL_GRAD(7) DECL_GRAD(8) DECL_GRAD(9)
 typedef cudaError_t (*grad_launch_fn)(int, const GradTask&, int, cudaStream_t, int*, size_t*);
+#define DECL_GRADMAT(n) cudaError_t cf_launch_gradmat_bra##n(int, const GradTask&, int, cudaStream_t, int*, size_t*);
+DECL_GRADMAT(0) DECL_GRADMAT(1) DECL_GRADMAT(2) DECL_GRADMAT(3) DECL_GRADMAT(4) DECL_GRADMAT(5) DECL_GRADMAT(6) DECL_GRADMAT(7) DECL_GRADMAT(8) DECL_GRADMAT(9)
+static grad_launch_fn g_gradmat_launch[CF_NCLS] = {cf_launch_gradmat_bra0, cf_launch_gradmat_bra1, cf_launch_gradmat_bra2, cf_launch_gradmat_bra3, cf_launch_gradmat_bra4,
+                                                   cf_launch_gradmat_bra5, cf_launch_gradmat_bra6, cf_launch_gradmat_bra7, cf_launch_gradmat_bra8, cf_launch_gradmat_bra9};
 static grad_launch_fn g_grad_launch[CF_NCLS] = {cf_launch_grad_bra0, cf_launch_grad_bra1, cf_launch_grad_bra2, cf_launch_grad_bra3, cf_launch_grad_bra4,
                                                 cf_launch_grad_bra5, cf_launch_grad_bra6, cf_launch_grad_bra7, cf_launch_grad_bra8, cf_launch_grad_bra9};
 static bra_launch_fn g_bra_launch[CF_NCLS] = {cf_launch_bra0, cf_launch_bra1, cf_launch_bra2, cf_launch_bra3, cf_launch_bra4,
@@ -387,6 +391,7 @@ struct ClassPairTask {
     double per_prim = 0;             // model flops of ONE primitive quartet of this class pair
     double nfun_q = 0;               // N_s of one quartet
     int index = 0;                   // position in cf_handle::tasks = slot of the task's device counters
+    int owner = -1;                  // multi-GPU: -1 = items dealt round-robin over all ranks; r >= 0 = rank r runs the whole (small) task
 };
 
 struct cf_handle {
@@ -867,6 +872,10 @@ static int launch_task(cf_handle* h, ClassPairTask* t, QuartetTask& qt, int stor
     qt.border = B.d_border.p; qt.brec_i = B.d_brec_i.p; qt.brec_d = B.d_brec_d.p; qt.bprim = B.d_bprim.p; qt.bprim_stride = B.bprim_stride;
     qt.same_class = (t->bra == t->ket);
     qt.thr = h->opt.threshold > 0 ? h->opt.threshold : 0.0;
+    if (!store && t->owner >= 0) {            // small task owned by one rank
+        if (qt.rank != t->owner) return CF_OK;
+        qt.rank = 0; qt.world = 1;
+    }
     const long long nq = qt.nquartet;
     if (nq == 0) return CF_OK;
     int grid;
@@ -1392,6 +1401,28 @@ extern "C" cf_handle* cf_create(const cf_basis* basis, const cf_options* opts) {
     // heavy tasks first so the tail of the build is made of small kernels
     std::sort(h->tasks.begin(), h->tasks.end(), [](const ClassPairTask* a, const ClassPairTask* b) { return a->flops_eri > b->flops_eri; });
     for (size_t i = 0; i < h->tasks.size(); i++) h->tasks[i]->index = (int)i;
+    if (h->opt.world_size > 1) {
+        // Static, cost-balanced partition (north_star): large tasks deal their work items round-robin over the ranks; a task
+        // whose share per rank would be less than ~2 waves of CTAs cannot get faster by splitting (its duration is one
+        // item chain), so it is given WHOLE to the least-loaded rank (longest-processing-time-first over the modelled
+        // cost).  Every rank derives the same assignment from the same setup; the integer accumulators make the sum
+        // independent of who computed what.
+        const int world = h->opt.world_size;
+        std::vector<double> load(world, 0.0);
+        for (ClassPairTask* t : h->tasks) {          // already sorted by descending cost
+            const double cost = t->flops_eri + 12.0 * t->nfun_sum;
+            const long long units = t->kind == 0 ? t->nquartet / 16 : t->nitem;
+            const long long two_waves = t->kind == 1 ? 148LL * 4 * 4 * 2 : 148LL * 2 * 2;
+            const char* e = getenv("CF_TASK_OWNER");
+            if ((e ? atoi(e) != 0 : true) && units / world < two_waves) {
+                int best = 0;
+                for (int r = 1; r < world; r++) if (load[r] < load[best]) best = r;
+                t->owner = best; load[best] += cost;
+            } else {
+                for (int r = 0; r < world; r++) load[r] += cost / world;
+            }
+        }
+    }
     h->cnt_host.assign(h->tasks.size() * CF_CNT_WORDS, 0ull);
 
     // ---- work space
@@ -1797,6 +1828,98 @@ extern "C" int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const 
         if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->stats.ms_grad_last = ms;
         h->stats.n_launches_last = nlaunch + 1;
     }
+    return CF_OK;
+}
+
+// G_pure(block) = C_a (raw + raw^T) C_b^T for one (atom, direction) matrix of the matrix-form gradient (doubles)
+__global__ void finalize_gradmat_kernel(int nbf, int ncart, const double* __restrict__ raw, const double* __restrict__ ctrans,
+                                        const int* __restrict__ ct_off, const int* __restrict__ bf_off, const int* __restrict__ cao_off,
+                                        const int* __restrict__ nfun, const int* __restrict__ ncsh, double* __restrict__ out) {
+    const int sa = blockIdx.x, sb = blockIdx.y;
+    if (sb > sa) return;
+    const size_t n2c = (size_t)ncart * ncart, n2p = (size_t)nbf * nbf;
+    raw += (size_t)blockIdx.z * n2c; out += (size_t)blockIdx.z * n2p;
+    const int na = nfun[sa], nb = nfun[sb], nca = ncsh[sa], ncb = ncsh[sb];
+    const double* Ca = ctrans + ct_off[sa];
+    const double* Cb = ctrans + ct_off[sb];
+    for (int e = threadIdx.x; e < na * nb; e += blockDim.x) {
+        const int m = e / nb, n = e % nb;
+        if (sa == sb && n > m) continue;
+        double s = 0.0;
+        for (int x = 0; x < nca; x++) {
+            const double cam = Ca[m * nca + x];
+            if (cam == 0.0) continue;
+            for (int y = 0; y < ncb; y++) {
+                const size_t i = cao_off[sa] + x, j = cao_off[sb] + y;
+                s = fma(cam * Cb[n * ncb + y], raw[j * ncart + i] + raw[i * ncart + j], s);
+            }
+        }
+        out[(size_t)(bf_off[sb] + n) * nbf + bf_off[sa] + m] = s;
+        out[(size_t)(bf_off[sa] + m) * nbf + bf_off[sb] + n] = s;
+    }
+}
+
+// Int4C2E::ContractGrads(D, output) (Int4C2E.cpp:766-790): the 3*natom matrices G^(atom,xyz)[D] = d/dR (J[2D] - exx K[D]),
+// HOST pointers, G = [3*natom][nbf*nbf] col-major (index 3*atom + xyz), each exactly symmetric.  A handle with
+// world_size > 1 returns its partition's share (sum over ranks).
+extern "C" int cf_contract_grads_matrices(cf_handle* h, int nbf, const double* D, double exx, int natom, double* G) {
+    if (!h || !D || !G || natom <= 0) return CF_ERR_BAD_ARGUMENT;
+    if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
+    if (h->multi) { set_error(h, "cf_contract_grads_matrices works on single-device handles"); return CF_ERR_BAD_ARGUMENT; }
+    if (h->shell2atom.empty()) { set_error(h, "cf_contract_grads_matrices needs cf_basis.shell2atom"); return CF_ERR_BAD_ARGUMENT; }
+    for (int a : h->shell2atom) if (a < 0 || a >= natom) { set_error(h, "shell2atom entry outside [0, natom)"); return CF_ERR_BAD_ARGUMENT; }
+    DeviceGuard guard(h->device);
+    const int ns = h->nshell, ncart = h->ncart, ngrad = 3 * natom;
+    const size_t n2p = (size_t)nbf * nbf, n2c = (size_t)ncart * ncart, ns2 = (size_t)ns * ns;
+    if (h->d_shell2atom.n == 0 && h->d_shell2atom.upload(h->shell2atom) != cudaSuccess) { set_error(h, "cudaMalloc failed (shell2atom)"); return CF_ERR_CUDA; }
+    DevBuf<double> raw, outp;
+    raw.pooled = false; outp.pooled = false;
+    if (raw.alloc((size_t)ngrad * n2c) != cudaSuccess || outp.alloc((size_t)ngrad * n2p) != cudaSuccess) {
+        set_error(h, "cudaMalloc failed (3*natom gradient matrices)"); raw.release(); outp.release(); return CF_ERR_CUDA;
+    }
+    CUDA_TRY(cudaMemsetAsync(raw.p, 0, sizeof(double) * ngrad * n2c, 0));
+    CUDA_TRY(cudaMemcpyAsync(h->d_Dpure[0].p, D, sizeof(double) * n2p, cudaMemcpyHostToDevice, 0));
+    dim3 grid2(ns, ns);
+    pure_to_cart_kernel<<<grid2, 64>>>(ns, nbf, ncart, h->d_Dpure[0].p, nullptr, nullptr, 1.0, 0.0, 0.0, h->d_ctrans.p, h->d_ct_off.p,
+                                        h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[1].p, h->d_B.p, h->d_Bmax.p);
+    (void)ns2;
+    const int max_grid = 148 * 8;
+    for (ClassPairTask* t : h->tasks) {
+        const PairClassHost& B = h->cls[t->bra];
+        const PairClassHost& K = h->cls[t->ket];
+        if (t->nquartet == 0) continue;
+        if (t->d_qoff.n == 0) {
+            const int nb = B.npair(), nk = K.npair();
+            std::vector<long long> qoff(nb + 1, 0);
+            for (int i = 0; i < nb; i++) qoff[i + 1] = qoff[i] + (t->bra == t->ket ? i + 1 : nk);
+            if (t->d_qoff.upload(qoff) != cudaSuccess) { set_error(h, "qoff upload failed"); return CF_ERR_CUDA; }
+        }
+        GradTask gt{};
+        gt.bra = B.dev(); gt.ket = K.dev();
+        gt.bra_aexp = B.d_aexp.p; gt.ket_aexp = K.d_aexp.p;
+        gt.qoff = t->d_qoff.p; gt.nquartet = t->nquartet;
+        gt.rank = h->opt.rank; gt.world = h->opt.world_size;
+        gt.same_class = (t->bra == t->ket); gt.ncart = ncart;
+        gt.D1 = h->d_Dcart[1].p; gt.D2 = h->d_Dcart[1].p; gt.exx = exx;
+        gt.shell2atom = h->d_shell2atom.p; gt.gmat = raw.p; gt.ngrad = ngrad;
+        gt.prim_cut = 1e-22; gt.thr = h->opt.threshold > 0 ? h->opt.threshold : 0.0;
+        fill_rys_tables(gt.rys, h);
+        long long chunk = t->nquartet / ((long long)max_grid * 4 * std::max(1, gt.world));
+        chunk = std::max(1LL, std::min(64LL, chunk));
+        gt.chunk = (int)chunk;
+        const long long nchunk_total = (t->nquartet + chunk - 1) / chunk;
+        const long long nchunk_local = (nchunk_total - gt.rank + gt.world - 1) / gt.world;
+        if (nchunk_local <= 0) continue;
+        const int grid = (int)std::min<long long>(nchunk_local, max_grid);
+        cudaError_t e = g_gradmat_launch[t->bra](t->ket, gt, grid, 0, nullptr, nullptr);
+        if (e != cudaSuccess) { set_error(h, std::string("gradient-matrix kernel launch failed: ") + cudaGetErrorString(e)); raw.release(); outp.release(); return CF_ERR_CUDA; }
+    }
+    dim3 grid3(ns, ns, ngrad);
+    finalize_gradmat_kernel<<<grid3, 64>>>(nbf, ncart, raw.p, h->d_ctrans.p, h->d_ct_off.p, h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p,
+                                           h->d_ncartsh.p, outp.p);
+    cudaError_t e = cudaMemcpy(G, outp.p, sizeof(double) * ngrad * n2p, cudaMemcpyDeviceToHost);
+    raw.release(); outp.release();
+    if (e != cudaSuccess) { set_error(h, std::string("gradient-matrix kernels failed: ") + cudaGetErrorString(e)); return CF_ERR_CUDA; }
     return CF_OK;
 }
 

@@ -30,6 +30,7 @@ struct GradTask {
     const int* shell2atom;
     double* gpart;               // [gridDim.x][ngrad] per-CTA partial gradients
     int ngrad;                   // 3 * natom
+    double* gmat;                // matrix form (eri_gradmat_generic): [3 * natom][ncart * ncart] raw Cartesian accumulators
     RysTablesDev rys;
     double prim_cut, thr;
 };
@@ -357,5 +358,207 @@ __global__ void __launch_bounds__(GRAD_TPQ_THREADS) eri_grad_tpq(const GradTask 
         double s = 0.0;
         for (int w = 0; w < GRAD_TPQ_THREADS / 32; w++) s += rows[(size_t)w * t.ngrad + j];
         grow[j] += s;
+    }
+}
+
+// ================================================================================================
+// Matrix form: the 3*natom matrices G^(A,x)[D] = d/dA_x ( J[2 D] - exx K[D] ) that Int4C2E::ContractGrads(D) returns
+// (src/Integral/Int4C2E.cpp:766-790 over getRepulsion1 :312-408; consumer Restricted/Hess.cpp:72).  Same derivative
+// integrals as above, but instead of the scalar contraction with Gamma every derivative block is digested like a J/K
+// build (the reference's six scatter updates per unique integral, :377-389): in the Cartesian working basis
+//     raw^(X)(a,b) += 1/2 w dV(abcd) D(c,d)      raw^(X)(c,d) += 1/2 w dV D(a,b)
+//     raw^(X)(a,c) -= exx/8 w dV D(b,d)   (a,d), (b,c), (b,d) alike,          G^(X) = raw + raw^T  (then Cartesian -> pure),
+// X = (atom of the differentiated centre, direction); centre D from translational invariance.  One CTA per quartet; the
+// nine contracted derivative blocks live in registers / local memory per lane, and each goes through shared memory for
+// an owner-computes digestion with FP64 atomics (this path feeds the Hessian driver, not the SCF loop).
+// ================================================================================================
+template <int LA, int LB, int LC, int LD>
+constexpr size_t eri_gradmat_smem(int G) {
+    constexpr int NR = (LA + LB + LC + LD + 1) / 2 + 1;
+    constexpr int GSZ2 = (LA + 2) * (LB + 2) * (LC + 2) * (LD + 2);
+    constexpr int NA = cf_ncart(LA), NB = cf_ncart(LB), NC = cf_ncart(LC), ND = cf_ncart(LD);
+    return sizeof(double) * (size_t)(2 * NR + NR * 3 * GSZ2 + NA * NB * NC * ND + NA * NB + NC * ND + NA * NC + NA * ND + NB * NC + NB * ND + 16);
+}
+
+template <int LA, int LB, int LC, int LD, int G>
+__global__ void __launch_bounds__(G) eri_gradmat_generic(const GradTask t) {
+    constexpr int NA = cf_ncart(LA), NB = cf_ncart(LB), NC = cf_ncart(LC), ND = cf_ncart(LD);
+    constexpr int NAB = NA * NB, NCD = NC * ND, NOUT = NAB * NCD;
+    constexpr int NR = (LA + LB + LC + LD + 1) / 2 + 1;
+    constexpr int GSZ2 = (LA + 2) * (LB + 2) * (LC + 2) * (LD + 2);
+    constexpr int SA = (LB + 2) * (LC + 2) * (LD + 2), SB = (LC + 2) * (LD + 2), SC = (LD + 2);
+    constexpr int NPL = (NOUT + G - 1) / G;
+    extern __shared__ double smem[];
+    double* rw = smem;
+    double* g = rw + 2 * NR;
+    double* V = g + NR * 3 * GSZ2;          // [NOUT] one derivative block at a time
+    double* Dab = V + NOUT;                 // density blocks of the quartet
+    double* Dcd = Dab + NAB;
+    double* Dac = Dcd + NCD;
+    double* Dad = Dac + NA * NC;
+    double* Dbc = Dad + NA * ND;
+    double* Dbd = Dbc + NB * NC;
+    const int lane = threadIdx.x;
+    const size_t ld = (size_t)t.ncart, n2c = ld * ld;
+    const double* D = t.D2;
+
+    const long long nchunk_total = (t.nquartet + t.chunk - 1) / t.chunk;
+    const long long nchunk_local = (nchunk_total - t.rank + t.world - 1) / t.world;
+    for (long long lc = blockIdx.x; lc < nchunk_local; lc += gridDim.x) {
+        const long long chunk = lc * t.world + t.rank;
+        long long q = chunk * t.chunk;
+        const long long q_end = min(q + (long long)t.chunk, t.nquartet);
+        int lo = 0, hi = t.bra.npair;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (t.qoff[mid] <= q) lo = mid; else hi = mid;
+        }
+        int ib = lo;
+        for (; q < q_end; q++) {
+            while (t.qoff[ib + 1] <= q) ib++;
+            const int ik = (int)(q - t.qoff[ib]);
+            if (t.thr > 0.0 && !(t.bra.Q[ib] * t.ket.Q[ik] > t.thr)) continue;
+            const int sa = t.bra.sa[ib], sb = t.bra.sb[ib], sc = t.ket.sa[ik], sd = t.ket.sb[ik];
+            const double Ax = t.bra.A[3 * ib], Ay = t.bra.A[3 * ib + 1], Az = t.bra.A[3 * ib + 2];
+            const double ABx = t.bra.AB[3 * ib], ABy = t.bra.AB[3 * ib + 1], ABz = t.bra.AB[3 * ib + 2];
+            const double Cx = t.ket.A[3 * ik], Cy = t.ket.A[3 * ik + 1], Cz = t.ket.A[3 * ik + 2];
+            const double CDx = t.ket.AB[3 * ik], CDy = t.ket.AB[3 * ik + 1], CDz = t.ket.AB[3 * ik + 2];
+            const int pab0 = t.bra.pbase[ib], npab = t.bra.nprim[ib];
+            const int pcd0 = t.ket.pbase[ik], npcd = t.ket.nprim[ik];
+            double wgt = (sa == sb ? 1.0 : 2.0) * (sc == sd ? 1.0 : 2.0);
+            wgt *= (t.same_class && ib == ik) ? 1.0 : 2.0;
+            const int ca = t.bra.cao_a[ib], cb = t.bra.cao_b[ib], cc = t.ket.cao_a[ik], cdd = t.ket.cao_b[ik];
+
+            double dv[NPL][9];          // contracted derivative integrals of this lane's components: (A|B|C) x (x,y,z)
+#pragma unroll
+            for (int m = 0; m < NPL; m++)
+#pragma unroll
+                for (int k = 0; k < 9; k++) dv[m][k] = 0.0;
+
+            for (int iab = 0; iab < npab; iab++) {
+                const int sab = pab0 + iab * CF_PSTRIDE;
+                const double p = t.bra.p[sab], cab = t.bra.c[sab];
+                const double Px = t.bra.Px[sab], Py = t.bra.Py[sab], Pz = t.bra.Pz[sab];
+                const double ta = 2.0 * t.bra_aexp[sab], tb = 2.0 * p - ta;
+                for (int icd = 0; icd < npcd; icd++) {
+                    const int scd = pcd0 + icd * CF_PSTRIDE;
+                    const double ccd = t.ket.c[scd];
+                    if (fabs(cab * ccd) < t.prim_cut) continue;
+                    const double qe = t.ket.p[scd];
+                    const double Qx = t.ket.Px[scd], Qy = t.ket.Py[scd], Qz = t.ket.Pz[scd];
+                    const double tc = 2.0 * t.ket_aexp[scd];
+                    const double pq = p + qe;
+                    const double rho = p * qe / pq;
+                    const double PQx = Px - Qx, PQy = Py - Qy, PQz = Pz - Qz;
+                    const double T = rho * (PQx * PQx + PQy * PQy + PQz * PQz);
+                    __syncthreads();
+                    if (lane < 2 * NR) rw[lane] = rys_value<NR>(t.rys, T, lane);
+                    __syncthreads();
+                    for (int tk = lane; tk < 3 * NR; tk += G) {
+                        const int r = tk / 3, dim = tk - 3 * r;
+                        const double x = rw[r];
+                        const double rx_p = rho * x / p, rx_q = rho * x / qe;
+                        const double b00 = 0.5 * x / pq, b10 = (1.0 - rx_p) * (0.5 / p), b01 = (1.0 - rx_q) * (0.5 / qe);
+                        double PA, PQ, QC, ab, cd, w0;
+                        if (dim == 0) { PA = Px - Ax; PQ = PQx; QC = Qx - Cx; ab = ABx; cd = CDx; w0 = 1.0; }
+                        else if (dim == 1) { PA = Py - Ay; PQ = PQy; QC = Qy - Cy; ab = ABy; cd = CDy; w0 = 1.0; }
+                        else { PA = Pz - Az; PQ = PQz; QC = Qz - Cz; ab = ABz; cd = CDz; w0 = rw[NR + r] * cab * ccd * rsqrt(pq) * wgt; }
+                        rys_2d<LA + 1, LB + 1, LC + 1, LD + 1>(w0, PA - rx_p * PQ, QC + rx_q * PQ, b10, b01, b00, ab, cd, g + (size_t)tk * GSZ2);
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int m = 0; m < NPL; m++) {
+                        const int n = lane + m * G;
+                        if (n >= NOUT) continue;
+                        int ea[3], eb[3], ec[3], ed[3];
+                        cart_comp(LA, n / (ND * NC * NB), ea[0], ea[1], ea[2]);
+                        cart_comp(LB, (n / (ND * NC)) % NB, eb[0], eb[1], eb[2]);
+                        cart_comp(LC, (n / ND) % NC, ec[0], ec[1], ec[2]);
+                        cart_comp(LD, n % ND, ed[0], ed[1], ed[2]);
+                        int id3[3];
+#pragma unroll
+                        for (int d = 0; d < 3; d++) id3[d] = ea[d] * SA + eb[d] * SB + ec[d] * SC + ed[d];
+                        for (int r = 0; r < NR; r++) {
+                            const double* gr = g + (size_t)(3 * r) * GSZ2;
+                            double f[3], dA[3], dB[3], dC[3];
+#pragma unroll
+                            for (int d = 0; d < 3; d++) {
+                                const double* gd = gr + d * GSZ2 + id3[d];
+                                f[d] = gd[0];
+                                dA[d] = ta * gd[SA] - (ea[d] ? ea[d] * gd[-SA] : 0.0);
+                                dB[d] = tb * gd[SB] - (eb[d] ? eb[d] * gd[-SB] : 0.0);
+                                dC[d] = tc * gd[SC] - (ec[d] ? ec[d] * gd[-SC] : 0.0);
+                            }
+                            const double fyz = f[1] * f[2], fxz = f[0] * f[2], fxy = f[0] * f[1];
+                            dv[m][0] = fma(dA[0], fyz, dv[m][0]); dv[m][1] = fma(dA[1], fxz, dv[m][1]); dv[m][2] = fma(dA[2], fxy, dv[m][2]);
+                            dv[m][3] = fma(dB[0], fyz, dv[m][3]); dv[m][4] = fma(dB[1], fxz, dv[m][4]); dv[m][5] = fma(dB[2], fxy, dv[m][5]);
+                            dv[m][6] = fma(dC[0], fyz, dv[m][6]); dv[m][7] = fma(dC[1], fxz, dv[m][7]); dv[m][8] = fma(dC[2], fxy, dv[m][8]);
+                        }
+                    }
+                }
+            }
+
+            // ---- density blocks of the quartet (bra shell as the column, like the J/K kernels) ----------------------
+            __syncthreads();
+            for (int e = lane; e < NAB; e += G) Dab[e] = D[(size_t)(cb + e % NB) * ld + ca + e / NB];
+            for (int e = lane; e < NCD; e += G) Dcd[e] = D[(size_t)(cdd + e % ND) * ld + cc + e / ND];
+            for (int e = lane; e < NA * NC; e += G) Dac[e] = D[(size_t)(ca + e / NC) * ld + cc + e % NC];
+            for (int e = lane; e < NA * ND; e += G) Dad[e] = D[(size_t)(ca + e / ND) * ld + cdd + e % ND];
+            for (int e = lane; e < NB * NC; e += G) Dbc[e] = D[(size_t)(cb + e / NC) * ld + cc + e % NC];
+            for (int e = lane; e < NB * ND; e += G) Dbd[e] = D[(size_t)(cb + e / ND) * ld + cdd + e % ND];
+            const int at[4] = {t.shell2atom[sa], t.shell2atom[sb], t.shell2atom[sc], t.shell2atom[sd]};
+            const double fj = 0.5, fk = t.exx > 0.0 ? -0.125 * t.exx : 0.0;
+            // 12 derivative blocks: centres A, B, C from dv, centre D = -(A + B + C)
+            for (int cen = 0; cen < 4; cen++)
+                for (int dir = 0; dir < 3; dir++) {
+                    __syncthreads();
+#pragma unroll
+                    for (int m = 0; m < NPL; m++) {
+                        const int n = lane + m * G;
+                        if (n < NOUT) V[n] = cen < 3 ? dv[m][3 * cen + dir] : -(dv[m][dir] + dv[m][3 + dir] + dv[m][6 + dir]);
+                    }
+                    __syncthreads();
+                    double* Gm = t.gmat + (size_t)(3 * at[cen] + dir) * n2c;
+                    for (int e = lane; e < NAB + NCD; e += G) {
+                        double s = 0.0;
+                        if (e < NAB) {
+                            for (int kl = 0; kl < NCD; kl++) s = fma(V[e * NCD + kl], Dcd[kl], s);
+                            atomicAdd(Gm + (size_t)(cb + e % NB) * ld + ca + e / NB, fj * s);
+                        } else {
+                            const int kl = e - NAB;
+                            for (int ij = 0; ij < NAB; ij++) s = fma(V[ij * NCD + kl], Dab[ij], s);
+                            atomicAdd(Gm + (size_t)(cdd + kl % ND) * ld + cc + kl / ND, fj * s);
+                        }
+                    }
+                    if (fk != 0.0) {
+                        constexpr int NDX = NA * NC + NA * ND + NB * NC + NB * ND;
+                        for (int e = lane; e < NDX; e += G) {
+                            double s = 0.0;
+                            if (e < NA * NC) {
+                                const int i = e / NC, k = e % NC;
+                                for (int j = 0; j < NB; j++)
+                                    for (int l = 0; l < ND; l++) s = fma(V[((i * NB + j) * NC + k) * ND + l], Dbd[j * ND + l], s);
+                                atomicAdd(Gm + (size_t)(ca + i) * ld + cc + k, fk * s);
+                            } else if (e < NA * NC + NA * ND) {
+                                const int f = e - NA * NC, i = f / ND, l = f % ND;
+                                for (int j = 0; j < NB; j++)
+                                    for (int k = 0; k < NC; k++) s = fma(V[((i * NB + j) * NC + k) * ND + l], Dbc[j * NC + k], s);
+                                atomicAdd(Gm + (size_t)(ca + i) * ld + cdd + l, fk * s);
+                            } else if (e < NA * NC + NA * ND + NB * NC) {
+                                const int f = e - NA * NC - NA * ND, j = f / NC, k = f % NC;
+                                for (int i = 0; i < NA; i++)
+                                    for (int l = 0; l < ND; l++) s = fma(V[((i * NB + j) * NC + k) * ND + l], Dad[i * ND + l], s);
+                                atomicAdd(Gm + (size_t)(cb + j) * ld + cc + k, fk * s);
+                            } else {
+                                const int f = e - NA * NC - NA * ND - NB * NC, j = f / ND, l = f % ND;
+                                for (int i = 0; i < NA; i++)
+                                    for (int k = 0; k < NC; k++) s = fma(V[((i * NB + j) * NC + k) * ND + l], Dac[i * NC + k], s);
+                                atomicAdd(Gm + (size_t)(cb + j) * ld + cdd + l, fk * s);
+                            }
+                        }
+                    }
+                }
+            __syncthreads();
+        }
     }
 }

@@ -198,3 +198,33 @@ struct GradDispatch<BRA, -1> {
 cudaError_t CF_CAT(cf_launch_grad_bra, CF_BRA)(int ket, const GradTask& t, int grid, cudaStream_t s, int* g, size_t* sm) {
     return GradDispatch<CF_BRA, CF_BRA>::go(ket, t, grid, s, g, sm);
 }
+
+// ---- matrix-form gradient kernels (Int4C2E::ContractGrads(D), eri_grad.cuh) -----------------------------------------
+template <int BRA, int KET>
+static cudaError_t launch_gradmat_pair(const GradTask& t, int grid, cudaStream_t s, int* g_out, size_t* smem_out) {
+    constexpr int LA = ClassL<BRA>::a, LB = ClassL<BRA>::b, LC = ClassL<KET>::a, LD = ClassL<KET>::b;
+    constexpr int NOUT = cf_ncart(LA) * cf_ncart(LB) * cf_ncart(LC) * cf_ncart(LD);
+    constexpr int G = group_size(NOUT) < 64 ? 64 : group_size(NOUT);
+    const size_t smem = eri_gradmat_smem<LA, LB, LC, LD>(G);
+    if (g_out) *g_out = G;
+    if (smem_out) *smem_out = smem;
+    if (grid <= 0) return cudaSuccess;
+    auto k = eri_gradmat_generic<LA, LB, LC, LD, G>;
+    if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+    k<<<grid, G, smem, s>>>(t);
+    return cudaGetLastError();
+}
+template <int BRA, int KET>
+struct GradMatDispatch {
+    static cudaError_t go(int ket, const GradTask& t, int grid, cudaStream_t s, int* g, size_t* sm) {
+        if (ket == KET) return launch_gradmat_pair<BRA, KET>(t, grid, s, g, sm);
+        return GradMatDispatch<BRA, KET - 1>::go(ket, t, grid, s, g, sm);
+    }
+};
+template <int BRA>
+struct GradMatDispatch<BRA, -1> {
+    static cudaError_t go(int, const GradTask&, int, cudaStream_t, int*, size_t*) { return cudaErrorInvalidValue; }
+};
+cudaError_t CF_CAT(cf_launch_gradmat_bra, CF_BRA)(int ket, const GradTask& t, int grid, cudaStream_t s, int* g, size_t* sm) {
+    return GradMatDispatch<CF_BRA, CF_BRA>::go(ket, t, grid, s, g, sm);
+}

@@ -92,6 +92,7 @@ def load_library(path: str = LIB_PATH):
     L.cf_finalize_device.argtypes = [vp, ip, vp, C.c_double, ip, ip, ip, vp, vp, vp, vp, vp]
     L.cf_build_g_multi.argtypes = [vp, ip, ip, dp, C.c_double, dp]
     L.cf_contract_grads.argtypes = [vp, ip, dp, dp, C.c_double, ip, dp]
+    L.cf_contract_grads_matrices.argtypes = [vp, ip, dp, C.c_double, ip, dp]
     L.cf_device_info.argtypes = [ip, C.c_char_p, ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]
     L.cf_measure_fp64_peak.argtypes = [ip, dp]
     L.cf_sync_stats.argtypes = [vp]
@@ -275,10 +276,43 @@ class Int4C2E:
         return [np.asfortranarray(out[k].T) for k in range(len(Ds))]
 
     # ---- nuclear gradient (Int4C2E.cpp:747-763) ------------------------------------------------------
-    def ContractGrads(self, D1, D2, output=0):
-        """ContractGrads(D1, D2, output) -> [3*natoms]: sum_ij D1_ij d/dR (J[2 D2] - EXX K[D2])_ij, index 3*atom + xyz.
-        (The reference's other overloads return the 3*natoms intermediate matrices; they are not formed here.)
-        With world_size > 1 this is the partition's share: sum over the ranks."""
+    def ContractGrads(self, *args):
+        """The reference's three overloads (Int4C2E.h:45-47, Int4C2E.cpp:747-790):
+          ContractGrads(D, output=0)            -> list of 3*natoms matrices G^(atom,xyz)[D] = d/dR (J[2D] - EXX K[D]); cached
+                                                   in GradCache like the reference (:769-772)
+          ContractGrads(D1, D2, output=0)       -> [3*natoms]: sum_ij D1_ij G^(.)[D2]_ij (fused on the device: the matrices
+                                                   are never formed)
+          ContractGrads([D1...], D2, output=0)  -> list of [3*natoms] vectors, one per D1 (reference: D1 o ContractGrads(D2))
+        With world_size > 1 every form returns the partition's share: sum over the ranks."""
+        if len(args) >= 1 and isinstance(args[0], (list, tuple)):
+            D1s, D2 = args[0], args[1]
+            Gs = self.ContractGrads(D2, 0)
+            n = self.nbf
+            return [np.array([float(np.sum(_fmat(D1, n) * G)) for G in Gs]) for D1 in D1s]
+        if len(args) == 1 or (len(args) == 2 and np.ndim(args[1]) == 0):
+            return self._contract_grads_matrices(args[0])
+        return self._contract_grads(args[0], args[1])
+
+    def _contract_grads_matrices(self, D):
+        self._ensure()
+        n = self.nbf
+        D = _fmat(D, n)
+        if D is None:
+            raise FockEngineError("ContractGrads(D) needs an nbf x nbf matrix")
+        if not hasattr(self, "GradCache"):
+            self.GradCache = []
+        for key, exx, value in self.GradCache:                 # the reference's isApprox lookup (Int4C2E.cpp:770)
+            if exx == self.EXX and np.allclose(key, D, rtol=1e-12, atol=0.0):
+                return value
+        natom = int(np.max(self.MWFN.shell2atom)) + 1
+        G = np.zeros((3 * natom, n * n))
+        self._check(self._lib.cf_contract_grads_matrices(self._h, n, _dptr(D), self.EXX, natom, _dptr(G)))
+        value = [np.asfortranarray(g.reshape(n, n).T) for g in G]
+        self.GradCache.append((D.copy(), self.EXX, value))
+        return value
+
+    def _contract_grads(self, D1, D2):
+        """ContractGrads(D1, D2, output) -> [3*natoms]: sum_ij D1_ij d/dR (J[2 D2] - EXX K[D2])_ij, index 3*atom + xyz."""
         self._ensure()
         n = self.nbf
         D1, D2 = _fmat(D1, n), _fmat(D2, n)

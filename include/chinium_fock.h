@@ -196,6 +196,12 @@ int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const double* D2,
 int cf_one_electron(cf_handle* h, int natom, const double* Z, const double* xyz, double* S, double* T, double* V);
 int cf_one_electron_device(cf_handle* h, int natom, const double* Z, const double* xyz, double* S, double* T, double* V, void* stream);
 
+/* Matrix form of the gradient contraction; replaces Int4C2E::ContractGrads(D, output) (Int4C2E.cpp:766-790, consumer
+ * Restricted/Hess.cpp:72): G[(3*atom + xyz) * nbf*nbf ...] = d/dR_(atom,xyz) ( J[2 D] - exx K[D] ) at fixed D, 3*natom
+ * symmetric nbf x nbf col-major matrices, HOST pointers.  (The reference keeps the result in its GradCache; the C++
+ * adaptor does the same.)  Single-device handles; with world_size > 1 the partition's share (sum over ranks). */
+int cf_contract_grads_matrices(cf_handle* h, int nbf, const double* D, double exx, int natom, double* G);
+
 /* After the caller has synchronised the stream of a *_device call: refresh ms_device_last / ms_eri_last and run the
  * fixed-point range check of that build (the *_device calls never synchronise, so CF_ERR_RANGE for a non-finite or
  * astronomically large density is reported here; cf_build_jk reports it itself). */

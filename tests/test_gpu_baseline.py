@@ -388,3 +388,26 @@ def test_device_resident_scf(Int4C2E, oracle):
         assert np.abs(D_dev.cpu().numpy() - D_cpu).max() < 1e-6
         if golden is not None:
             assert abs(E_dev - golden) < 1e-7
+
+
+@pytest.mark.parametrize("name,exx", [("h2o", 1.0), ("hf_tz", 0.7), ("bo3h3", 0.0)])
+def test_contract_grads_matrix_form(Int4C2E, oracle, name, exx):
+    """Int4C2E::ContractGrads(D, output) (Int4C2E.cpp:766-790): the 3*natoms matrices G^(atom,xyz)[D] against the oracle's
+    literal getRepulsion1 restatement (:312-408), s..f shells; consistency with the fused vector form; GradCache."""
+    mol, fb = load_fixture_molecule(name)
+    n = fb.nbf
+    D, D1 = H.random_symmetric_density(n, 31) * n, H.random_symmetric_density(n, 32) * n
+    eng = _engine(Int4C2E, fb, exx=exx)
+    Gs = eng.ContractGrads(D, 0)
+    ref = oracle.grad_matrices(fb, D, exx)
+    assert len(Gs) == len(ref) == 3 * (int(np.max(fb.shell2atom)) + 1)
+    scale = max(1.0, max(np.abs(r).max() for r in ref))
+    for G, R in zip(Gs, ref):
+        assert np.abs(G - R).max() < 1e-9 * scale
+        assert np.abs(G - G.T).max() == 0.0
+    v = eng.ContractGrads(D1, D, 0)                          # fused vector form == D1 o matrices
+    assert np.abs(v - np.array([np.sum(D1 * G) for G in Gs])).max() < 1e-9 * max(1.0, np.abs(v).max())
+    vs = eng.ContractGrads([D1, D], D, 0)
+    assert np.abs(vs[0] - v).max() < 1e-9 * max(1.0, np.abs(v).max())
+    assert eng.ContractGrads(D, 0) is Gs                     # served from GradCache
+    eng.close()
