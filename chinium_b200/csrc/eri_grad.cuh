@@ -429,11 +429,24 @@ __global__ void __launch_bounds__(G) eri_gradmat_generic(const GradTask t) {
             wgt *= (t.same_class && ib == ik) ? 1.0 : 2.0;
             const int ca = t.bra.cao_a[ib], cb = t.bra.cao_b[ib], cc = t.ket.cao_a[ik], cdd = t.ket.cao_b[ik];
 
-            double dv[NPL][9];          // contracted derivative integrals of this lane's components: (A|B|C) x (x,y,z)
+            // ---- density blocks of the quartet (bra shell as the column, like the J/K kernels) ----------------------
+            __syncthreads();
+            for (int e = lane; e < NAB; e += G) Dab[e] = D[(size_t)(cb + e % NB) * ld + ca + e / NB];
+            for (int e = lane; e < NCD; e += G) Dcd[e] = D[(size_t)(cdd + e % ND) * ld + cc + e / ND];
+            for (int e = lane; e < NA * NC; e += G) Dac[e] = D[(size_t)(ca + e / NC) * ld + cc + e % NC];
+            for (int e = lane; e < NA * ND; e += G) Dad[e] = D[(size_t)(ca + e / ND) * ld + cdd + e % ND];
+            for (int e = lane; e < NB * NC; e += G) Dbc[e] = D[(size_t)(cb + e / NC) * ld + cc + e % NC];
+            for (int e = lane; e < NB * ND; e += G) Dbd[e] = D[(size_t)(cb + e / ND) * ld + cdd + e % ND];
+            const int atA = t.shell2atom[sa], atB = t.shell2atom[sb], atC = t.shell2atom[sc], atD = t.shell2atom[sd];
+            const double fj = 0.5, fk = t.exx > 0.0 ? -0.125 * t.exx : 0.0;
+
+            // one Cartesian direction at a time (the integrals are recomputed per direction: three accumulators per
+            // component instead of nine keep the largest classes out of local memory; this path is not the SCF loop)
+            for (int dir = 0; dir < 3; dir++) {
+            double dvA[NPL], dvB[NPL], dvC[NPL];       // contracted d/dA_dir, d/dB_dir, d/dC_dir of this lane's components
 #pragma unroll
-            for (int m = 0; m < NPL; m++)
-#pragma unroll
-                for (int k = 0; k < 9; k++) dv[m][k] = 0.0;
+            for (int m = 0; m < NPL; m++) { dvA[m] = 0.0; dvB[m] = 0.0; dvC[m] = 0.0; }
+            const int d1 = dir == 0 ? 1 : 0, d2 = dir == 2 ? 1 : 2;     // the two other directions
 
             for (int iab = 0; iab < npab; iab++) {
                 const int sab = pab0 + iab * CF_PSTRIDE;
@@ -469,95 +482,82 @@ __global__ void __launch_bounds__(G) eri_gradmat_generic(const GradTask t) {
 #pragma unroll
                     for (int m = 0; m < NPL; m++) {
                         const int n = lane + m * G;
-                        if (n >= NOUT) continue;
-                        int ea[3], eb[3], ec[3], ed[3];
-                        cart_comp(LA, n / (ND * NC * NB), ea[0], ea[1], ea[2]);
-                        cart_comp(LB, (n / (ND * NC)) % NB, eb[0], eb[1], eb[2]);
-                        cart_comp(LC, (n / ND) % NC, ec[0], ec[1], ec[2]);
-                        cart_comp(LD, n % ND, ed[0], ed[1], ed[2]);
-                        int id3[3];
-#pragma unroll
-                        for (int d = 0; d < 3; d++) id3[d] = ea[d] * SA + eb[d] * SB + ec[d] * SC + ed[d];
-                        for (int r = 0; r < NR; r++) {
-                            const double* gr = g + (size_t)(3 * r) * GSZ2;
-                            double f[3], dA[3], dB[3], dC[3];
-#pragma unroll
-                            for (int d = 0; d < 3; d++) {
-                                const double* gd = gr + d * GSZ2 + id3[d];
-                                f[d] = gd[0];
-                                dA[d] = ta * gd[SA] - (ea[d] ? ea[d] * gd[-SA] : 0.0);
-                                dB[d] = tb * gd[SB] - (eb[d] ? eb[d] * gd[-SB] : 0.0);
-                                dC[d] = tc * gd[SC] - (ec[d] ? ec[d] * gd[-SC] : 0.0);
+                        if (n < NOUT) {
+                            int ea[3], eb[3], ec[3], ed[3];
+                            cart_comp(LA, n / (ND * NC * NB), ea[0], ea[1], ea[2]);
+                            cart_comp(LB, (n / (ND * NC)) % NB, eb[0], eb[1], eb[2]);
+                            cart_comp(LC, (n / ND) % NC, ec[0], ec[1], ec[2]);
+                            cart_comp(LD, n % ND, ed[0], ed[1], ed[2]);
+                            const int i0 = ea[dir] * SA + eb[dir] * SB + ec[dir] * SC + ed[dir];      // differentiated direction
+                            const int i1 = ea[d1] * SA + eb[d1] * SB + ec[d1] * SC + ed[d1];
+                            const int i2 = ea[d2] * SA + eb[d2] * SB + ec[d2] * SC + ed[d2];
+                            const int na_ = ea[dir], nb_ = eb[dir], nc_ = ec[dir];
+                            double sA = 0.0, sB = 0.0, sC = 0.0;
+                            for (int r = 0; r < NR; r++) {
+                                const double* gr = g + (size_t)(3 * r) * GSZ2;
+                                const double* gd = gr + dir * GSZ2 + i0;
+                                const double ff = gr[d1 * GSZ2 + i1] * gr[d2 * GSZ2 + i2];
+                                sA = fma(ta * gd[SA] - (na_ ? na_ * gd[-SA] : 0.0), ff, sA);
+                                sB = fma(tb * gd[SB] - (nb_ ? nb_ * gd[-SB] : 0.0), ff, sB);
+                                sC = fma(tc * gd[SC] - (nc_ ? nc_ * gd[-SC] : 0.0), ff, sC);
                             }
-                            const double fyz = f[1] * f[2], fxz = f[0] * f[2], fxy = f[0] * f[1];
-                            dv[m][0] = fma(dA[0], fyz, dv[m][0]); dv[m][1] = fma(dA[1], fxz, dv[m][1]); dv[m][2] = fma(dA[2], fxy, dv[m][2]);
-                            dv[m][3] = fma(dB[0], fyz, dv[m][3]); dv[m][4] = fma(dB[1], fxz, dv[m][4]); dv[m][5] = fma(dB[2], fxy, dv[m][5]);
-                            dv[m][6] = fma(dC[0], fyz, dv[m][6]); dv[m][7] = fma(dC[1], fxz, dv[m][7]); dv[m][8] = fma(dC[2], fxy, dv[m][8]);
+                            dvA[m] += sA; dvB[m] += sB; dvC[m] += sC;
                         }
                     }
                 }
             }
 
-            // ---- density blocks of the quartet (bra shell as the column, like the J/K kernels) ----------------------
-            __syncthreads();
-            for (int e = lane; e < NAB; e += G) Dab[e] = D[(size_t)(cb + e % NB) * ld + ca + e / NB];
-            for (int e = lane; e < NCD; e += G) Dcd[e] = D[(size_t)(cdd + e % ND) * ld + cc + e / ND];
-            for (int e = lane; e < NA * NC; e += G) Dac[e] = D[(size_t)(ca + e / NC) * ld + cc + e % NC];
-            for (int e = lane; e < NA * ND; e += G) Dad[e] = D[(size_t)(ca + e / ND) * ld + cdd + e % ND];
-            for (int e = lane; e < NB * NC; e += G) Dbc[e] = D[(size_t)(cb + e / NC) * ld + cc + e % NC];
-            for (int e = lane; e < NB * ND; e += G) Dbd[e] = D[(size_t)(cb + e / ND) * ld + cdd + e % ND];
-            const int at[4] = {t.shell2atom[sa], t.shell2atom[sb], t.shell2atom[sc], t.shell2atom[sd]};
-            const double fj = 0.5, fk = t.exx > 0.0 ? -0.125 * t.exx : 0.0;
-            // 12 derivative blocks: centres A, B, C from dv, centre D = -(A + B + C)
-            for (int cen = 0; cen < 4; cen++)
-                for (int dir = 0; dir < 3; dir++) {
-                    __syncthreads();
+            // four derivative blocks of this direction: centres A, B, C, and D = -(A + B + C)
+            for (int cen = 0; cen < 4; cen++) {
+                __syncthreads();
 #pragma unroll
-                    for (int m = 0; m < NPL; m++) {
-                        const int n = lane + m * G;
-                        if (n < NOUT) V[n] = cen < 3 ? dv[m][3 * cen + dir] : -(dv[m][dir] + dv[m][3 + dir] + dv[m][6 + dir]);
+                for (int m = 0; m < NPL; m++) {
+                    const int n = lane + m * G;
+                    if (n < NOUT) V[n] = cen == 0 ? dvA[m] : cen == 1 ? dvB[m] : cen == 2 ? dvC[m] : -(dvA[m] + dvB[m] + dvC[m]);
+                }
+                __syncthreads();
+                const int atom = cen == 0 ? atA : cen == 1 ? atB : cen == 2 ? atC : atD;
+                double* Gm = t.gmat + (size_t)(3 * atom + dir) * n2c;
+                for (int e = lane; e < NAB + NCD; e += G) {
+                    double s = 0.0;
+                    if (e < NAB) {
+                        for (int kl = 0; kl < NCD; kl++) s = fma(V[e * NCD + kl], Dcd[kl], s);
+                        atomicAdd(Gm + (size_t)(cb + e % NB) * ld + ca + e / NB, fj * s);
+                    } else {
+                        const int kl = e - NAB;
+                        for (int ij = 0; ij < NAB; ij++) s = fma(V[ij * NCD + kl], Dab[ij], s);
+                        atomicAdd(Gm + (size_t)(cdd + kl % ND) * ld + cc + kl / ND, fj * s);
                     }
-                    __syncthreads();
-                    double* Gm = t.gmat + (size_t)(3 * at[cen] + dir) * n2c;
-                    for (int e = lane; e < NAB + NCD; e += G) {
+                }
+                if (fk != 0.0) {
+                    constexpr int NDX = NA * NC + NA * ND + NB * NC + NB * ND;
+                    for (int e = lane; e < NDX; e += G) {
                         double s = 0.0;
-                        if (e < NAB) {
-                            for (int kl = 0; kl < NCD; kl++) s = fma(V[e * NCD + kl], Dcd[kl], s);
-                            atomicAdd(Gm + (size_t)(cb + e % NB) * ld + ca + e / NB, fj * s);
+                        if (e < NA * NC) {
+                            const int i = e / NC, k = e % NC;
+                            for (int j = 0; j < NB; j++)
+                                for (int l = 0; l < ND; l++) s = fma(V[((i * NB + j) * NC + k) * ND + l], Dbd[j * ND + l], s);
+                            atomicAdd(Gm + (size_t)(ca + i) * ld + cc + k, fk * s);
+                        } else if (e < NA * NC + NA * ND) {
+                            const int f = e - NA * NC, i = f / ND, l = f % ND;
+                            for (int j = 0; j < NB; j++)
+                                for (int k = 0; k < NC; k++) s = fma(V[((i * NB + j) * NC + k) * ND + l], Dbc[j * NC + k], s);
+                            atomicAdd(Gm + (size_t)(ca + i) * ld + cdd + l, fk * s);
+                        } else if (e < NA * NC + NA * ND + NB * NC) {
+                            const int f = e - NA * NC - NA * ND, j = f / NC, k = f % NC;
+                            for (int i = 0; i < NA; i++)
+                                for (int l = 0; l < ND; l++) s = fma(V[((i * NB + j) * NC + k) * ND + l], Dad[i * ND + l], s);
+                            atomicAdd(Gm + (size_t)(cb + j) * ld + cc + k, fk * s);
                         } else {
-                            const int kl = e - NAB;
-                            for (int ij = 0; ij < NAB; ij++) s = fma(V[ij * NCD + kl], Dab[ij], s);
-                            atomicAdd(Gm + (size_t)(cdd + kl % ND) * ld + cc + kl / ND, fj * s);
-                        }
-                    }
-                    if (fk != 0.0) {
-                        constexpr int NDX = NA * NC + NA * ND + NB * NC + NB * ND;
-                        for (int e = lane; e < NDX; e += G) {
-                            double s = 0.0;
-                            if (e < NA * NC) {
-                                const int i = e / NC, k = e % NC;
-                                for (int j = 0; j < NB; j++)
-                                    for (int l = 0; l < ND; l++) s = fma(V[((i * NB + j) * NC + k) * ND + l], Dbd[j * ND + l], s);
-                                atomicAdd(Gm + (size_t)(ca + i) * ld + cc + k, fk * s);
-                            } else if (e < NA * NC + NA * ND) {
-                                const int f = e - NA * NC, i = f / ND, l = f % ND;
-                                for (int j = 0; j < NB; j++)
-                                    for (int k = 0; k < NC; k++) s = fma(V[((i * NB + j) * NC + k) * ND + l], Dbc[j * NC + k], s);
-                                atomicAdd(Gm + (size_t)(ca + i) * ld + cdd + l, fk * s);
-                            } else if (e < NA * NC + NA * ND + NB * NC) {
-                                const int f = e - NA * NC - NA * ND, j = f / NC, k = f % NC;
-                                for (int i = 0; i < NA; i++)
-                                    for (int l = 0; l < ND; l++) s = fma(V[((i * NB + j) * NC + k) * ND + l], Dad[i * ND + l], s);
-                                atomicAdd(Gm + (size_t)(cb + j) * ld + cc + k, fk * s);
-                            } else {
-                                const int f = e - NA * NC - NA * ND - NB * NC, j = f / ND, l = f % ND;
-                                for (int i = 0; i < NA; i++)
-                                    for (int k = 0; k < NC; k++) s = fma(V[((i * NB + j) * NC + k) * ND + l], Dac[i * NC + k], s);
-                                atomicAdd(Gm + (size_t)(cb + j) * ld + cdd + l, fk * s);
-                            }
+                            const int f = e - NA * NC - NA * ND - NB * NC, j = f / ND, l = f % ND;
+                            for (int i = 0; i < NA; i++)
+                                for (int k = 0; k < NC; k++) s = fma(V[((i * NB + j) * NC + k) * ND + l], Dac[i * NC + k], s);
+                            atomicAdd(Gm + (size_t)(cb + j) * ld + cdd + l, fk * s);
                         }
                     }
                 }
+            }
+            }   // directions
             __syncthreads();
         }
     }
