@@ -229,6 +229,26 @@ class Int4C2E_T {
         return out;
     }
 
+    // nuclear Hessian (Int4C2E.cpp:792-811 over getRepulsion2 :410-492; consumer Restricted/Hess.cpp:67): like the reference,
+    // only D2 enters (`EigenMatrix D = D1; D = D2;`, :793); GDs[i][j], i, j = 3*atom + xyz
+    std::vector<std::vector<double>> ContractHesss(Matrix D1, Matrix D2, int output) {
+        (void)D1;
+        ensure(0);
+        const int n = cf_nbf(h_.get());
+        if (D2.rows() != n || D2.cols() != n) throw std::runtime_error("ContractHesss: matrix is not nbf x nbf");
+        auto t0 = std::chrono::steady_clock::now();
+        if (output > 0) std::printf("Contracting 4c-2e repulsion integral nuclear hessian with 1 matrix ... ");
+        int natom = 0;
+        for (int a : basis_->shell2atom) natom = a + 1 > natom ? a + 1 : natom;
+        const size_t nh = 3 * (size_t)natom;
+        std::vector<double> buf(nh * nh, 0.0);
+        check(cf_contract_hess(h_.get(), n, D2.data(), EXX, natom, buf.data()));
+        std::vector<std::vector<double>> GDs(nh, std::vector<double>(nh));
+        for (size_t i = 0; i < nh; i++) for (size_t j = 0; j < nh; j++) GDs[i][j] = buf[j * nh + i];
+        if (output > 0) std::printf("Done in %f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        return GDs;
+    }
+
     // extension for direct SCF (no counterpart in the stored-ERI reference): density-weighted screening for incremental
     // builds G[D_n - D_(n-1)]; 0 switches it off (see cf_set_density_threshold)
     void setDensityThreshold(double dthr) { ensure(0); check(cf_set_density_threshold(h_.get(), dthr)); }

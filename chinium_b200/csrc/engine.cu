@@ -60,6 +60,10 @@ typedef cudaError_t (*grad_launch_fn)(int, const GradTask&, int, cudaStream_t, i
 DECL_GRADMAT(0) DECL_GRADMAT(1) DECL_GRADMAT(2) DECL_GRADMAT(3) DECL_GRADMAT(4) DECL_GRADMAT(5) DECL_GRADMAT(6) DECL_GRADMAT(7) DECL_GRADMAT(8) DECL_GRADMAT(9)
 static grad_launch_fn g_gradmat_launch[CF_NCLS] = {cf_launch_gradmat_bra0, cf_launch_gradmat_bra1, cf_launch_gradmat_bra2, cf_launch_gradmat_bra3, cf_launch_gradmat_bra4,
                                                    cf_launch_gradmat_bra5, cf_launch_gradmat_bra6, cf_launch_gradmat_bra7, cf_launch_gradmat_bra8, cf_launch_gradmat_bra9};
+#define DECL_HESS(n) cudaError_t cf_launch_hess_bra##n(int, const GradTask&, int, cudaStream_t, int*, size_t*);
+DECL_HESS(0) DECL_HESS(1) DECL_HESS(2) DECL_HESS(3) DECL_HESS(4) DECL_HESS(5) DECL_HESS(6) DECL_HESS(7) DECL_HESS(8) DECL_HESS(9)
+static grad_launch_fn g_hess_launch[CF_NCLS] = {cf_launch_hess_bra0, cf_launch_hess_bra1, cf_launch_hess_bra2, cf_launch_hess_bra3, cf_launch_hess_bra4,
+                                                cf_launch_hess_bra5, cf_launch_hess_bra6, cf_launch_hess_bra7, cf_launch_hess_bra8, cf_launch_hess_bra9};
 static grad_launch_fn g_grad_launch[CF_NCLS] = {cf_launch_grad_bra0, cf_launch_grad_bra1, cf_launch_grad_bra2, cf_launch_grad_bra3, cf_launch_grad_bra4,
                                                 cf_launch_grad_bra5, cf_launch_grad_bra6, cf_launch_grad_bra7, cf_launch_grad_bra8, cf_launch_grad_bra9};
 static bra_launch_fn g_bra_launch[CF_NCLS] = {cf_launch_bra0, cf_launch_bra1, cf_launch_bra2, cf_launch_bra3, cf_launch_bra4,
@@ -403,7 +407,7 @@ struct cf_handle {
     std::vector<int> shell2atom;           // empty when the caller gave none (gradients then refuse)
     DevBuf<int> d_shell2atom, d_l, d_nprim_sh, d_prim_off_sh;
     DevBuf<double> d_exps, d_coefs, d_xyz, d_atomZ, d_atomxyz;
-    DevBuf<double> d_gpart, d_grad;
+    DevBuf<double> d_gpart, d_grad, d_hess;
     // per-shell transformation (function x cartesian), pooled by type
     std::vector<double> ctrans;            // pool
     std::vector<int> ct_off;               // [nshell] offset into pool
@@ -442,6 +446,7 @@ static int multi_build_jk(cf_handle* h, int nbf, const double* Dd, const double*
                           double* J, double* Kd, double* Ka, double* Kb);
 static int multi_build_g(cf_handle* h, int nbf, int nmat, const double* Ds, double exx, double* Gs);
 static int multi_contract_grads(cf_handle* h, int nbf, const double* D1, const double* D2, double exx, int natom, double* grad);
+static int multi_contract_hess(cf_handle* h, int nbf, const double* D, double exx, int natom, double* hess);
 static void multi_destroy(cf_handle* h);
 static cf_handle* multi_part0(const cf_handle* h);
 static void multi_set_density_threshold(cf_handle* h, double dthr);
@@ -983,7 +988,7 @@ extern "C" void cf_destroy(cf_handle* h) {
     for (auto& b : h->d_out) b.release();
     h->d_partial.release(); h->d_diag.release(); h->d_acc.release(); h->d_cnt.release();
     h->d_QS.release(); h->d_B.release(); h->d_Bmax.release(); h->d_rwork.release();
-    h->d_shell2atom.release(); h->d_gpart.release(); h->d_grad.release();
+    h->d_shell2atom.release(); h->d_gpart.release(); h->d_grad.release(); h->d_hess.release();
     h->d_atomZ.release(); h->d_atomxyz.release();
     h->d_l.release(); h->d_nprim_sh.release(); h->d_prim_off_sh.release(); h->d_exps.release(); h->d_coefs.release(); h->d_xyz.release();
     for (auto& e : h->ev) cudaEventDestroy(e);
@@ -1831,6 +1836,77 @@ extern "C" int cf_contract_grads(cf_handle* h, int nbf, const double* D1, const 
     return CF_OK;
 }
 
+// Int4C2E::ContractHesss(D1, D2, output) (Int4C2E.cpp:792-811) on top of getRepulsion2 (:410-492); this partition's share.
+// hess: [3*natom][3*natom] col-major (symmetric).  The second-derivative integrals are contracted with the two-particle
+// density on the fly (eri_hess.cuh); FP64 atomics into the small matrix (not the SCF loop: one call per `derivative 2` job).
+extern "C" int cf_contract_hess(cf_handle* h, int nbf, const double* D, double exx, int natom, double* hess) {
+    if (!h || !D || !hess || natom <= 0) return CF_ERR_BAD_ARGUMENT;
+    if (nbf != h->nbf) { set_error(h, "nbf does not match the basis of this handle"); return CF_ERR_BAD_ARGUMENT; }
+    if (h->multi) return multi_contract_hess(h, nbf, D, exx, natom, hess);
+    if (h->shell2atom.empty()) { set_error(h, "cf_contract_hess needs cf_basis.shell2atom"); return CF_ERR_BAD_ARGUMENT; }
+    for (int a : h->shell2atom) if (a < 0 || a >= natom) { set_error(h, "shell2atom entry outside [0, natom)"); return CF_ERR_BAD_ARGUMENT; }
+    DeviceGuard guard(h->device);
+    const int ns = h->nshell, ncart = h->ncart, nh = 3 * natom;
+    const size_t bytes = sizeof(double) * (size_t)nbf * nbf, ns2 = (size_t)ns * ns, nh2 = (size_t)nh * nh;
+    const int max_grid = 148 * 8;
+    if (h->d_shell2atom.n == 0 && h->d_shell2atom.upload(h->shell2atom) != cudaSuccess) { set_error(h, "cudaMalloc failed (shell2atom)"); return CF_ERR_CUDA; }
+    if (h->d_hess.n < nh2 && h->d_hess.alloc(nh2) != cudaSuccess) { set_error(h, "cudaMalloc failed (hessian)"); return CF_ERR_CUDA; }
+    CUDA_TRY(cudaMemcpyAsync(h->d_Dpure[0].p, D, bytes, cudaMemcpyHostToDevice, 0));
+    dim3 grid2(ns, ns);
+    pure_to_cart_kernel<<<grid2, 64>>>(ns, nbf, ncart, h->d_Dpure[0].p, nullptr, nullptr, 1.0, 0.0, 0.0, h->d_ctrans.p, h->d_ct_off.p,
+                                        h->d_bf_off.p, h->d_cao_off.p, h->d_nfun.p, h->d_ncartsh.p, h->d_Dcart[1].p, h->d_B.p, h->d_Bmax.p);
+    CUDA_TRY(cudaMemsetAsync(h->d_hess.p, 0, sizeof(double) * nh2, 0));
+    CUDA_TRY(cudaEventRecord(h->ev[1], 0));
+    int nlaunch = 1;
+    for (ClassPairTask* t : h->tasks) {
+        const PairClassHost& B = h->cls[t->bra];
+        const PairClassHost& K = h->cls[t->ket];
+        if (t->nquartet == 0) continue;
+        if (t->d_qoff.n == 0) {       // quartet offsets of the CTA-per-quartet enumeration (shared with the gradient calls)
+            const int nb = B.npair(), nk = K.npair();
+            std::vector<long long> qoff(nb + 1, 0);
+            for (int i = 0; i < nb; i++) qoff[i + 1] = qoff[i] + (t->bra == t->ket ? i + 1 : nk);
+            if (t->d_qoff.upload(qoff) != cudaSuccess) { set_error(h, "qoff upload failed"); return CF_ERR_CUDA; }
+        }
+        GradTask gt{};
+        gt.bra = B.dev(); gt.ket = K.dev();
+        gt.bra_aexp = B.d_aexp.p; gt.ket_aexp = K.d_aexp.p;
+        gt.qoff = t->d_qoff.p; gt.nquartet = t->nquartet;
+        gt.rank = h->opt.rank; gt.world = h->opt.world_size;
+        gt.same_class = (t->bra == t->ket); gt.ncart = ncart;
+        gt.D1 = h->d_Dcart[1].p; gt.D2 = h->d_Dcart[1].p; gt.exx = exx;
+        gt.shell2atom = h->d_shell2atom.p; gt.gmat = h->d_hess.p; gt.ngrad = nh;
+        gt.prim_cut = 1e-22; gt.thr = h->opt.threshold > 0 ? h->opt.threshold : 0.0;
+        fill_rys_tables(gt.rys, h);
+        long long chunk = t->nquartet / ((long long)max_grid * 4 * std::max(1, gt.world));
+        chunk = std::max(1LL, std::min(64LL, chunk));
+        gt.chunk = (int)chunk;
+        const long long nchunk_total = (t->nquartet + chunk - 1) / chunk;
+        const long long nchunk_local = (nchunk_total - gt.rank + gt.world - 1) / gt.world;
+        if (nchunk_local <= 0) continue;
+        const int grid = (int)std::min<long long>(nchunk_local, max_grid);
+        cudaError_t e = g_hess_launch[t->bra](t->ket, gt, grid, 0, nullptr, nullptr);
+        if (e != cudaSuccess) { set_error(h, std::string("hessian kernel launch failed: ") + cudaGetErrorString(e)); return CF_ERR_CUDA; }
+        nlaunch++;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[2], 0));
+    CUDA_TRY(cudaMemcpyAsync(hess, h->d_hess.p, sizeof(double) * nh2, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    CUDA_TRY(cudaGetLastError());
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->stats.ms_grad_last = ms;
+        h->stats.n_launches_last = nlaunch;
+    }
+    // exact symmetry (the two triangles saw the same terms in different atomic orders)
+    for (int x = 0; x < nh; x++)
+        for (int y = 0; y < x; y++) {
+            const double v = 0.5 * (hess[(size_t)y * nh + x] + hess[(size_t)x * nh + y]);
+            hess[(size_t)y * nh + x] = v; hess[(size_t)x * nh + y] = v;
+        }
+    return CF_OK;
+}
+
 // G_pure(block) = C_a (raw + raw^T) C_b^T for one (atom, direction) matrix of the matrix-form gradient (doubles)
 __global__ void finalize_gradmat_kernel(int nbf, int ncart, const double* __restrict__ raw, const double* __restrict__ ctrans,
                                         const int* __restrict__ ct_off, const int* __restrict__ bf_off, const int* __restrict__ cao_off,
@@ -2350,6 +2426,17 @@ static int multi_build_g(cf_handle* h, int nbf, int nmat, const double* Ds, doub
 }
 
 // every partition contracts its share of the quartets; the 3*natom partial vectors are added in device order (fixed)
+static int multi_contract_hess(cf_handle* h, int nbf, const double* D, double exx, int natom, double* hess) {
+    MultiCtx* M = h->multi;
+    const size_t nh2 = 9 * (size_t)natom * natom;
+    std::vector<std::vector<double>> part(M->ndev, std::vector<double>(nh2, 0.0));
+    int rc = M->run([&](int i) -> int { return cf_contract_hess(M->parts[i], nbf, D, exx, natom, part[i].data()); });
+    if (rc != CF_OK) return multi_fail(h, rc);
+    for (size_t j = 0; j < nh2; j++) { double s_ = 0.0; for (int i = 0; i < M->ndev; i++) s_ += part[i][j]; hess[j] = s_; }
+    multi_refresh_stats(h);
+    return CF_OK;
+}
+
 static int multi_contract_grads(cf_handle* h, int nbf, const double* D1, const double* D2, double exx, int natom, double* grad) {
     MultiCtx* M = h->multi;
     std::vector<std::vector<double>> part(M->ndev, std::vector<double>(3 * (size_t)natom, 0.0));

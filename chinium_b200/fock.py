@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 
 import numpy as np
 
@@ -93,6 +94,8 @@ def load_library(path: str = LIB_PATH):
     L.cf_build_g_multi.argtypes = [vp, ip, ip, dp, C.c_double, dp]
     L.cf_contract_grads.argtypes = [vp, ip, dp, dp, C.c_double, ip, dp]
     L.cf_contract_grads_matrices.argtypes = [vp, ip, dp, C.c_double, ip, dp]
+    if not (os.environ.get("CHINIUM_FOCK_LIB") and not hasattr(L, "cf_contract_hess")):   # A/B builds of older kernels may lack it
+        L.cf_contract_hess.argtypes = [vp, ip, dp, C.c_double, ip, dp]
     L.cf_device_info.argtypes = [ip, C.c_char_p, ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]
     L.cf_measure_fp64_peak.argtypes = [ip, dp]
     L.cf_sync_stats.argtypes = [vp]
@@ -322,6 +325,26 @@ class Int4C2E:
         g = np.zeros(3 * natom)
         self._check(self._lib.cf_contract_grads(self._h, n, _dptr(D1), _dptr(D2), self.EXX, natom, _dptr(g)))
         return g
+
+    # ---- nuclear Hessian (Int4C2E.cpp:792-811) -------------------------------------------------------
+    def ContractHesss(self, D1, D2, output=0):
+        """The reference's ContractHesss(D1, D2, output) (Int4C2E.h:48, Int4C2E.cpp:792-811 over getRepulsion2 :410-492):
+        3*natoms x 3*natoms matrix of sum over unique ERIs of d^2(ab|cd)/dX dY [2 D_ab D_cd - EXX/2 (D_ac D_bd + D_ad D_bc)].
+        Like the reference (:793: `D = D1; D = D2;`) only D2 is used.  With world_size > 1: the partition's share."""
+        self._ensure()
+        n = self.nbf
+        if output > 0:
+            print("Contracting 4c-2e repulsion integral nuclear hessian with 1 matrix ... ", end="")
+        t0 = time.perf_counter()
+        D = _fmat(D2, n)
+        if D is None:
+            raise FockEngineError("ContractHesss needs an nbf x nbf matrix")
+        natom = int(np.max(self.MWFN.shell2atom)) + 1
+        Hm = np.zeros((3 * natom, 3 * natom), order="F")
+        self._check(self._lib.cf_contract_hess(self._h, n, _dptr(D), self.EXX, natom, _dptr(Hm)))
+        if output > 0:
+            print("Done in %f s" % (time.perf_counter() - t0))
+        return Hm
 
     # ---- device-resident / multi-GPU building blocks (plain pointers: e.g. torch tensors' data_ptr()) ---
     def acc_len(self, nk):

@@ -202,6 +202,15 @@ int cf_one_electron_device(cf_handle* h, int natom, const double* Z, const doubl
  * adaptor does the same.)  Single-device handles; with world_size > 1 the partition's share (sum over ranks). */
 int cf_contract_grads_matrices(cf_handle* h, int nbf, const double* D, double exx, int natom, double* G);
 
+/* Nuclear-Hessian contraction (tail); replaces Int4C2E::ContractHesss(D1, D2, output)
+ * (Int4C2E.cpp:792-811, which uses D = D2 only, :793) on top of getRepulsion2 (:410-492): hess[(3*atomY + y) * 3*natom +
+ * 3*atomX + x] = sum over unique ERIs of d^2 (ab|cd) / dR_X,x dR_Y,y * [ 2 D_ab D_cd - exx/2 (D_ac D_bd + D_ad D_bc) ] at
+ * fixed D, the derivatives acting on all ordered pairs of the four centres (libint2's 78 buffers, :468-477, and the
+ * raw + raw^T - diag assembly of :487-491).  3*natom x 3*natom col-major, exactly symmetric, HOST pointers; consumer
+ * Restricted/Hess.cpp:67.  Needs cf_basis.shell2atom.  With world_size > 1 the partition's share (sum over ranks);
+ * multi-device handles return the total. */
+int cf_contract_hess(cf_handle* h, int nbf, const double* D, double exx, int natom, double* hess);
+
 /* After the caller has synchronised the stream of a *_device call: refresh ms_device_last / ms_eri_last and run the
  * fixed-point range check of that build (the *_device calls never synchronise, so CF_ERR_RANGE for a non-finite or
  * astronomically large density is reported here; cf_build_jk reports it itself). */

@@ -787,8 +787,8 @@ static void make_pair_shift(const cf_basis* b, int sa, int sb, int da, int db, i
     for (int i = 0; i < na; i++)
         for (int j = 0; j < nb; j++, n++) {
             double a = b->exps[b->prim_offset[sa] + i], bb = b->exps[b->prim_offset[sb] + j];
-            if (ea) pd->K[n] *= 2.0 * a;
-            if (eb) pd->K[n] *= 2.0 * bb;
+            for (int k = 0; k < ea; k++) pd->K[n] *= 2.0 * a;     /* ea, eb: powers of 2*alpha (0..2) */
+            for (int k = 0; k < eb; k++) pd->K[n] *= 2.0 * bb;
             for (int x = 0; x < 3; x++) hermite_E(la, lb, pd->p[n], pd->P[3 * n + x] - A[x], pd->P[3 * n + x] - B[x], &pd->E[3 * n + x]);
         }
 }
@@ -957,6 +957,193 @@ void ref_ContractGrads(const cf_basis* b, int natom, const double* D1, const dou
         grad[j] = s;
     }
     free(G);
+}
+
+/* ================================================================ second-derivative ERIs (tail)
+ * The reference asks libint2 for deriv_order = 2 (Int4C2E.cpp:432) and reads 78 buffers: the upper triangle of the
+ * 12 x 12 matrix d^2 (s1 s2|s3 s4) / dR_{p,t} dR_{q,s}, rows/columns ordered (centre of s1..s4) x (x,y,z), row-major with
+ * (q,s) >= (p,t) (:468-472).  Restated from first principles like the first derivatives: each application of d/dR_{p,t}
+ * to a primitive Cartesian Gaussian gives 2a * (component raised by one in t) - n_t * (component lowered by one), so a
+ * second derivative is a combination of <= 4 Cartesian blocks with angular momenta shifted by -2..+2 and primitive
+ * prefactors scaled by (2a)^0..2.  Blocks are computed on demand and cached for the quartet; the pure transformation of
+ * the ORIGINAL shells is applied at the end. */
+typedef struct { double c; int n[4][3]; int e[4]; } dterm;
+
+static int apply_deriv(const dterm* in, int nin, int pos, int dir, dterm* out) {
+    int nout = 0;
+    for (int i = 0; i < nin; i++) {
+        dterm up = in[i];
+        up.n[pos][dir] += 1; up.e[pos] += 1;
+        out[nout++] = up;
+        if (in[i].n[pos][dir] > 0) {
+            dterm dn = in[i];
+            dn.c *= -(double)in[i].n[pos][dir];
+            dn.n[pos][dir] -= 1;
+            out[nout++] = dn;
+        }
+    }
+    return nout;
+}
+
+typedef struct { int key; int l[4]; int nc[4]; double* v; } d2block;
+typedef struct { int key; pairdata pd; } d2pair;
+
+static pairdata* d2_get_pair(const cf_basis* b, d2pair* cache, int* ncache, int sa, int sb, int da, int db, int ea, int eb) {
+    int key = (((da + 2) * 5 + (db + 2)) * 3 + ea) * 3 + eb;
+    for (int i = 0; i < *ncache; i++) if (cache[i].key == key) return &cache[i].pd;
+    cache[*ncache].key = key;
+    make_pair_shift(b, sa, sb, da, db, ea, eb, &cache[*ncache].pd);
+    return &cache[(*ncache)++].pd;
+}
+
+void oracle_eri_deriv2_quartet(const cf_basis* b, int s1, int s2, int s3, int s4, double* buf78) {
+    int sh[4] = {s1, s2, s3, s4};
+    int l[4], nc[4], nf[4];
+    for (int i = 0; i < 4; i++) { l[i] = sh_l(b, sh[i]); nc[i] = NCART(l[i]); nf[i] = sh_nfun(b, sh[i]); }
+    size_t ncart = (size_t)nc[0] * nc[1] * nc[2] * nc[3], nfun = (size_t)nf[0] * nf[1] * nf[2] * nf[3];
+    d2pair bra[64], ket[64];
+    int nbra = 0, nket = 0;
+    d2block blk[128];
+    int nblk = 0;
+    double* dcart = (double*)malloc(sizeof(double) * ncart);
+    double* t1 = (double*)malloc(sizeof(double) * ncart);
+    double* t2 = (double*)malloc(sizeof(double) * ncart);
+    double C[(2 * LMAX + 1) * NCMAX];
+    int comp[4][NCMAX][3];
+    for (int i = 0; i < 4; i++) cart_components(l[i], comp[i]);
+    int ptqs = 0;
+    for (int p = 0; p < 4; p++) for (int t = 0; t < 3; t++)
+        for (int q = p; q < 4; q++) for (int s = (q == p ? t : 0); s < 3; s++, ptqs++) {
+            size_t n = 0;
+            for (int ia = 0; ia < nc[0]; ia++) for (int ib = 0; ib < nc[1]; ib++)
+                for (int ic = 0; ic < nc[2]; ic++) for (int id = 0; id < nc[3]; id++, n++) {
+                    dterm a0, a1[2], a2[4];
+                    a0.c = 1.0;
+                    int idx[4] = {ia, ib, ic, id};
+                    for (int i = 0; i < 4; i++) { a0.e[i] = 0; for (int x = 0; x < 3; x++) a0.n[i][x] = comp[i][idx[i]][x]; }
+                    int n1 = apply_deriv(&a0, 1, p, t, a1);
+                    int n2 = apply_deriv(a1, n1, q, s, a2);
+                    double v = 0.0;
+                    for (int k = 0; k < n2; k++) {
+                        int ll[4], key = 0;
+                        for (int i = 0; i < 4; i++) {
+                            ll[i] = a2[k].n[i][0] + a2[k].n[i][1] + a2[k].n[i][2];
+                            key = (key * 5 + (ll[i] - l[i] + 2)) * 3 + a2[k].e[i];
+                        }
+                        d2block* B = NULL;
+                        for (int i = 0; i < nblk; i++) if (blk[i].key == key) { B = &blk[i]; break; }
+                        if (!B) {
+                            B = &blk[nblk++];
+                            B->key = key;
+                            size_t sz = 1;
+                            for (int i = 0; i < 4; i++) { B->l[i] = ll[i]; B->nc[i] = NCART(ll[i]); sz *= B->nc[i]; }
+                            B->v = (double*)malloc(sizeof(double) * sz);
+                            pairdata* ab = d2_get_pair(b, bra, &nbra, s1, s2, ll[0] - l[0], ll[1] - l[1], a2[k].e[0], a2[k].e[1]);
+                            pairdata* cd = d2_get_pair(b, ket, &nket, s3, s4, ll[2] - l[2], ll[3] - l[3], a2[k].e[2], a2[k].e[3]);
+                            eri_cart(ab, cd, B->v);
+                        }
+                        size_t off = 0;
+                        for (int i = 0; i < 4; i++) off = off * B->nc[i] + cart_index(B->l[i], a2[k].n[i][0], a2[k].n[i][1]);
+                        v += a2[k].c * B->v[off];
+                    }
+                    dcart[n] = v;
+                }
+            int nn[4] = {nc[0], nc[1], nc[2], nc[3]};
+            memcpy(t1, dcart, sizeof(double) * ncart);
+            double* src = t1; double* dst = t2;
+            for (int i = 0; i < 4; i++) {
+                int nnew = shell_transform(b->type[sh[i]], C);
+                transform_index(src, dst, nn, i, C, nnew);
+                nn[i] = nnew;
+                double* tmp = src; src = dst; dst = tmp;
+            }
+            memcpy(buf78 + (size_t)ptqs * nfun, src, sizeof(double) * nfun);
+        }
+    for (int i = 0; i < nblk; i++) free(blk[i].v);
+    for (int i = 0; i < nbra; i++) free_pair(&bra[i].pd);
+    for (int i = 0; i < nket; i++) free_pair(&ket[i].pd);
+    free(dcart); free(t1); free(t2);
+}
+
+/* getRepulsion2 (Int4C2E.cpp:410-492) restated: the reference's quartet list (:83-93), uniqueness predicate and abcd_deg
+ * (:461-466), the 78 buffers scattered to (3*atom[p]+t, 3*atom[q]+s) with scale 2 where two DIFFERENT positions land on the
+ * same nuclear coordinate (:471-477), hessianj *= 2, raw = hessianj - 1/2 kscale hessiank, H = raw + raw^T - diag(raw)
+ * (:487-491).  H: [3*natom][3*natom] col-major (symmetric). */
+void ref_getRepulsion2(const cf_basis* b, int natom, const double* D, double kscale, double* H, int nthreads) {
+    int nbf = oracle_nbf(b), ns = b->nshell;
+    int* s2bf = (int*)malloc(sizeof(int) * ns);
+    shell2bf(b, s2bf);
+    int nh = 3 * natom;
+    size_t nh2 = (size_t)nh * nh;
+    if (nthreads < 1) nthreads = 1;
+    double* raw = (double*)calloc(2 * nh2 * nthreads, sizeof(double));   /* per thread: hessianj | hessiank */
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
+    for (int s1 = ns - 1; s1 >= 0; s1--) {
+#ifdef _OPENMP
+        int ith = omp_get_thread_num();
+#else
+        int ith = 0;
+#endif
+        double* hj = raw + (size_t)ith * 2 * nh2;
+        double* hk = hj + nh2;
+        double* buf = (double*)malloc(sizeof(double) * 78 * (size_t)(2 * LMAX + 1) * (2 * LMAX + 1) * (2 * LMAX + 1) * (2 * LMAX + 1));
+        short bf1_first = s2bf[s1], n1 = sh_nfun(b, s1);
+        for (short s2 = 0; s2 <= s1; s2++) {
+            short bf2_first = s2bf[s2], n2f = sh_nfun(b, s2);
+            for (short s3 = 0; s3 <= s1; s3++) {
+                short bf3_first = s2bf[s3], n3 = sh_nfun(b, s3);
+                for (short s4 = 0; s4 <= (s2 > s3 ? s2 : s3); s4++) {
+                    short bf4_first = s2bf[s4], n4 = sh_nfun(b, s4);
+                    size_t nfun = (size_t)n1 * n2f * n3 * n4;
+                    oracle_eri_deriv2_quartet(b, s1, s2, s3, s4, buf);
+                    const int atomlist[4] = {b->shell2atom[s1], b->shell2atom[s2], b->shell2atom[s3], b->shell2atom[s4]};
+                    int f1234 = 0;
+                    for (short f1 = 0; f1 != n1; f1++) {
+                        const short bf1 = bf1_first + f1;
+                        for (short f2 = 0; f2 != n2f; f2++) {
+                            const short bf2 = bf2_first + f2;
+                            const double ab_deg = (bf1 == bf2) ? 1 : 2;
+                            for (short f3 = 0; f3 != n3; f3++) {
+                                const short bf3 = bf3_first + f3;
+                                for (short f4 = 0; f4 != n4; f4++, f1234++) {
+                                    const short bf4 = bf4_first + f4;
+                                    if (bf2 <= bf1 && bf3 <= bf1 && bf4 <= ((bf1 == bf3) ? bf2 : bf3)) {
+                                        const double cd_deg = (bf3 == bf4) ? 1 : 2;
+                                        const double ab_cd_deg = (bf1 == bf3) ? (bf2 == bf4 ? 1 : 2) : 2;
+                                        const double abcd_deg = ab_deg * cd_deg * ab_cd_deg;
+                                        const double dj = M(D, bf1, bf2) * M(D, bf3, bf4);
+                                        const double dk = M(D, bf1, bf3) * M(D, bf2, bf4) + M(D, bf1, bf4) * M(D, bf2, bf3);
+                                        for (int p = 0, ptqs = 0; p < 4; p++) for (int t = 0; t < 3; t++) {
+                                            const int xpert = 3 * atomlist[p] + t;
+                                            for (int q = p; q < 4; q++) for (int s = (q == p ? t : 0); s < 3; s++, ptqs++) {
+                                                const int ypert = 3 * atomlist[q] + s;
+                                                const double scale = (xpert == ypert && p != q) ? 2 : 1;
+                                                const double tmp = scale * abcd_deg * buf[(size_t)ptqs * nfun + f1234];
+                                                hj[(size_t)ypert * nh + xpert] += tmp * dj;
+                                                if (kscale > 0) hk[(size_t)ypert * nh + xpert] += tmp * dk;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        free(buf);
+    }
+    for (int t = 1; t < nthreads; t++)
+        for (size_t i = 0; i < 2 * nh2; i++) raw[i] += raw[(size_t)t * 2 * nh2 + i];
+    const double* hj = raw;
+    const double* hk = raw + nh2;
+    for (int x = 0; x < nh; x++)
+        for (int y = 0; y < nh; y++) {
+            const double rxy = 2.0 * hj[(size_t)y * nh + x] - 0.5 * kscale * hk[(size_t)y * nh + x];
+            const double ryx = 2.0 * hj[(size_t)x * nh + y] - 0.5 * kscale * hk[(size_t)x * nh + y];
+            H[(size_t)y * nh + x] = (x == y) ? rxy : rxy + ryx;
+        }
+    free(raw); free(s2bf);
 }
 
 /* The whole reference path in one call (setup :49-53 of SelfConsistentField.cpp + ContractInts).

@@ -64,6 +64,9 @@ int main(int argc, char** argv) {
         const std::vector<double> grads = copy.ContractGrads(D, D, 1);     // Restricted/Grad.cpp:66
         out << grads.size() << "\n";
         for (double x : grads) out << x << "\n";
+        const std::vector<std::vector<double>> hess = copy.ContractHesss(D, D, 1);   // Restricted/Hess.cpp:67
+        out << "HESS " << hess.size() << "\n";
+        for (const auto& row : hess) for (double x : row) out << x << "\n";
         if (argc > 3) {   // the same calls through ONE process driving several GPUs (cf_create_multi): must be bit-identical
             const int nd = std::atoi(argv[3]);
             Int4C2E multi = Int4C2E::MultiDevice(fb, 1, -1, nd);

@@ -176,6 +176,25 @@ class Oracle:
                                    C.c_int(nthreads or self.nthreads))
         return g
 
+    # second-derivative path (SURVEY 8f rank 4, tail)
+    def eri_deriv2_quartet(self, fb, s1, s2, s3, s4):
+        """[78 = upper triangle of the 12 x 12 (centre, xyz) matrix, row-major][n1][n2][n3][n4]: the buffers libint2 hands the
+        reference for deriv_order 2 (Int4C2E.cpp:468-472)"""
+        b, keep = as_cf_basis(fb)
+        n = [int(fb.nfun[s]) for s in (s1, s2, s3, s4)]
+        buf = np.zeros([78] + n)
+        self.lib.oracle_eri_deriv2_quartet(C.byref(b), s1, s2, s3, s4, _dp(buf))
+        return buf
+
+    def contract_hess(self, fb, D, exx=1.0, nthreads=None):
+        """getRepulsion2 / Int4C2E::ContractHesss (Int4C2E.cpp:410-492, :792-811) -> [3*natom][3*natom]"""
+        b, keep = as_cf_basis(fb)
+        natom = int(np.max(fb.shell2atom)) + 1
+        D = _fmat(D)
+        H = np.zeros((3 * natom, 3 * natom), order="F")
+        self.lib.ref_getRepulsion2(C.byref(b), C.c_int(natom), _dp(D), C.c_double(exx), _dp(H), C.c_int(nthreads or self.nthreads))
+        return H
+
     # stored-integral handle (B1 timing)
     def store_build(self, fb, threshold=-1.0):
         b, keep = as_cf_basis(fb)

@@ -273,7 +273,8 @@ def test_cpp_adaptor_matches_oracle(Int4C2E, oracle, tmp_path):
     assert "Done in" in r.stdout and "After screening" in r.stdout
     lines = open(outp).read().split()
     assert int(lines[0]) == 45150 and int(lines[1]) == 3214        # the reference's own counts for h2o (its loop keeps 3214 of 4368 quartets)
-    v = np.array([float(x) for x in lines[2:]])
+    ih = lines.index("HESS")
+    v = np.array([float(x) for x in lines[2:ih]])
     J = v[:n * n].reshape(n, n, order="F"); K = v[n * n:2 * n * n].reshape(n, n, order="F")
     G = v[2 * n * n:3 * n * n].reshape(n, n, order="F")
     Jo, Ko, _, _, _ = oracle.direct_jk(fb, D, exx=0.5)
@@ -284,6 +285,10 @@ def test_cpp_adaptor_matches_oracle(Int4C2E, oracle, tmp_path):
     g = v[3 * n * n + 2:3 * n * n + 2 + ng]
     go = oracle.contract_grads(fb, D, D, 0.5)
     assert ng == len(go) and np.abs(g - go).max() < 1e-9 * max(1.0, np.abs(go).max())     # Restricted/Grad.cpp:66 call
+    nh = int(lines[ih + 1])                                                                  # Restricted/Hess.cpp:67 call
+    Hc = np.array([float(x) for x in lines[ih + 2:ih + 2 + nh * nh]]).reshape(nh, nh)
+    Ho = oracle.contract_hess(fb, D, 0.5)
+    assert nh == Ho.shape[0] and np.abs(Hc - Ho).max() < 1e-9 * max(1.0, np.abs(Ho).max())
 
 
 def test_h2o64_schwarz_screened_blocks(Int4C2E, oracle):
@@ -464,3 +469,45 @@ def test_sn2_recorded_forces_gpu(Int4C2E, oracle):
     assert abs(E - (-598.514802895)) < 1e-7
     assert np.abs(forces - H.SN2_FORCES_LOG).max() < 1e-5, forces
     assert np.abs(forces.sum(axis=0)).max() < 1e-7
+
+
+@pytest.mark.parametrize("name", ["h2o", "hf_tz", "bo3h3"])
+def test_contract_hess_golden(Int4C2E, name):
+    """ContractHesss (Int4C2E.cpp:792-811 over getRepulsion2 :410-492): the fused second-derivative kernels (eri_hess.cuh)
+    vs the committed outputs of the oracle's literal restatement (tests/golden/make_hess_golden.py: 78 buffers per quartet,
+    per-atom scatter, raw + raw^T - diag), s..f shells, with and without exchange."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hess_golden.npz"))
+    mol, fb = load_fixture_molecule(name)
+    n = fb.nbf
+    D = H.random_symmetric_density(n, 31) * n
+    eng = _engine(Int4C2E, fb, exx=0.6)
+    Hm = eng.ContractHesss(D, D, 0)
+    ref = g[name + "_hess"]
+    assert Hm.shape == ref.shape
+    assert np.abs(Hm - Hm.T).max() == 0.0
+    assert np.abs(Hm - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), (np.abs(Hm - ref).max(), np.abs(ref).max())
+    natom = ref.shape[0] // 3
+    assert np.abs(Hm.reshape(3 * natom, natom, 3).sum(axis=1)).max() < 1e-8 * max(1.0, np.abs(ref).max())   # translation
+    eng.EXX = 0.0                                                    # Coulomb part only (reference: kscale > 0 guard, :475)
+    Hj = eng.ContractHesss(None, D, 0)                               # D1 is ignored like in the reference (:793)
+    refj = g[name + "_hess_j"]
+    assert np.abs(Hj - refj).max() < 1e-9 * max(1.0, np.abs(refj).max())
+    eng.close()
+
+
+def test_contract_hess_oracle_and_partition(Int4C2E, oracle):
+    """Against the live oracle with a different density and EXX, and world_size = 2: the partitions' shares add up."""
+    mol, fb = load_fixture_molecule("h2o")
+    n = fb.nbf
+    D = H.random_symmetric_density(n, 77) * n
+    eng = _engine(Int4C2E, fb, exx=1.0)
+    Hm = eng.ContractHesss(D, D, 0)
+    eng.close()
+    Ho = oracle.contract_hess(fb, D, 1.0)
+    assert np.abs(Hm - Ho).max() < 1e-9 * max(1.0, np.abs(Ho).max())
+    parts = []
+    for r in range(2):
+        e = _engine(Int4C2E, fb, exx=1.0, rank=r, world_size=2)
+        parts.append(e.ContractHesss(D, D, 0))
+        e.close()
+    assert np.abs(parts[0] + parts[1] - Hm).max() < 1e-11 * max(1.0, np.abs(Hm).max())

@@ -222,6 +222,86 @@ def test_gradient_restatement_against_energy_finite_difference(oracle):
     assert np.abs(np.array([np.sum(D1 * m) for m in G]) - g).max() < 1e-12
 
 
+def _ptqs_index():
+    """(p, t, q, s) -> position in libint2's deriv_order-2 buffer list as the reference walks it (Int4C2E.cpp:468-472)"""
+    idx, n = {}, 0
+    for p in range(4):
+        for t in range(3):
+            for q in range(p, 4):
+                for s in range(t if q == p else 0, 3):
+                    idx[(p, t, q, s)] = n
+                    n += 1
+    assert n == 78
+    return idx
+
+
+def test_second_derivative_eris_finite_difference_and_translation(oracle):
+    """78 second-derivative buffers of a shell quartet (Int4C2E.cpp:432, :468-472): central differences of the FIRST
+    derivative buffers with one shell displaced, translational invariance of every row of the 12 x 12 matrix, and the
+    symmetry of mixed partials through the two orders of differentiation."""
+    mol, fb = load_fixture_molecule("h2o")
+    l = [abs(int(t)) for t in fb.type]
+    d = l.index(2)
+    p = [i for i, v in enumerate(l) if v == 1]
+    idx = _ptqs_index()
+    quartets = [(d, p[0], p[-1], 0), (p[1], 0, d, p[2]), (fb.nshell - 1, d, p[0], 1)]     # four different shells each
+    h = 1e-4
+    for qt in quartets:
+        assert len(set(qt)) == 4
+        d2 = oracle.eri_deriv2_quartet(fb, *qt)
+        full = np.zeros((12, 12) + d2.shape[1:])
+        for (pp, t, q, s), n in idx.items():
+            full[3 * pp + t, 3 * q + s] = d2[n]
+            full[3 * q + s, 3 * pp + t] = d2[n]
+        # translational invariance: sum over the four centres of d/dR_{q,s} of any first derivative vanishes
+        assert np.abs(full.reshape(12, 4, 3, -1).sum(axis=1)).max() < 1e-11
+        for q in range(4):
+            for s in range(3):
+                fp, fm = _displaced(fb, [qt[q]], s, h), _displaced(fb, [qt[q]], s, -h)
+                fd = (oracle.eri_deriv_quartet(fp, *qt) - oracle.eri_deriv_quartet(fm, *qt)) / (2 * h)   # [12][...]
+                an = full[:, 3 * q + s]
+                assert np.abs(fd - an).max() < 5e-7 * max(1.0, np.abs(an).max()), (qt, q, s)
+
+
+def test_hessian_restatement_against_gradient_finite_difference(oracle):
+    """getRepulsion2 / ContractHesss (Int4C2E.cpp:410-492, :792-811): H = d/dR of ContractGrads(D, D) at fixed density
+    (both are derivatives of sum D o (J[2D] - EXX K[D])), symmetric, rows sum to zero over the atoms."""
+    mol, fb = load_fixture_molecule("h2o")
+    n = fb.nbf
+    D = H.random_symmetric_density(n, 21) * n
+    exx = 0.6
+    Hs = oracle.contract_hess(fb, D, exx)
+    natom = int(np.max(fb.shell2atom)) + 1
+    assert Hs.shape == (3 * natom, 3 * natom)
+    assert np.abs(Hs - Hs.T).max() < 1e-11
+    assert np.abs(Hs.reshape(3 * natom, natom, 3).sum(axis=1)).max() < 1e-9           # translation of the whole molecule
+    s2a = np.asarray(fb.shell2atom)
+    h = 1e-4
+    for atom, x in ((0, 1), (1, 0), (2, 2)):
+        shells = [s for s in range(fb.nshell) if s2a[s] == atom]
+        gp = oracle.contract_grads(_displaced(fb, shells, x, h), D, D, exx)
+        gm = oracle.contract_grads(_displaced(fb, shells, x, -h), D, D, exx)
+        fd = (gp - gm) / (2 * h)
+        assert np.abs(fd - Hs[3 * atom + x]).max() < 5e-7 * max(1.0, np.abs(fd).max()), (atom, x)
+    # Coulomb-only form (EXX <= 0: the reference skips hessiank, :475)
+    Hj = oracle.contract_hess(fb, D, 0.0)
+    gp = oracle.contract_grads(_displaced(fb, [s for s in range(fb.nshell) if s2a[s] == 0], 2, h), D, D, 0.0)
+    gm = oracle.contract_grads(_displaced(fb, [s for s in range(fb.nshell) if s2a[s] == 0], 2, -h), D, D, 0.0)
+    assert np.abs((gp - gm) / (2 * h) - Hj[2]).max() < 5e-7 * max(1.0, np.abs(Hj[2]).max())
+
+
+def test_hessian_golden_fixture_reproducible(oracle):
+    """tests/golden/hess_golden.npz (generator: tests/golden/make_hess_golden.py): the h2o entries recomputed here."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hess_golden.npz"))
+    mol, fb = load_fixture_molecule("h2o")
+    D = H.random_symmetric_density(fb.nbf, 31) * fb.nbf
+    assert np.abs(oracle.contract_hess(fb, D, 0.6) - g["h2o_hess"]).max() < 1e-10
+    assert np.abs(oracle.contract_hess(fb, D, 0.0) - g["h2o_hess_j"]).max() < 1e-10
+    for name in ("hf_tz", "bo3h3"):
+        assert g[name + "_hess"].shape[0] == 3 * (int(np.max(load_fixture_molecule(name)[1].shell2atom)) + 1)
+
+
 def test_sn2_recorded_forces(oracle):
     """External pin of the gradient row: the forces Chinium itself recorded for CH3ClF- (tools/sn2/sn2.cnm.log:211-216),
     reproduced with the oracle's ContractGrads restatement inside the reference's gradient assembly (Restricted/Grad.cpp:
