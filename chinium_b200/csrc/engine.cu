@@ -71,6 +71,15 @@ static bra_launch_fn g_bra_launch[CF_NCLS] = {cf_launch_bra0, cf_launch_bra1, cf
 
 static std::string g_last_error;
 
+// primitive-quartet cutoff of the J/K kernels: |c_ab c_cd wgt| below it is skipped.  Developer knob CF_PRIM_CUT for the
+// accuracy/time scan of tools/prim_cut_scan.py (read once); the default is what every parity test runs with.
+#define CF_PRIM_CUT_DEFAULT 1e-22
+static double cf_prim_cut() {
+    static double v = -1.0;
+    if (v < 0.0) { const char* e = getenv("CF_PRIM_CUT"); v = e ? atof(e) : CF_PRIM_CUT_DEFAULT; if (!(v >= 0.0)) v = CF_PRIM_CUT_DEFAULT; }
+    return v;
+}
+
 // Device buffer.  Setup allocates a few hundred arrays (per class, per task): they come from the device's stream-ordered
 // memory pool (cudaMallocAsync on the default stream; the pool keeps freed blocks, so repeated handles cost microseconds
 // per allocation instead of a cudaMalloc each).  `pooled = false` (plain cudaMalloc) is used for the accumulators that
@@ -1553,7 +1562,7 @@ extern "C" int cf_accumulate_device(cf_handle* h, int nbf, const double* Dd, con
         qt.nj = 1; qt.Dj[0] = qt.Dtot; qt.accJm[0] = qt.accJ;
         qt.jlo_off = (long long)((size_t)(1 + nk) * n2c);
         qt.scales = tail; qt.cnt = h->d_cnt.p + (size_t)t->index * CF_CNT_WORDS;
-        qt.store = nullptr; qt.diag = 0; qt.prim_cut = 1e-22;
+        qt.store = nullptr; qt.diag = 0; qt.prim_cut = cf_prim_cut();
         fill_rys(qt, h);
         cudaStream_t ts = (it % 4 == 0) ? s : h->side[it % 4 - 1];
         it++;
@@ -1727,7 +1736,7 @@ extern "C" int cf_profile_tasks(cf_handle* h, int nbf, const double* Dd_dev, con
         qt.rank = h->opt.rank; qt.world = h->opt.world_size; qt.ncart = h->ncart; qt.nk = nk;
         qt.Dtot = h->d_Dcart[0].p;
         for (int x = 0; x < nk; x++) { qt.Dk[x] = h->d_Dcart[1 + x].p; qt.accK[x] = h->d_acc.p + (size_t)(1 + x) * n2c; }
-        qt.accJ = h->d_acc.p; qt.scales = reinterpret_cast<const double*>(h->d_acc.p + (size_t)(2 + nk) * n2c); qt.prim_cut = 1e-22;
+        qt.accJ = h->d_acc.p; qt.scales = reinterpret_cast<const double*>(h->d_acc.p + (size_t)(2 + nk) * n2c); qt.prim_cut = cf_prim_cut();
         qt.nj = 1; qt.Dj[0] = qt.Dtot; qt.accJm[0] = qt.accJ; qt.jlo_off = (long long)((size_t)(1 + nk) * n2c);
         qt.cnt = h->d_cnt.p + (size_t)t->index * CF_CNT_WORDS;
         fill_rys(qt, h);
@@ -2052,7 +2061,7 @@ static int build_g_accumulate(cf_handle* h, int nmat, double exx, cudaStream_t s
         qt.Dtot = qt.Dj[0]; qt.accJ = qt.accJm[0];
         qt.jlo_off = (long long)(6 * n2c);
         qt.scales = tail; qt.cnt = h->d_cnt.p + (size_t)t->index * CF_CNT_WORDS;
-        qt.store = nullptr; qt.diag = 0; qt.prim_cut = 1e-22;
+        qt.store = nullptr; qt.diag = 0; qt.prim_cut = cf_prim_cut();
         fill_rys(qt, h);
         cudaStream_t ts = (it % 4 == 0) ? s : h->side[it % 4 - 1];
         it++;

@@ -22,8 +22,8 @@ CFG = {42: (3, 0, 1, 2), 44: (3, 0, 1, 2), 52: (1, 0, 1, 2), 53: (1, 0, 1, 2), 5
        64: (3, 1, 1, 2), 65: (1, 1, 1, 3), 72: (1, 0, 1, 3), 73: (1, 0, 1, 3), 74: (2, 0, 1, 2), 75: (2, 1, 1, 2),
        76: (2, 0, 1, 2), 77: (2, 0, 1, 2), 81: (1, 0, 1, 2), 82: (1, 0, 1, 2), 83: (1, 0, 1, 2), 84: (4, 1, 1, 2),
        85: (2, 1, 1, 2), 86: (1, 0, 1, 2), 87: (1, 0, 1, 2), 88: (2, 0, 2, 2), 91: (1, 0, 2, 2), 92: (1, 0, 2, 2),
-       93: (1, 0, 2, 2), 94: (4, 1, 1, 2), 95: (4, 1, 2, 2), 96: (1, 0, 2, 2), 97: (4, 1, 2, 2), 98: (2, 0, 5, 2),
-       99: (4, 0, 10, 2), 71: (1, 0, 1, 2), 51: (1, 0, 1, 2), 66: (1, 0, 1, 2), 43: (2, 0, 1, 2)}
+       93: (1, 0, 2, 2), 94: (4, 1, 1, 2), 95: (4, 1, 2, 2), 96: (1, 0, 2, 2), 97: (1, 0, 2, 2), 98: (2, 0, 5, 2),
+       99: (4, 0, 10, 2), 71: (1, 0, 1, 3), 51: (1, 0, 1, 2), 66: (1, 0, 1, 4), 43: (3, 0, 1, 2)}
 
 
 # alternatives measured as variant 1 (wg_cfg_alt1): the model's pick where it differs from the base configuration
