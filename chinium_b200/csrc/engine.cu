@@ -73,7 +73,10 @@ static std::string g_last_error;
 
 // primitive-quartet cutoff of the J/K kernels: |c_ab c_cd wgt| below it is skipped.  Developer knob CF_PRIM_CUT for the
 // accuracy/time scan of tools/prim_cut_scan.py (read once); the default is what every parity test runs with.
-#define CF_PRIM_CUT_DEFAULT 1e-22
+// 1e-18 from the scan of session r2l (profiles/r2l_primcut.txt; densities with O(1) entries, |J|max 110 - 620): against 1e-22
+// max|dJ| 5.1e-13 / max|dK| 1.7e-13 on c18, 2.4e-14 / 3.3e-14 on fe4s4, 1.4e-14 / 1.7e-13 on (H2O)64 -- 200x below the 1e-10 bar --
+// for 17 % / 10 % / 2 % fewer primitive quartets (c18 -7.5 %, fe4s4 -4 %); 1e-16 would leave only a factor 3 (2.9e-11).
+#define CF_PRIM_CUT_DEFAULT 1e-18
 static double cf_prim_cut() {
     static double v = -1.0;
     if (v < 0.0) { const char* e = getenv("CF_PRIM_CUT"); v = e ? atof(e) : CF_PRIM_CUT_DEFAULT; if (!(v >= 0.0)) v = CF_PRIM_CUT_DEFAULT; }

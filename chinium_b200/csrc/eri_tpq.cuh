@@ -39,8 +39,21 @@ __host__ __device__ constexpr bool tpq_ok(int la, int lb, int lc, int ld) {
 #else
 #define BOYS1_COLS 10
 #endif
+// Strides of the STAGED (shared-memory) copies.  Lanes read the same (value, coefficient) position of DIFFERENT rows (their own
+// T), so the row / interval stride decides the bank behaviour of every LDS.128: the global layout has 4 chunks of 16 bytes per
+// Boys row (2-root classes) and 14 * NROOTS chunks per Chebyshev interval -- an EVEN number, so lanes in different intervals
+// reach only 4, 2 or (NROOTS = 4, 8) ONE of the 8 bank groups (ncu r2l, c18 dp|ps: table reads = 96 % of the shared wavefronts
+// at 2.7x the ideal count).  The staged copy pads every Boys row to 5 chunks and every interval by one chunk: odd strides,
+// all 8 bank groups.  -DCF_TABLE_NOPAD restores the dense copy for A/B runs.
+#ifdef CF_TABLE_NOPAD
+#define BOYS2_STR 8
+__host__ __device__ constexpr int rys_istr(int nroots) { return 2 * nroots * RYS_NC; }
+#else
+#define BOYS2_STR 10
+__host__ __device__ constexpr int rys_istr(int nroots) { return 2 * nroots * RYS_NC + 2; }
+#endif
 __host__ __device__ constexpr int tpq_table_len(int nroots) {
-    return nroots == 1 ? BOYS_NROW * BOYS1_COLS : nroots == 2 ? BOYS_NROW * 8 : (rys_tmax(nroots) / 2) * 2 * nroots * RYS_NC + 2 * nroots;
+    return nroots == 1 ? BOYS_NROW * BOYS1_COLS : nroots == 2 ? BOYS_NROW * BOYS2_STR : (rys_tmax(nroots) / 2) * rys_istr(nroots) + 2 * nroots;
 }
 #define TPQ_WBP 32        // bra primitive pairs staged per pass and per warp by the thread-per-quartet kernel
 __host__ __device__ constexpr size_t tpq_smem(int nroots) {
@@ -69,7 +82,7 @@ template <int M>
 __device__ __forceinline__ void boys_small(const double* __restrict__ tab, double T, double* __restrict__ F) {
     const int i = (int)fma(T, 8.0, 0.5);
     const double mh = fma((double)i, 0.125, -T);   // -(T - T_i), |mh| <= 1/16
-    const double2* row = reinterpret_cast<const double2*>(tab + i * 8);
+    const double2* row = reinterpret_cast<const double2*>(tab + i * BOYS2_STR);
     const double2 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3];
     double s = r3.y;
     s = fma(s, mh * (1.0 / 7.0), r3.x);
@@ -118,12 +131,12 @@ __device__ __forceinline__ void tpq_stage_tables(double* __restrict__ tab, const
         for (int e = tid; e < BOYS_NROW * 10; e += nt) tab[e] = rys.boys[(e / 10) * BOYS_NCOL + (e % 10)];
     } else if constexpr (NROOTS <= 2) {
         constexpr int M = 2 * NROOTS - 1;
-        for (int e = tid; e < BOYS_NROW * 8; e += nt) tab[e] = rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
+        for (int e = tid; e < BOYS_NROW * 8; e += nt) tab[(e >> 3) * BOYS2_STR + (e & 7)] = rys.boys[(e >> 3) * BOYS_NCOL + M + (e & 7)];
     } else {
-        constexpr int NTAB = (rys_tmax(NROOTS) / 2) * 2 * NROOTS * RYS_NC;
+        constexpr int PER = 2 * NROOTS * RYS_NC, NTAB = (rys_tmax(NROOTS) / 2) * PER;
         const double* src = rys.table + rys_off(NROOTS);
-        for (int e = tid; e < NTAB; e += nt) tab[e] = src[e];
-        if (tid < 2 * NROOTS) tab[NTAB + tid] = rys.asym[rys_asym_off(NROOTS) + tid];
+        for (int e = tid; e < NTAB; e += nt) tab[(e / PER) * rys_istr(NROOTS) + e % PER] = src[e];
+        if (tid < 2 * NROOTS) tab[(rys_tmax(NROOTS) / 2) * rys_istr(NROOTS) + tid] = rys.asym[rys_asym_off(NROOTS) + tid];
     }
 }
 
@@ -163,14 +176,14 @@ __device__ __forceinline__ void tpq_roots(const double* __restrict__ tab, double
     } else {
         constexpr int NV = 2 * NROOTS;
         if (T >= (double)rys_tmax(NROOTS)) {
-            const double* asym = tab + (rys_tmax(NROOTS) / 2) * NV * RYS_NC;
+            const double* asym = tab + (rys_tmax(NROOTS) / 2) * rys_istr(NROOTS);
             const double rs = rsqrt(T), it = rs * rs;
 #pragma unroll
             for (int v = 0; v < NROOTS; v++) { x[v] = asym[v] * it; w[v] = asym[NROOTS + v] * rs; }
         } else {
             const int it = (int)(T * 0.5);
             const double u = T - (2.0 * it + 1.0), u2 = u + u;
-            const double2* cs = reinterpret_cast<const double2*>(tab + (size_t)it * NV * RYS_NC);
+            const double2* cs = reinterpret_cast<const double2*>(tab + (size_t)it * rys_istr(NROOTS));
 #pragma unroll
             for (int v = 0; v < NV; v++) {
                 double2 c[RYS_NC / 2];
@@ -196,6 +209,42 @@ __device__ __forceinline__ double warp_sum_fixed(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Sums of N per-lane values over the 32 lanes by RECURSIVE HALVING: at distance 16, 8, 4, 2, 1 a lane keeps one half of
+// its values and adds the partner's copy of that half, so N values cost ~N double shuffles instead of 5 N (ncu r2l: the 18
+// warp_sum_fixed calls of J(a,b) were 24 % of the samples of the c18 dp|ps kernel).  The summation tree of every element
+// is the butterfly of warp_sum_fixed (own + partner at each distance; addition commutes): results are bit-identical to it.
+// On return the lane holds out[i] = total of element `first + i` for i < count (count may be 0).
+#ifndef CF_NO_WARP_MULTI_SUM
+#define CF_WARP_MULTI_SUM 1
+#endif
+__host__ __device__ constexpr int wms_half(int n) { return (n + 1) / 2; }
+__host__ __device__ constexpr int wms_len(int n) { return wms_half(wms_half(wms_half(wms_half(wms_half(n))))); }
+template <int N, int O>
+__device__ __forceinline__ void wms_step(const double (&v)[N], double (&w)[(N + 1) / 2], int lane, int& first, int& count) {
+    constexpr int H = (N + 1) / 2;
+    const bool up = (lane & O) != 0;
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+        const double lo = v[i];
+        const double hi = (i + H < N) ? v[i + H] : 0.0;
+        const double keep = up ? hi : lo, send = up ? lo : hi;
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+    }
+    if (up) { first += H; count -= H; }
+    count = max(0, min(count, H));
+}
+template <int N>
+__device__ __forceinline__ void warp_multi_sum(const double (&v)[N], double (&out)[wms_len(N)], int lane, int& first, int& count) {
+    constexpr int N1 = wms_half(N), N2 = wms_half(N1), N3 = wms_half(N2), N4 = wms_half(N3);
+    double a1[N1], a2[N2], a3[N3], a4[N4];
+    first = 0; count = N;
+    wms_step<N, 16>(v, a1, lane, first, count);
+    wms_step<N1, 8>(a1, a2, lane, first, count);
+    wms_step<N2, 4>(a2, a3, lane, first, count);
+    wms_step<N3, 2>(a3, a4, lane, first, count);
+    wms_step<N4, 1>(a4, out, lane, first, count);
 }
 
 #ifndef TPQ_MINB
@@ -355,6 +404,9 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
             double dcd[NCD], jcd[NCD];
 #pragma unroll
             for (int kl = 0; kl < NCD; kl++) { dcd[kl] = active ? DJ[(cd0 + kl % ND) * ld + cc0 + kl / ND] : 0.0; jcd[kl] = 0.0; }
+#ifdef CF_WARP_MULTI_SUM
+            double sab[NAB];
+#endif
 #pragma unroll
             for (int ij = 0; ij < NAB; ij++) {
                 const size_t off = (cb + ij % NB) * ld + ca + ij / NB;
@@ -366,9 +418,26 @@ __global__ void __launch_bounds__(TPQ_THREADS, tpq_minb(cf_ncart(LA) * cf_ncart(
                     jcd[kl] = fma(gout[ij * NCD + kl], dab, jcd[kl]);
                 }
                 // the bra pair is common to the warp's 32 quartets: one add per element and warp instead of 32
+#ifdef CF_WARP_MULTI_SUM
+                sab[ij] = s;
+#else
                 s = warp_sum_fixed(s);
                 if (lane == 0) fixed_add_j(aJ + off, jlo, s, scaleJ);
+#endif
             }
+#ifdef CF_WARP_MULTI_SUM
+            {   // all NAB warp sums at once; the lanes that end up holding totals add them (one atomic instruction per slot)
+                double tot[wms_len(NAB)];
+                int first, count;
+                warp_multi_sum<NAB>(sab, tot, lane, first, count);
+#pragma unroll
+                for (int i = 0; i < wms_len(NAB); i++)
+                    if (i < count) {
+                        const int ij = first + i;
+                        fixed_add_j(aJ + (size_t)(cb + ij % NB) * ld + ca + ij / NB, jlo, tot[i], scaleJ);
+                    }
+            }
+#endif
             if (active) {
 #pragma unroll
                 for (int kl = 0; kl < NCD; kl++) fixed_add_j(aJ + (cd0 + kl % ND) * ld + cc0 + kl / ND, jlo, jcd[kl], scaleJ);
@@ -707,6 +776,9 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
             double dcd[NCD], jcd[NCD];
 #pragma unroll
             for (int kl = 0; kl < NCD; kl++) { dcd[kl] = active ? DJ[(cd0 + kl % ND) * ld + cc0 + kl / ND] : 0.0; jcd[kl] = 0.0; }
+#ifdef CF_WARP_MULTI_SUM
+            double sab[MA * NB];
+#endif
 #pragma unroll
             for (int m = 0; m < MA; m++)
 #pragma unroll
@@ -720,9 +792,26 @@ __global__ void __launch_bounds__(GS * tpqs_nq(GS), TPQS_MINB(GS * tpqs_nq(GS)))
                         jcd[kl] = fma(gout[(m * NB + j) * NCD + kl], dab, jcd[kl]);
                     }
                     // the bra pair and the slice are warp-uniform: one add per element and warp
+#ifdef CF_WARP_MULTI_SUM
+                    sab[m * NB + j] = sum;
+#else
                     sum = warp_sum_fixed(sum);
                     if ((threadIdx.x & 31) == 0) fixed_add_j(aJ + off, jlo, sum, scaleJ);
+#endif
                 }
+#ifdef CF_WARP_MULTI_SUM
+            {
+                double tot[wms_len(MA * NB)];
+                int first, count;
+                warp_multi_sum<MA * NB>(sab, tot, threadIdx.x & 31, first, count);
+#pragma unroll
+                for (int i = 0; i < wms_len(MA * NB); i++)
+                    if (i < count) {
+                        const int e = first + i;
+                        fixed_add_j(aJ + (size_t)(cb + e % NB) * ld + ca + ia0 + e / NB, jlo, tot[i], scaleJ);
+                    }
+            }
+#endif
             reduce_add(std::integral_constant<int, NCD>{}, jcd,
                        [&](int kl) { return (size_t)(cd0 + kl % ND) * ld + cc0 + kl / ND; }, aJ, scaleJ, jlo);
         }

@@ -268,6 +268,9 @@ eri_jk_tpqa(const QuartetTask t) {
                 if (xj >= t.nj) break;
                 const double* __restrict__ DJ = t.Dj[xj];
                 long long* aJ = t.accJm[xj];
+#ifdef CF_WARP_MULTI_SUM
+                double sab[NAB];
+#endif
 #pragma unroll
                 for (int ij = 0; ij < NAB; ij++) {
                     const size_t off = (cb + ij % NB) * ld + ca + ij / NB;
@@ -278,9 +281,26 @@ eri_jk_tpqa(const QuartetTask t) {
                         s = fma(gout[ij * NCD + kl], dcd[xj * NCD + kl], s);
                         jcd[xj * NCD + kl] = fma(gout[ij * NCD + kl], dab, jcd[xj * NCD + kl]);
                     }
+#ifdef CF_WARP_MULTI_SUM
+                    sab[ij] = s;
+#else
                     s = warp_sum_fixed(s);
                     if (lane == 0) fixed_add_j(aJ + off, jlo, s, scaleJ);
+#endif
                 }
+#ifdef CF_WARP_MULTI_SUM
+                {   // all NAB warp sums by recursive halving (eri_tpq.cuh); the lanes holding totals add them
+                    double tot[wms_len(NAB)];
+                    int first, count;
+                    warp_multi_sum<NAB>(sab, tot, lane, first, count);
+#pragma unroll
+                    for (int i = 0; i < wms_len(NAB); i++)
+                        if (i < count) {
+                            const int ij = first + i;
+                            fixed_add_j(aJ + (size_t)(cb + ij % NB) * ld + ca + ij / NB, jlo, tot[i], scaleJ);
+                        }
+                }
+#endif
             }
             if (!act) continue;
 #pragma unroll

@@ -15,3 +15,6 @@ for w in c18 fe4s4 h2o64; do
   run pfk libchinium_fock_pfk.so $w
 done
 timeout 1500 python tools/prim_cut_scan.py --workloads c18 fe4s4 h2o64 --cuts 1e-22 1e-20 1e-18 1e-16 1e-14 --out gpurun_out/${TAG}_primcut.json 2>&1 | tee gpurun_out/${TAG}_primcut.txt
+# one `ncu --set full` capture of the heaviest warp-group kernel (dp|ds, MK 3) and the heaviest thread-per-quartet kernel (dp|ps) of a c18 build
+bash tools/ncu_capture.sh ${TAG}_c18_top c18 "eri_jk_wgILi2ELi1ELi2ELi0ELi3E|eri_jk_tpqILi2ELi1ELi1ELi0E" 2
+timeout 600 python tools/time_hess.py h2o bo3h3 fe4s4 c18 > gpurun_out/${TAG}_hess_timing.jsonl 2> gpurun_out/${TAG}_hess_timing.err; echo "hess timing rc=$?"; cat gpurun_out/${TAG}_hess_timing.jsonl
