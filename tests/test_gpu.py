@@ -511,3 +511,36 @@ def test_contract_hess_oracle_and_partition(Int4C2E, oracle):
         parts.append(e.ContractHesss(D, D, 0))
         e.close()
     assert np.abs(parts[0] + parts[1] - Hm).max() < 1e-11 * max(1.0, np.abs(Hm).max())
+
+
+def test_primitive_cutoff_margin(tmp_path):
+    """The J/K kernels skip primitive quartets with |c_ab c_cd wgt| < 1e-18 (engine.cu, CF_PRIM_CUT_DEFAULT; scan in
+    profiles/r2l_primcut.txt).  Against a build with the cutoff switched off (developer knob CF_PRIM_CUT=0, fresh process: the
+    knob is read once) an O(1) all-positive density -- skipped positive integrals add up coherently -- must agree to 1e-11,
+    a tenth of the parity bar, on a molecule with s..f shells and on bo3h3."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, os
+        sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+        import numpy as np
+        from chinium_b200 import Int4C2E
+        from chinium_b200.inputs import load_fixture_molecule
+        import scf_harness as H
+        for name in ("hf_tz", "bo3h3"):
+            mol, fb = load_fixture_molecule(name)
+            D = np.abs(H.random_symmetric_density(fb.nbf, 5) * fb.nbf)
+            eng = Int4C2E(fb, 1.0, -1.0)
+            J, K, _, _ = eng.ContractInts(D, None, None, 1, 0)
+            np.save(os.path.join(%r, name + "_" + os.environ.get("TAGX", "x") + ".npy"), np.stack([J, K]))
+            eng.close()
+    """ % (ROOT, ROOT, str(tmp_path)))
+    for tag, extra in (("default", {}), ("nocut", {"CF_PRIM_CUT": "0"})):
+        env = {k: v for k, v in os.environ.items() if k != "CF_PRIM_CUT"}
+        env.update(TAGX=tag, **extra)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+    for name in ("hf_tz", "bo3h3"):
+        a, b = np.load(tmp_path / (name + "_default.npy")), np.load(tmp_path / (name + "_nocut.npy"))
+        assert np.abs(b).max() > 1.0                                   # O(1) and larger elements
+        assert np.abs(a - b).max() < 1e-11, (name, np.abs(a - b).max())
+
