@@ -402,19 +402,19 @@ def main():
     # N = 1: cf_build_jk, the C entry point the C++ adaptor's ContractInts calls (H2D, all kernels, D2H inside the call);
     # N > 1: the same through the per-rank partition + NCCL int64 all-reduce (chinium_b200/distributed.py)
     n = fb.nbf
+    pin = lambda: torch.empty((n, n), dtype=torch.float64).pin_memory()
+    hin = [pin() if p else None for p in present]
+    for k, D in enumerate((Dd, Da, Db)):
+        if D is not None:
+            hin[k].numpy()[...] = D
+    hout = [pin() for _ in range(4)]
+    fview = lambda t: None if t is None else t.numpy().T        # F-ordered view of the pinned block (matrices are symmetric)
+    args_in = [fview(t) for t in hin]
+    outs = [fview(t) for t in hout]
     if world == 1:
-        pin = lambda: torch.empty((n, n), dtype=torch.float64).pin_memory()
-        hin = [pin() if p else None for p in present]
-        for k, D in enumerate((Dd, Da, Db)):
-            if D is not None:
-                hin[k].numpy()[...] = D
-        hout = [pin() for _ in range(4)]
-        fview = lambda t: None if t is None else t.numpy().T        # F-ordered view of the pinned block (matrices are symmetric)
-        args_in = [fview(t) for t in hin]
-        outs = [fview(t) for t in hout]
         call = lambda: eng.eng._contract(args_in[0], args_in[1], args_in[2], out=outs)
     else:
-        call = lambda: eng.ContractInts(Dd, Da, Db, 1, 0)
+        call = lambda: eng.ContractInts(args_in[0], args_in[1], args_in[2], 1, 0, out=outs)
     for _ in range(2):
         call()
     barrier()
@@ -456,7 +456,7 @@ def main():
             "fock_build_ms": ms_per_step,
             "e2e": {"value": total_q / e2e_s, "unit": "quartets/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": n2 * sum(present), "d2h_bytes_per_step": n2 * (1 + nk),
-                    "call": "cf_build_jk (C ABI host call, pinned host buffers)" if world == 1 else "DistributedInt4C2E.ContractInts"},
+                    "call": "cf_build_jk (C ABI host call, pinned host buffers)" if world == 1 else "DistributedInt4C2E.ContractInts (pinned host buffers in and out)"},
             "gpu_launches": launches,
             "clocks": clocks,
             # `frac` / `achieved`: model flops of the work the kernels really EXECUTED (device counters of primitive quartets

@@ -55,8 +55,11 @@ class DistributedInt4C2E:
         self.eng.finalize_device(acc.data_ptr(), present, self._out[0].data_ptr(), ptr(self._out[1], present[0]),
                                  ptr(self._out[2], present[1]), ptr(self._out[3], present[2]), stream)
 
-    def ContractInts(self, Dd=None, Da=None, Db=None, nthreads=1, output=0):
-        """Host matrices in, host matrices out (the reference's call); H2D / D2H through pinned buffers.
+    def ContractInts(self, Dd=None, Da=None, Db=None, nthreads=1, output=0, out=None):
+        """Host matrices in, host matrices out (the reference's call).  `out`: optional (J, Kd, Ka, Kb) of caller-owned
+        F-ordered float64 nbf x nbf arrays to write into (entries for absent densities may be None) -- with page-locked
+        arrays on both sides (e.g. views of torch pinned tensors) the copies are plain DMA transfers and nothing is
+        allocated per call; without `out` fresh arrays are returned like the reference returns by value.
         No transposes: the engine symmetrises D on the device ((D + D^T)/2, the reference's precondition) and J/K come
         back exactly symmetric, so the row-major torch view and the column-major reference layout hold the same bytes."""
         n = self.nbf
@@ -69,17 +72,27 @@ class DistributedInt4C2E:
         # cost 2 ms per call on c18 and ~40 ms on (H2O)64 (60 MB matrices) -- VERDICT round 1, weak #6.
         for k, D in enumerate((Dd, Da, Db)):
             if present[k]:
-                src = np.ascontiguousarray(np.asarray(D, dtype=np.float64).reshape(n, n))
+                A = np.asarray(D, dtype=np.float64).reshape(n, n)
+                # no host copy for either layout: the engine symmetrises D on the device, so the C-contiguous transpose VIEW of
+                # an F-ordered matrix holds the same matrix
+                src = A if A.flags["C_CONTIGUOUS"] else (A.T if A.flags["F_CONTIGUOUS"] else np.ascontiguousarray(A))
                 self._D[k].copy_(torch.from_numpy(src))
         self.build_device(present)
         res = []
         for k in range(4):
             if k == 0 or present[k - 1]:
-                out = np.empty((n, n), dtype=np.float64)
-                torch.from_numpy(out).copy_(self._out[k])          # blocking device -> host copy on the current stream
-                res.append(out.T)                                   # F-contiguous view; the matrix is exactly symmetric
+                if out is not None and out[k] is not None:
+                    dst = out[k]
+                    if dst.shape != (n, n) or dst.dtype != np.float64 or not dst.flags["F_CONTIGUOUS"]:
+                        raise FockEngineError("out matrices must be F-ordered float64 nbf x nbf")
+                    torch.from_numpy(dst.T).copy_(self._out[k])     # dst.T is the C-contiguous view of the same memory
+                    res.append(dst)
+                else:
+                    buf = np.empty((n, n), dtype=np.float64)
+                    torch.from_numpy(buf).copy_(self._out[k])       # blocking device -> host copy on the current stream
+                    res.append(buf.T)                               # F-contiguous view; the matrix is exactly symmetric
             else:
-                res.append(np.zeros((n, n), order="F"))
+                res.append(np.zeros((n, n), order="F") if out is None or out[k] is None else out[k])
         torch.cuda.current_stream(self.device).synchronize()
         self.eng.sync_stats()            # timings + the deferred range check (raises on non-finite densities)
         return tuple(res)

@@ -17,7 +17,9 @@
  *     tools/sn2/sn2.cnm.log:204 (reproduced by tests/test_oracle.py through this oracle to
  *     < 1e-7 Eh), plus first-principles checks (Boys vs mpmath, permutational symmetry,
  *     diag(S)=1, brute-force einsum); for the derivative path the forces recorded in the same
- *     log (:211-216), reproduced to < 7e-6 Eh/bohr (tests/test_oracle.py::test_sn2_recorded_forces).
+ *     log (:211-216), reproduced to < 7e-6 Eh/bohr (tests/test_oracle.py::test_sn2_recorded_forces); the 12 first- and 78
+ *     second-derivative buffers agree to 1e-12 with analytic derivatives assembled from 40-digit Obara-Saika integrals
+ *     (tests/test_oracle.py::test_derivative_buffers_against_obara_saika).
  *     The device kernels use a DIFFERENT algorithm (Rys
  *     quadrature), so oracle == device agreement is a two-route check.
  */

@@ -10,3 +10,4 @@ for w in c18 h2o64; do
   echo "n=2 $w rc=$?"; tail -c 600 gpurun_out/${TAG}_n2_$w.json | head -c 300; echo
 done
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --steps 2 --warmup 1 --impl reference > gpurun_out/${TAG}_n2_reference.json 2> gpurun_out/${TAG}_n2_reference.err; echo "reference arm rc=$?"; head -c 300 gpurun_out/${TAG}_n2_reference.json; echo
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29535 tests/dist_grad_check.py bo3h3 > gpurun_out/${TAG}_dist_check.log 2>&1; echo "dist check rc=$?"; tail -3 gpurun_out/${TAG}_dist_check.log
