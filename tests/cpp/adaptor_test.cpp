@@ -76,8 +76,12 @@ int main(int argc, char** argv) {
             auto [J2, Kd2, Ka2, Kb2] = multi.ContractInts(D, Mat(0, 0), Mat(0, 0), 4, 1);
             auto Gs2 = multi.ContractInts(Ds, 4, 1);
             const std::vector<double> grads2 = multi.ContractGrads(D, D, 0);
+            const std::vector<std::vector<double>> hess2 = multi.ContractHesss(D, D, 0);
             bool same = J2.v == J.v && Kd2.v == Kd.v && Gs2[1].v == Gs[1].v && multi.RepulsionLength == int4c2e.RepulsionLength;
             double dg = 0; for (size_t i = 0; i < grads.size(); i++) dg = std::max(dg, std::fabs(grads[i] - grads2[i]));
+            double hmax = 1.0;
+            for (size_t i = 0; i < hess.size(); i++) for (size_t j = 0; j < hess.size(); j++) hmax = std::max(hmax, std::fabs(hess[i][j]));
+            for (size_t i = 0; i < hess.size(); i++) for (size_t j = 0; j < hess.size(); j++) dg = std::max(dg, std::fabs(hess[i][j] - hess2[i][j]) / hmax);
             std::printf("multi-device handle: %d GPUs, J/K/G bit-identical to one GPU: %s, max|dgrad| %.3e\n", multi.NumDevices(), same ? "yes" : "NO", dg);
             out << "MULTI " << multi.NumDevices() << " " << (same ? 1 : 0) << " " << dg << "\n";
         }
