@@ -23,6 +23,17 @@
 #include "eri_generic.cuh"
 #include "eri_tpq.cuh"
 
+// developer experiment (session r2u): L1 prefetch hints for the three places where the (H2O)64 profile shows long-scoreboard
+// stalls -- bit 0: the chunk's bra records at item start, bit 1: the item's ket primitive rows at item start, bit 2: the
+// bra-dependent density lines of the digestion at the top of a bra-pair iteration.  0 = off (the default build).
+#ifndef CF_TPQA_PF
+#define CF_TPQA_PF 0
+#endif
+#ifndef CF_HAVE_PREFETCH_L1
+#define CF_HAVE_PREFETCH_L1
+__device__ __forceinline__ void cf_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
+
 #ifndef TPQA_ACCK_MAX
 #define TPQA_ACCK_MAX 44      // K(a,c)/K(a,d) register accumulators: at most this many doubles per thread
 #endif
@@ -102,6 +113,24 @@ eri_jk_tpqa(const QuartetTask t) {
         }
         const double qrun = thr > 0.0 ? warp_max(Qk) : 0.0;
         const double wcd = (sc == sd) ? 1.0 : 2.0;
+#if CF_TPQA_PF & 1
+        {   // the chunk's records are read one after the other by the bra loop: their lines, up front
+            const char* pi = reinterpret_cast<const char*>(t.brec_i + i0);
+            const char* pd = reinterpret_cast<const char*>(t.brec_d + 4 * (size_t)i0);
+            if (lane * 128 < nbra * 16) cf_prefetch_l1(pi + lane * 128);
+            if (lane * 128 < nbra * 32) cf_prefetch_l1(pd + lane * 128);
+        }
+#endif
+#if CF_TPQA_PF & 2
+        if (lane_ok && (lane & 15) == 0) {   // ket primitive rows of the block (32 pairs interleaved: 256 bytes per array and primitive)
+            const int np = min(npcd, 6);
+            for (int icd = 0; icd < np; icd++) {
+                const int scd = pcd0 + icd * CF_PSTRIDE;
+                cf_prefetch_l1(t.ket.p + scd); cf_prefetch_l1(t.ket.hp + scd); cf_prefetch_l1(t.ket.c + scd);
+                cf_prefetch_l1(t.ket.Px + scd); cf_prefetch_l1(t.ket.Py + scd); cf_prefetch_l1(t.ket.Pz + scd);
+            }
+        }
+#endif
 
         // ---- shell a: common to the chunk --------------------------------------------------------------------
         // Bra pairs come from the bra-role copy of the class (records + CONTIGUOUS primitives in `border` order), so the
@@ -203,6 +232,18 @@ eri_jk_tpqa(const QuartetTask t) {
             cnt_q += act ? 1u : 0u;
 
             const int sb = ri0.y & 0xffff, cb = ri0.z;
+#if CF_TPQA_PF & 4
+            if (act) {   // density lines of this bra pair's digestion: rows of shell b
+#pragma unroll
+                for (int j = 0; j < NB; j++) {
+                    for (int x = 0; x < t.nk; x++) {
+                        cf_prefetch_l1(t.Dk[x] + (size_t)(cb + j) * ld + cd0);
+                        cf_prefetch_l1(t.Dk[x] + (size_t)(cb + j) * ld + cc0);
+                    }
+                    if (lane == 0) cf_prefetch_l1(t.Dj[0] + (size_t)(cb + j) * ld + ca);
+                }
+            }
+#endif
             const double ABx = rq0.y, ABy = rz0.x, ABz = rz0.y;
             const int pab0 = ri0.w, npab = ri0.y >> 16;
             const double wgt = (sa == sb ? 1.0 : 2.0) * wcd * ((same && ib == ik) ? 1.0 : 2.0);
