@@ -131,3 +131,38 @@ def test_cpp_adaptor_compiles_and_fails_loudly_without_gpu(tmp_path, have_gpu):
     out = subprocess.run([exe, str(inp), str(tmp_path / "out.txt")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 3, (out.returncode, out.stderr)
     assert "no CPU fallback" in out.stderr or "no CUDA device" in out.stderr
+
+
+def test_wg_strides_table_matches_bank_model():
+    """chinium_b200/csrc/wg_strides_data.h is generated by tools/wg_bank_model.py --emit: every warp-group configuration of
+    eri_wg.cuh (wg_cfg_base) must be known to the tool with the same (MK, swap, HS, MINB), and the header must hold the
+    strides the model picks for it, within the kernel's size / alignment constraints."""
+    import re, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import importlib
+    wbm = importlib.import_module("wg_bank_model")
+    src = open(os.path.join(root, "chinium_b200", "csrc", "eri_wg.cuh")).read()
+    body = src[src.index("constexpr int wg_cfg_base(int key)"):src.index("constexpr int wg_cfg_alt1(int key)")]
+    WGC = lambda mk, sw, hs, minb: mk | (sw << 8) | (hs << 12) | (minb << 16)
+    cfg = {}
+    for m in re.finditer(r"case (\d+): return ([^;]+);", body):
+        v = eval(m.group(2), {"WGC": WGC})
+        cfg[int(m.group(1))] = (v & 255, (v >> 8) & 1, ((v >> 12) & 15) or 1, ((v >> 16) & 15) or 2)
+    assert len(cfg) >= 30
+    for key, c in cfg.items():
+        assert wbm.CFG[key] == c, (key, c, wbm.CFG[key])
+    hdr = {}
+    for line in open(os.path.join(root, "chinium_b200", "csrc", "wg_strides_data.h")):
+        m = re.match(r"\s+case (\d+): return (\d+)LL \| \((\d+)LL << 8\) \| \((\d+)LL << 20\);", line)
+        if m:
+            hdr[int(m.group(1))] = tuple(int(x) for x in m.groups()[1:])
+    for key in cfg:
+        shp, cur, cb, best = wbm.search(key)
+        la, lb, lc, ld, mk, hs, minb = shp
+        k = ((((la * 4 + lb) * 4 + lc) * 4 + ld) * 8 + mk) * 16 + hs
+        assert k in hdr, (key, shp)
+        labp, tsz, scr = hdr[k]
+        assert (labp, tsz, scr) == (best[2], best[3], best[1]), (key, hdr[k], best)
+        assert wbm.constraints(la, lb, lc, ld, mk, hs, labp, tsz, scr)
+
